@@ -1,0 +1,180 @@
+// Exact-fp32 convolution as a flat shifted GEMM on CUDA cores (DVC_MATH_FP32).
+//
+// This is the first correct CUDA path and stays as the on-GPU fp32 reference that the tcgen05
+// (3xTF32) engine is validated against.  Replaces nn.Conv2d + bias + ReLU/LeakyReLU (+ skip add,
+// + InstanceNorm statistics) at NonlocalNet.py:235-255,364-423 and ColorVidNet.py:96-143.
+//
+// Tile: 128 padded pixels x BN output channels x 8 input channels per step, 256 threads, 8 x (BN/16)
+// accumulators per thread, register-prefetch double buffering (one __syncthreads per k-step).
+#include "dvc_internal.cuh"
+
+namespace dvc {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 8;
+
+template <int BN>
+__global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const ConvParams p) {
+  constexpr int TN = BN / 16;
+  constexpr int BV = BN / 4;  // float4 per weight k-row
+  __shared__ __align__(16) float smem[2 * BK * BM + 2 * BK * BN];
+  float(*As)[BK][BM] = reinterpret_cast<float(*)[BK][BM]>(smem);
+  float(*Bs)[BK][BN] = reinterpret_cast<float(*)[BK][BN]>(smem + 2 * BK * BM);
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int npix = p.Hp * p.Wp;
+  const float* __restrict__ xb = p.x + (size_t)b * npix * p.Cin;
+
+  const int a_row = tid >> 1, a_k4 = (tid & 1) * 4;
+  const int b_k = tid / BV, b_n4 = (tid % BV) * 4;
+  const bool b_active = tid < BK * BV;
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int kcs = p.Cin / BK;
+  const int nk = p.taps * kcs;
+  float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto gload = [&](int it) {
+    const int tap = it / kcs;
+    const int k0 = (it - tap * kcs) * BK;
+    int off = 0;
+    if (p.taps == 9) off = ((tap / 3 - 1) * p.Wp + (tap % 3 - 1)) * p.dil;
+    const int r = m0 + a_row + off;
+    if (r >= 0 && r < npix)
+      ra = __ldg(reinterpret_cast<const float4*>(xb + (size_t)r * p.Cin + k0 + a_k4));
+    else
+      ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b_active)
+      rb = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)(tap * p.Cin + k0 + b_k) * p.CoutPad + n0 + b_n4));
+  };
+  auto sstore = [&](int buf) {
+    As[buf][a_k4 + 0][a_row] = ra.x;
+    As[buf][a_k4 + 1][a_row] = ra.y;
+    As[buf][a_k4 + 2][a_row] = ra.z;
+    As[buf][a_k4 + 3][a_row] = ra.w;
+    if (b_active) *reinterpret_cast<float4*>(&Bs[buf][b_k][b_n4]) = rb;
+  };
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int it = 0; it < nk; ++it) {
+    const int cur = it & 1;
+    if (it + 1 < nk) gload(it + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bb[TN];
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+        bb[0] = b0.x, bb[1] = b0.y, bb[2] = b0.z, bb[3] = b0.w;
+        if constexpr (TN == 8) {
+          const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][64 + tx * 4]);
+          bb[4] = b1.x, bb[5] = b1.y, bb[6] = b1.z, bb[7] = b1.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    if (it + 1 < nk) sstore(cur ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue: bias, skip add, activation, masked store, InstanceNorm statistics ----
+  float ssum[TN], ssq[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) ssum[j] = 0.f, ssq[j] = 0.f;
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4));
+    const int pp = m0 + rl;
+    if (pp >= npix) continue;
+    const int yp = pp / p.Wp, xp = pp - yp * p.Wp;
+    const int y = yp - p.P, x = xp - p.P;
+    if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;
+    if (p.stride == 2 && ((y | x) & 1)) continue;
+    const int yo = y / p.stride, xo = x / p.stride;
+#pragma unroll
+    for (int g = 0; g < TN / 4; ++g) {
+      const int c = n0 + (g == 0 ? tx * 4 : 64 + tx * 4);
+      if (c >= p.Cout) continue;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = acc[i][g * 4 + j];
+      if (p.bias) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+        v[0] += bv.x, v[1] += bv.y, v[2] += bv.z, v[3] += bv.w;
+      }
+      if (p.add) {
+        const float4 av = __ldg(reinterpret_cast<const float4*>(
+            p.add + (((size_t)b * p.aHp + yo + p.aP) * p.aWp + xo + p.aP) * p.aC + c));
+        v[0] += av.x, v[1] += av.y, v[2] += av.z, v[3] += av.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+        if (p.act == ACT_LRELU) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+        ssum[g * 4 + j] += v[j];
+        ssq[g * 4 + j] += v[j] * v[j];
+      }
+      if (p.y)
+        *reinterpret_cast<float4*>(p.y + (((size_t)b * p.yHp + yo + p.yP) * p.yWp + xo + p.yP) * p.yC + p.yCoff + c) =
+            make_float4(v[0], v[1], v[2], v[3]);
+      if (p.nchw) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p.nchw[(((size_t)b * p.Cout + c + j) * p.Ho + yo) * p.Wo + xo] = v[j];
+      }
+    }
+  }
+
+  if (p.stats) {  // block-level reduction over the 16 row groups, then one double atomic per column
+    float* red = smem;  // [2][16][BN]
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int cl = (j < 4) ? (tx * 4 + j) : (64 + tx * 4 + (j - 4));
+      red[ty * BN + cl] = ssum[j];
+      red[16 * BN + ty * BN + cl] = ssq[j];
+    }
+    __syncthreads();
+    if (tid < BN) {
+      const int c = n0 + tid;
+      if (c < p.Cout) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) s += red[t * BN + tid], q += red[16 * BN + t * BN + tid];
+        atomicAdd(&p.stats[((size_t)b * p.Cout + c) * 2 + 0], (double)s);
+        atomicAdd(&p.stats[((size_t)b * p.Cout + c) * 2 + 1], (double)q);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+void launch_conv_simt(const ConvParams& p, int B, cudaStream_t s) {
+  const int npix = p.Hp * p.Wp;
+  if (p.CoutPad % 128 == 0) {
+    dim3 grid((npix + BM - 1) / BM, p.CoutPad / 128, B);
+    conv_gemm_simt_kernel<128><<<grid, 256, 0, s>>>(p);
+  } else {
+    dim3 grid((npix + BM - 1) / BM, p.CoutPad / 64, B);
+    conv_gemm_simt_kernel<64><<<grid, 256, 0, s>>>(p);
+  }
+  launch_counter_add(1);
+}
+
+}  // namespace dvc

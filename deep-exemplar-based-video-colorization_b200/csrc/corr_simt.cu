@@ -1,0 +1,225 @@
+// K7 on CUDA cores (DVC_MATH_FP32): fused  f = theta_hat^T phi_hat  ->  row max (similarity)  ->
+// softmax_j(f / T)  ->  y = P V,  never materialising the N x N matrix.
+// Replaces NonlocalNet.py:477-498 (torch.matmul, torch.max, F.softmax, torch.matmul).
+//
+// One CTA owns 128 query rows: its theta tile [C x 128] stays resident in shared memory for the
+// whole sweep over the reference positions; phi streams through a double-buffered [8 x 128] tile.
+// Each thread keeps an 8 x 8 block of scores in registers and folds it straight into per-row
+// running statistics:
+//   ARGMAX mode (T <= 2e-10, test.py:94): running (max, argmax); the softmax is exactly one-hot in
+//       fp32 there because distinct fp32 scores differ by > 104 T, so exp() underflows to 0.
+//   SOFTMAX mode: flash-style online softmax (running max, running sum, 3 weighted colour sums).
+#include <math.h>
+
+#include "dvc_internal.cuh"
+
+namespace dvc {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 8;
+
+template <bool SOFTMAX>
+__global__ void __launch_bounds__(256) corr_simt_kernel(const CorrParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                        // [C][BM]
+  float* Bs = smem + (size_t)p.C * BM;     // [2][BK][BN]
+  float4* Vs = reinterpret_cast<float4*>(Bs + 2 * BK * BN);  // [BN]
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int b = blockIdx.y;
+  const int bphi = (p.Bphi == 1) ? 0 : b;
+  const int m0 = blockIdx.x * BM;
+  const float* __restrict__ th = p.theta + (size_t)b * p.NA * p.C;
+  const float* __restrict__ ph = p.phi + (size_t)bphi * p.NB * p.C;
+  const float4* __restrict__ Vg = reinterpret_cast<const float4*>(p.V) + (size_t)bphi * p.NB;
+
+  const int l_row = tid >> 1, l_k4 = (tid & 1) * 4;
+
+  // resident theta tile, transposed to [k][row]
+  for (int k0 = 0; k0 < p.C; k0 += BK) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + l_row < p.NA) v = __ldg(reinterpret_cast<const float4*>(th + (size_t)(m0 + l_row) * p.C + k0 + l_k4));
+    As[(k0 + l_k4 + 0) * BM + l_row] = v.x;
+    As[(k0 + l_k4 + 1) * BM + l_row] = v.y;
+    As[(k0 + l_k4 + 2) * BM + l_row] = v.z;
+    As[(k0 + l_k4 + 3) * BM + l_row] = v.w;
+  }
+
+  float run_m[8], run_s[8], run_a[8][3];
+  int run_i[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    run_m[i] = -INFINITY, run_s[i] = 0.f, run_i[i] = 0;
+    run_a[i][0] = run_a[i][1] = run_a[i][2] = 0.f;
+  }
+  const float sc = 1.4426950408889634f / p.temperature;  // log2(e) / T
+
+  const int kcs = p.C / BK;
+  const int ntiles = (p.NB + BN - 1) / BN;
+  const int nsteps = ntiles * kcs;
+  float4 rb;
+  auto gload = [&](int step) {
+    const int jt = step / kcs, k0 = (step - jt * kcs) * BK;
+    const int r = jt * BN + l_row;
+    rb = (r < p.NB) ? __ldg(reinterpret_cast<const float4*>(ph + (size_t)r * p.C + k0 + l_k4))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto sstore = [&](int buf) {
+    float* d = Bs + buf * BK * BN;
+    d[(l_k4 + 0) * BN + l_row] = rb.x;
+    d[(l_k4 + 1) * BN + l_row] = rb.y;
+    d[(l_k4 + 2) * BN + l_row] = rb.z;
+    d[(l_k4 + 3) * BN + l_row] = rb.w;
+  };
+
+  float acc[8][8];
+  gload(0);
+  sstore(0);
+  if (SOFTMAX && tid < BN) Vs[tid] = (tid < p.NB) ? __ldg(Vg + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+
+  for (int step = 0; step < nsteps; ++step) {
+    const int cur = step & 1;
+    const int jt = step / kcs, kc = step - jt * kcs;
+    if (kc == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    }
+    if (step + 1 < nsteps) gload(step + 1);
+    const float* Ab = As + (size_t)kc * BK * BM;
+    const float* Bb = Bs + cur * BK * BN;
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(Ab + k * BM + ty * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(Ab + k * BM + 64 + ty * 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(Bb + k * BN + tx * 4);
+      const float4 b1 = *reinterpret_cast<const float4*>(Bb + k * BN + 64 + tx * 4);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    if (kc == kcs - 1) {
+      // ---- fold this 128 x 128 score tile into the running row statistics ----
+      const int cbase = jt * BN;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!SOFTMAX) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = cbase + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (col < p.NB && acc[i][j] > run_m[i]) run_m[i] = acc[i][j], run_i[i] = col;
+          }
+        } else {
+          float tm = run_m[i];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = cbase + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (col < p.NB) tm = fmaxf(tm, acc[i][j]);
+          }
+          if (tm > -INFINITY) {
+            const float r = (run_m[i] == -INFINITY) ? 0.f : exp2f((run_m[i] - tm) * sc);
+            run_s[i] *= r, run_a[i][0] *= r, run_a[i][1] *= r, run_a[i][2] *= r;
+            run_m[i] = tm;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int cl = (j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4);
+              if (cbase + cl < p.NB) {
+                const float e = exp2f((acc[i][j] - tm) * sc);
+                const float4 v = Vs[cl];
+                run_s[i] += e;
+                run_a[i][0] = fmaf(e, v.x, run_a[i][0]);
+                run_a[i][1] = fmaf(e, v.y, run_a[i][1]);
+                run_a[i][2] = fmaf(e, v.z, run_a[i][2]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (step + 1 < nsteps) sstore(cur ^ 1);
+    __syncthreads();
+    if (SOFTMAX && kc == kcs - 1 && jt + 1 < ntiles) {
+      // colours of the next column tile (all threads passed the barrier above, so Vs is free)
+      if (tid < BN) {
+        const int r = (jt + 1) * BN + tid;
+        Vs[tid] = (r < p.NB) ? __ldg(Vg + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- merge the 16 column groups of every row (As is free now) ----
+  float* red = smem;  // [128 rows][16 groups][5]
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4));
+    float* r = red + ((size_t)rl * 16 + tx) * 5;
+    r[0] = run_m[i];
+    if (!SOFTMAX) {
+      r[1] = __int_as_float(run_i[i]);
+    } else {
+      r[1] = run_s[i], r[2] = run_a[i][0], r[3] = run_a[i][1], r[4] = run_a[i][2];
+    }
+  }
+  __syncthreads();
+  if (tid < BM && m0 + tid < p.NA) {
+    const float* r = red + (size_t)tid * 16 * 5;
+    const size_t o = (size_t)b * p.NA + m0 + tid;
+    if (!SOFTMAX) {
+      float m = r[0];
+      int idx = __float_as_int(r[1]);
+      for (int g = 1; g < 16; ++g) {
+        const float mg = r[g * 5];
+        const int ig = __float_as_int(r[g * 5 + 1]);
+        if (mg > m || (mg == m && ig < idx)) m = mg, idx = ig;
+      }
+      const float4 v = __ldg(Vg + idx);
+      reinterpret_cast<float4*>(p.y)[o] = make_float4(v.x, v.y, v.z, 0.f);
+      p.sim[o] = m;
+      if (p.argmax) p.argmax[o] = idx;
+    } else {
+      float m = -INFINITY;
+      for (int g = 0; g < 16; ++g) m = fmaxf(m, r[g * 5]);
+      float s = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      int idx = 0;
+      float best = -INFINITY;
+      for (int g = 0; g < 16; ++g) {
+        const float mg = r[g * 5];
+        if (mg == -INFINITY) continue;
+        const float w = exp2f((mg - m) * sc);
+        s += w * r[g * 5 + 1], a0 += w * r[g * 5 + 2], a1 += w * r[g * 5 + 3], a2 += w * r[g * 5 + 4];
+        if (mg > best) best = mg, idx = g;
+      }
+      (void)idx;
+      reinterpret_cast<float4*>(p.y)[o] = make_float4(a0 / s, a1 / s, a2 / s, 0.f);
+      p.sim[o] = m;
+      if (p.argmax) p.argmax[o] = -1;  // not defined for a true softmax
+    }
+  }
+}
+
+}  // namespace
+
+void launch_corr_simt(const CorrParams& p, cudaStream_t s) {
+  const size_t smem = ((size_t)p.C * BM + 2 * BK * BN) * sizeof(float) + BN * sizeof(float4);
+  dim3 grid((p.NA + BM - 1) / BM, p.B);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(corr_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(corr_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  if (p.temperature <= 2e-10f)
+    corr_simt_kernel<false><<<grid, 256, smem, s>>>(p);
+  else
+    corr_simt_kernel<true><<<grid, 256, smem, s>>>(p);
+  launch_counter_add(1);
+}
+
+}  // namespace dvc

@@ -1,0 +1,971 @@
+// libdvc.so host side: context, weight packing, the three layer programs (VGG19 trunk, WarpNet,
+// ColorVidNet) expressed over the kernels of this directory, and the C ABI of include/dvc.h.
+//
+// Reference interfaces replaced (file:line in the reference tree):
+//   VGG19_pytorch.forward   models/NonlocalNet.py:228-256
+//   WarpNet.forward         models/NonlocalNet.py:427-502
+//   ColorVidNet.forward     models/ColorVidNet.py:96-144
+//   frame_colorization      models/FrameColor.py:41-67, per-clip loop test.py:57-96
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/dvc.h"
+#include "corr_tc.cuh"
+#include "dvc_internal.cuh"
+
+namespace dvc {
+
+static std::atomic<int64_t> g_launches{0};
+int64_t launch_counter_add(int64_t n) { return g_launches.fetch_add(n) + n; }
+
+struct ConvW {
+  float* w = nullptr;  // [taps][cin_pad][cout_pad]
+  float* b = nullptr;  // [cout_pad]
+  int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, k = 0;
+};
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int sig[5] = {0, 0, 0, 0, 0};
+};
+
+}  // namespace dvc
+
+using namespace dvc;
+
+struct dvc_ctx {
+  int device = 0;
+  std::string err;
+  std::unordered_map<std::string, ConvW> conv[3];
+  std::unordered_map<std::string, float> slope[3];
+  std::unordered_map<std::string, float*> vec[3];
+  std::unordered_map<std::string, std::vector<float>> host_bias[3];  // bias seen before its weight
+  int conv_math = DVC_MATH_FP32, corr_math = DVC_MATH_FP32;
+  std::map<std::string, Buf> bufs;
+  // InstanceNorm statistics arena (doubles), bump-allocated per forward call
+  double* stats = nullptr;
+  size_t stats_cap = 0, stats_used = 0;
+  // exemplar cache
+  float* ex_phi = nullptr;  // [N][256]
+  float* ex_V = nullptr;    // [N][4]
+  int ex_H = 0, ex_W = 0, ex_N = 0;
+  bool ex_valid = false;
+  // module-level WarpNet B-side cache
+  bool warp_cache_valid = false;
+  int warp_cache_sig[3] = {0, 0, 0};
+  // correlation profiling
+  bool prof_corr = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> corr_events;
+};
+
+static std::string g_create_err;
+
+#define CUDA_TRY(ctx, expr)                                                                          \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess) {                                                                         \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                              \
+      return DVC_ERR_CUDA;                                                                            \
+    }                                                                                                 \
+  } while (0)
+
+#define DVC_TRY(expr)          \
+  do {                         \
+    int r__ = (expr);          \
+    if (r__ != DVC_OK) return r__; \
+  } while (0)
+
+static int fail(dvc_ctx* c, int code, const std::string& msg) {
+  c->err = msg;
+  return code;
+}
+
+// ------------------------------------------------------------------------------------------------
+// buffers
+// ------------------------------------------------------------------------------------------------
+static int get_buf(dvc_ctx* c, const std::string& name, size_t bytes, void** out, const int sig[5], bool zero_on_change,
+                   cudaStream_t s) {
+  Buf& b = c->bufs[name];
+  bool changed = false;
+  if (b.bytes < bytes) {
+    if (b.p) CUDA_TRY(c, cudaFree(b.p));
+    b.p = nullptr;
+    CUDA_TRY(c, cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    changed = true;
+  }
+  for (int i = 0; i < 5; ++i)
+    if (b.sig[i] != sig[i]) changed = true, b.sig[i] = sig[i];
+  if (changed && zero_on_change) CUDA_TRY(c, cudaMemsetAsync(b.p, 0, b.bytes, s));
+  *out = b.p;
+  return DVC_OK;
+}
+
+// padded NHWC activation; the zero border is established once per (name, shape) and never written by
+// the convolution epilogues, the gather kernels rewrite their own borders every call.
+static int get_act(dvc_ctx* c, const std::string& name, int B, int H, int W, int C, int P, Act* a, cudaStream_t s) {
+  a->B = B, a->H = H, a->W = W, a->C = C, a->P = P;
+  const int sig[5] = {B, H, W, C, P};
+  void* p = nullptr;
+  DVC_TRY(get_buf(c, name, a->elems() * sizeof(float), &p, sig, true, s));
+  a->d = (float*)p;
+  return DVC_OK;
+}
+
+static int get_raw(dvc_ctx* c, const std::string& name, size_t bytes, void** out, cudaStream_t s) {
+  const int sig[5] = {(int)(bytes & 0x7fffffff), 0, 0, 0, 0};
+  return get_buf(c, name, bytes, out, sig, false, s);
+}
+
+static int stats_begin(dvc_ctx* c, cudaStream_t s) {
+  const size_t need = 1 << 20;  // doubles (8 MB): far above the ~60 K used per forward at B <= 8
+  if (c->stats_cap < need) {
+    if (c->stats) CUDA_TRY(c, cudaFree(c->stats));
+    CUDA_TRY(c, cudaMalloc((void**)&c->stats, need * sizeof(double)));
+    c->stats_cap = need;
+  }
+  c->stats_used = 0;
+  return DVC_OK;
+}
+static int stats_alloc(dvc_ctx* c, int B, int C, double** out, cudaStream_t s) {
+  const size_t n = (size_t)B * C * 2;
+  if (c->stats_used + n > c->stats_cap) return fail(c, DVC_ERR_STATE, "statistics arena exhausted (batch too large)");
+  *out = c->stats + c->stats_used;
+  c->stats_used += n;
+  CUDA_TRY(c, cudaMemsetAsync(*out, 0, n * sizeof(double), s));
+  return DVC_OK;
+}
+
+static int check_launch(dvc_ctx* c, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, DVC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return DVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+static bool ends_with(const std::string& s, const char* suf) {
+  const size_t n = strlen(suf);
+  return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const float* data, const int64_t* shape,
+                              int ndim) {
+  if (!c || !key_c || !data || !shape || net < 0 || net > 2 || ndim < 1 || ndim > 4)
+    return c ? fail(c, DVC_ERR_ARG, "dvc_set_weight: bad argument") : DVC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const std::string key(key_c);
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
+  std::vector<float> h(n);
+  CUDA_TRY(c, cudaMemcpy(h.data(), data, n * sizeof(float), cudaMemcpyDefault));
+  c->warp_cache_valid = false;
+  c->ex_valid = c->ex_valid && net == DVC_NET_COLOR;  // exemplar operands depend on VGG/WarpNet weights
+
+  if (ndim == 4 && ends_with(key, ".weight")) {
+    const std::string base = key.substr(0, key.size() - 7);
+    const int co = (int)shape[0], ci = (int)shape[1], kh = (int)shape[2], kw = (int)shape[3];
+    if (ci == 1 && kh == 1 && kw == 1) {  // depthwise *_ss scale (ColorVidNet.py:12,16,21)
+      float*& d = c->vec[net][base];
+      if (d) cudaFree(d);
+      CUDA_TRY(c, cudaMalloc((void**)&d, n * sizeof(float)));
+      CUDA_TRY(c, cudaMemcpy(d, h.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+      return DVC_OK;
+    }
+    if (!((kh == 3 && kw == 3) || (kh == 1 && kw == 1))) return fail(c, DVC_ERR_SHAPE, "unsupported kernel size: " + key);
+    if (co == 2 && kh == 1) {  // conv10_ab: consumed as [2][C] by the fused 1x1 + tanh kernel
+      float*& d = c->vec[net][base];
+      if (d) cudaFree(d);
+      CUDA_TRY(c, cudaMalloc((void**)&d, n * sizeof(float)));
+      CUDA_TRY(c, cudaMemcpy(d, h.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    ConvW& cw = c->conv[net][base];
+    const int taps = kh * kw;
+    const int cin_pad = (ci + 7) / 8 * 8, cout_pad = (co + 63) / 64 * 64;
+    std::vector<float> packed((size_t)taps * cin_pad * cout_pad, 0.f);
+    for (int o = 0; o < co; ++o)
+      for (int i = 0; i < ci; ++i)
+        for (int t = 0; t < taps; ++t)
+          packed[((size_t)t * cin_pad + i) * cout_pad + o] = h[((size_t)o * ci + i) * taps + t];
+    if (cw.w) cudaFree(cw.w);
+    CUDA_TRY(c, cudaMalloc((void**)&cw.w, packed.size() * sizeof(float)));
+    CUDA_TRY(c, cudaMemcpy(cw.w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (!cw.b || cw.cout_pad != cout_pad) {
+      if (cw.b) cudaFree(cw.b);
+      CUDA_TRY(c, cudaMalloc((void**)&cw.b, cout_pad * sizeof(float)));
+      CUDA_TRY(c, cudaMemset(cw.b, 0, cout_pad * sizeof(float)));
+    }
+    cw.cin = ci, cw.cin_pad = cin_pad, cw.cout = co, cw.cout_pad = cout_pad, cw.k = kh;
+    auto hb = c->host_bias[net].find(base);
+    if (hb != c->host_bias[net].end())
+      CUDA_TRY(c, cudaMemcpy(cw.b, hb->second.data(), hb->second.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return DVC_OK;
+  }
+  if (ndim == 1 && ends_with(key, ".bias")) {
+    const std::string base = key.substr(0, key.size() - 5);
+    c->host_bias[net][base] = h;
+    auto it = c->conv[net].find(base);
+    if (it != c->conv[net].end() && it->second.b) {
+      if ((int)n > it->second.cout_pad) return fail(c, DVC_ERR_SHAPE, "bias longer than its weight: " + key);
+      CUDA_TRY(c, cudaMemcpy(it->second.b, h.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (base == "conv10_ab") {
+      float*& d = c->vec[net]["conv10_ab.bias"];
+      if (d) cudaFree(d);
+      CUDA_TRY(c, cudaMalloc((void**)&d, n * sizeof(float)));
+      CUDA_TRY(c, cudaMemcpy(d, h.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return DVC_OK;
+  }
+  if (ndim == 1 && n == 1 && ends_with(key, ".weight")) {  // PReLU slope
+    c->slope[net][key.substr(0, key.size() - 7)] = h[0];
+    return DVC_OK;
+  }
+  return fail(c, DVC_ERR_ARG, "dvc_set_weight: unrecognised tensor " + key);
+}
+
+static int need_conv(dvc_ctx* c, int net, const char* name, const ConvW** out) {
+  auto it = c->conv[net].find(name);
+  if (it == c->conv[net].end() || !it->second.w)
+    return fail(c, DVC_ERR_STATE, std::string("weight not set: ") + name + ".weight");
+  if (c->host_bias[net].find(name) == c->host_bias[net].end())
+    return fail(c, DVC_ERR_STATE, std::string("weight not set: ") + name + ".bias");
+  *out = &it->second;
+  return DVC_OK;
+}
+static int need_slope(dvc_ctx* c, int net, const char* name, float* out) {
+  auto it = c->slope[net].find(name);
+  if (it == c->slope[net].end()) return fail(c, DVC_ERR_STATE, std::string("weight not set: ") + name + ".weight");
+  *out = it->second;
+  return DVC_OK;
+}
+static int need_vec(dvc_ctx* c, int net, const char* name, const float** out) {
+  auto it = c->vec[net].find(name);
+  if (it == c->vec[net].end()) return fail(c, DVC_ERR_STATE, std::string("weight not set: ") + name);
+  *out = it->second;
+  return DVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layer primitives
+// ------------------------------------------------------------------------------------------------
+struct ConvOpt {
+  int dil = 1, stride = 1, act = ACT_NONE;
+  float slope = 0.f;
+  const Act* add = nullptr;
+  double* stats = nullptr;
+  int yCoff = 0;
+};
+
+static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const ConvOpt& o, cudaStream_t s) {
+  if (x.C != w->cin_pad) return fail(c, DVC_ERR_SHAPE, "conv: input channel mismatch");
+  const int taps = w->k * w->k;
+  if (taps == 9 && x.P < o.dil) return fail(c, DVC_ERR_STATE, "conv: input border narrower than the dilation");
+  ConvParams p{};
+  p.x = x.d, p.Hp = x.Hp(), p.Wp = x.Wp(), p.P = x.P, p.H = x.H, p.W = x.W, p.Cin = x.C;
+  p.w = w->w, p.bias = w->b, p.taps = taps, p.dil = o.dil, p.Cout = w->cout, p.CoutPad = w->cout_pad;
+  p.stride = o.stride;
+  p.Ho = (x.H + o.stride - 1) / o.stride, p.Wo = (x.W + o.stride - 1) / o.stride;
+  if (y.H != p.Ho || y.W != p.Wo || y.B != x.B || o.yCoff + w->cout > y.C)
+    return fail(c, DVC_ERR_SHAPE, "conv: output shape mismatch");
+  p.y = y.d, p.yHp = y.Hp(), p.yWp = y.Wp(), p.yP = y.P, p.yC = y.C, p.yCoff = o.yCoff;
+  if (o.add) {
+    if (o.add->H != p.Ho || o.add->W != p.Wo || o.add->C < w->cout) return fail(c, DVC_ERR_SHAPE, "conv: addend mismatch");
+    p.add = o.add->d, p.aHp = o.add->Hp(), p.aWp = o.add->Wp(), p.aP = o.add->P, p.aC = o.add->C;
+  }
+  p.nchw = nullptr;
+  p.act = o.act, p.slope = o.slope, p.stats = o.stats;
+  launch_conv_simt(p, x.B, s);
+  return check_launch(c, "conv");
+}
+
+struct XfOpt {
+  int pad_mode = PAD_ZERO, up = 1, sub = 1, rowpad = 0;
+  const double* stats = nullptr;
+  double count = 1.0;
+  const float* scale = nullptr;
+  const Act* res = nullptr;
+  int act = 0;
+  float slope = 0.f;
+  int dCoff = 0, C = 0;
+};
+
+static int run_xform(dvc_ctx* c, const Act& src, Act& dst, const XfOpt& o, cudaStream_t s) {
+  const int C = o.C ? o.C : src.C;
+  const int eh = ((src.H + o.sub - 1) / o.sub) * o.up + 2 * o.rowpad, ew = ((src.W + o.sub - 1) / o.sub) * o.up;
+  if (dst.H != eh || dst.W != ew || dst.B != src.B || o.dCoff + C > dst.C || (C & 3))
+    return fail(c, DVC_ERR_SHAPE, "xform: shape mismatch");
+  if (o.pad_mode == PAD_REFLECT && (dst.P >= dst.H || dst.P >= dst.W)) return fail(c, DVC_ERR_SHAPE, "xform: reflect pad too wide");
+  XformParams p{};
+  p.src = src.d, p.sH = src.H, p.sW = src.W, p.sP = src.P, p.sC = src.C, p.sCoff = 0;
+  p.dst = dst.d, p.dH = dst.H, p.dW = dst.W, p.dP = dst.P, p.dC = dst.C, p.dCoff = o.dCoff;
+  p.C = C, p.pad_mode = o.pad_mode, p.up = o.up, p.sub = o.sub, p.rowpad = o.rowpad;
+  p.stats = o.stats, p.count = o.count, p.eps = 1e-5f, p.scale = o.scale;
+  if (o.res) {
+    if (o.res->H != dst.H || o.res->W != dst.W || o.res->C < C) return fail(c, DVC_ERR_SHAPE, "xform: residual mismatch");
+    p.res = o.res->d, p.rP = o.res->P, p.rC = o.res->C;
+  }
+  p.act = o.act, p.slope = o.slope;
+  launch_xform(p, src.B, s);
+  return check_launch(c, "xform");
+}
+
+static int run_pixnorm(dvc_ctx* c, const Act& src, float* dst, int dP, int pad_mode, const double* stats, double count,
+                       cudaStream_t s) {
+  if (src.C != 128 && src.C != 256 && src.C != 512) return fail(c, DVC_ERR_SHAPE, "pixnorm: channel count");
+  PixNormParams p{};
+  p.src = src.d, p.sH = src.H, p.sW = src.W, p.sP = src.P, p.sC = src.C;
+  p.dst = dst, p.dP = dP, p.dC = src.C, p.C = src.C, p.pad_mode = pad_mode;
+  p.stats = stats, p.count = count, p.eps = 2.220446049250313e-16f;  // sys.float_info.epsilon
+  launch_pixnorm(p, src.B, s);
+  return check_launch(c, "pixnorm");
+}
+
+// ------------------------------------------------------------------------------------------------
+// VGG19 trunk (NonlocalNet.py:228-256)
+// ------------------------------------------------------------------------------------------------
+struct VggMaps {
+  std::map<std::string, Act> m;  // "r11".."r54", "p1".."p5"
+};
+
+static const char* kVggSeq[] = {"conv1_1", "conv1_2", "P", "conv2_1", "conv2_2", "P", "conv3_1", "conv3_2", "conv3_3",
+                                "conv3_4", "P", "conv4_1", "conv4_2", "conv4_3", "conv4_4", "P", "conv5_1", "conv5_2",
+                                "conv5_3", "conv5_4", "P"};
+
+// x0: padded NHWC, 8 channels (3 used), P=1.  Runs until `last_key` has been produced.
+static int vgg_trunk(dvc_ctx* c, const std::string& tag, const Act& x0, const std::string& last_key, VggMaps* out,
+                     cudaStream_t s) {
+  Act cur = x0;
+  int block = 1, idx = 1;
+  for (const char* name : kVggSeq) {
+    std::string key;
+    Act nxt;
+    if (name[0] == 'P') {
+      key = "p" + std::to_string(block);
+      DVC_TRY(get_act(c, tag + "." + key, cur.B, cur.H / 2, cur.W / 2, cur.C, 1, &nxt, s));
+      launch_maxpool2(cur.d, cur.H, cur.W, cur.P, cur.C, nxt.d, 1, cur.B, s);
+      DVC_TRY(check_launch(c, "maxpool"));
+      block++, idx = 1;
+    } else {
+      key = "r" + std::to_string(block) + std::to_string(idx);
+      const ConvW* w;
+      DVC_TRY(need_conv(c, DVC_NET_VGG, name, &w));
+      DVC_TRY(get_act(c, tag + "." + key, cur.B, cur.H, cur.W, w->cout, 1, &nxt, s));
+      ConvOpt o;
+      o.act = ACT_RELU;
+      DVC_TRY(run_conv(c, w, cur, nxt, o, s));
+      idx++;
+    }
+    out->m[key] = nxt;
+    cur = nxt;
+    if (key == last_key) break;
+    if (cur.H < 2 || cur.W < 2) break;
+  }
+  return DVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// WarpNet feature side (NonlocalNet.py:451-476 for one of A / B)
+// ------------------------------------------------------------------------------------------------
+// n[4]: normalised r22,r32,r42,r52 maps, reflect-padded (P=1).  Writes rows [B][N][256] to `rows_out`.
+static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const char* proj, float* rows_out, int h, int w,
+                     cudaStream_t s) {
+  const int net = DVC_NET_WARP;
+  const int B = n[0].B;
+  Act cat;
+  DVC_TRY(get_act(c, tag + ".cat", B, h, w, 256, 1, &cat, s));
+
+  struct Head {
+    const char* c1;
+    const char* s1;
+    const char* c2;
+    const char* s2;
+    int stride2, up_mid, up_end;
+  };
+  const Head heads[4] = {{"layer2_1.1", "layer2_1.3", "layer2_1.5", "layer2_1.7", 2, 1, 1},
+                         {"layer3_1.1", "layer3_1.3", "layer3_1.5", "layer3_1.7", 1, 1, 1},
+                         {"layer4_1.1", "layer4_1.3", "layer4_1.5", "layer4_1.7", 1, 1, 2},
+                         {"layer5_1.1", "layer5_1.3", "layer5_1.6", "layer5_1.8", 1, 2, 2}};
+  for (int k = 0; k < 4; ++k) {
+    const Head& hd = heads[k];
+    const ConvW *w1, *w2;
+    float s1, s2;
+    DVC_TRY(need_conv(c, net, hd.c1, &w1));
+    DVC_TRY(need_conv(c, net, hd.c2, &w2));
+    DVC_TRY(need_slope(c, net, hd.s1, &s1));
+    DVC_TRY(need_slope(c, net, hd.s2, &s2));
+    const std::string t = tag + ".h" + std::to_string(k);
+    const Act& x = n[k];
+    Act raw1, mid, raw2;
+    double *st1, *st2;
+    DVC_TRY(get_act(c, t + ".raw1", B, x.H, x.W, w1->cout, 0, &raw1, s));
+    DVC_TRY(stats_alloc(c, B, w1->cout, &st1, s));
+    ConvOpt o1;
+    o1.stats = st1;
+    DVC_TRY(run_conv(c, w1, x, raw1, o1, s));
+    DVC_TRY(get_act(c, t + ".mid", B, x.H * hd.up_mid, x.W * hd.up_mid, w1->cout, 1, &mid, s));
+    XfOpt x1;
+    x1.pad_mode = PAD_REFLECT, x1.up = hd.up_mid, x1.stats = st1, x1.count = (double)x.H * x.W, x1.act = 2, x1.slope = s1;
+    DVC_TRY(run_xform(c, raw1, mid, x1, s));
+    const int h2 = (mid.H + hd.stride2 - 1) / hd.stride2, w2o = (mid.W + hd.stride2 - 1) / hd.stride2;
+    DVC_TRY(get_act(c, t + ".raw2", B, h2, w2o, 64, 0, &raw2, s));
+    DVC_TRY(stats_alloc(c, B, 64, &st2, s));
+    ConvOpt o2;
+    o2.stats = st2, o2.stride = hd.stride2;
+    DVC_TRY(run_conv(c, w2, mid, raw2, o2, s));
+    XfOpt x2;
+    x2.pad_mode = PAD_REFLECT, x2.up = hd.up_end, x2.stats = st2, x2.count = (double)h2 * w2o, x2.act = 2, x2.slope = s2;
+    x2.dCoff = 64 * k, x2.C = 64;
+    const int fh = h2 * hd.up_end, fw = w2o * hd.up_end;
+    if (fw != w) return fail(c, DVC_ERR_SHAPE, "WarpNet: feature widths disagree (W must be a multiple of 16)");
+    if (fh != h) {
+      // NonlocalNet.py:461-463 repairs only the r5 head, rows only, by exactly one row top and bottom
+      if (k != 3 || fh + 2 != h) return fail(c, DVC_ERR_SHAPE, "WarpNet: feature heights disagree (H must be a multiple of 8)");
+      x2.rowpad = 1;
+    }
+    DVC_TRY(run_xform(c, raw2, cat, x2, s));
+  }
+
+  // three residual blocks (NonlocalNet.py:341-352), ping-pong between two padded buffers
+  Act xa = cat, xb, raw, mid;
+  DVC_TRY(get_act(c, tag + ".res_b", B, h, w, 256, 1, &xb, s));
+  DVC_TRY(get_act(c, tag + ".res_raw", B, h, w, 256, 0, &raw, s));
+  DVC_TRY(get_act(c, tag + ".res_mid", B, h, w, 256, 1, &mid, s));
+  for (int i = 0; i < 3; ++i) {
+    const std::string base = "layer." + std::to_string(i);
+    const ConvW *w1, *w2;
+    float sl;
+    DVC_TRY(need_conv(c, net, (base + ".conv1").c_str(), &w1));
+    DVC_TRY(need_conv(c, net, (base + ".conv2").c_str(), &w2));
+    DVC_TRY(need_slope(c, net, (base + ".prelu").c_str(), &sl));
+    double *st1, *st2;
+    DVC_TRY(stats_alloc(c, B, 256, &st1, s));
+    DVC_TRY(stats_alloc(c, B, 256, &st2, s));
+    ConvOpt o1;
+    o1.stats = st1;
+    DVC_TRY(run_conv(c, w1, xa, raw, o1, s));
+    XfOpt x1;
+    x1.pad_mode = PAD_REFLECT, x1.stats = st1, x1.count = (double)h * w, x1.act = 2, x1.slope = sl;
+    DVC_TRY(run_xform(c, raw, mid, x1, s));
+    ConvOpt o2;
+    o2.stats = st2;
+    DVC_TRY(run_conv(c, w2, mid, raw, o2, s));
+    XfOpt x2;
+    x2.pad_mode = PAD_REFLECT, x2.stats = st2, x2.count = (double)h * w, x2.act = 2, x2.slope = sl, x2.res = &xa;
+    DVC_TRY(run_xform(c, raw, xb, x2, s));
+    std::swap(xa, xb);
+  }
+
+  // theta / phi: 1x1 conv, centre over positions, unit L2 norm over channels (NonlocalNet.py:468-476)
+  const ConvW* wp;
+  DVC_TRY(need_conv(c, net, proj, &wp));
+  double* stp;
+  DVC_TRY(stats_alloc(c, B, 256, &stp, s));
+  ConvOpt op;
+  op.stats = stp;
+  DVC_TRY(run_conv(c, wp, xa, raw, op, s));
+  DVC_TRY(run_pixnorm(c, raw, rows_out, 0, PAD_ZERO, stp, (double)h * w, s));
+  return DVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// correlation dispatch
+// ------------------------------------------------------------------------------------------------
+static int run_corr(dvc_ctx* c, const CorrParams& p, cudaStream_t s) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->prof_corr) {
+    CUDA_TRY(c, cudaEventCreate(&e0));
+    CUDA_TRY(c, cudaEventCreate(&e1));
+    CUDA_TRY(c, cudaEventRecord(e0, s));
+  }
+  if (c->corr_math == DVC_MATH_FP32) {
+    launch_corr_simt(p, s);
+  } else {
+    std::string err;
+    if (launch_corr_tc(p, c->corr_math, s, &err) != 0) return fail(c, DVC_ERR_CUDA, "corr_tc: " + err);
+  }
+  DVC_TRY(check_launch(c, "corr"));
+  if (c->prof_corr) {
+    CUDA_TRY(c, cudaEventRecord(e1, s));
+    c->corr_events.emplace_back(e0, e1);
+  }
+  return DVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ColorVidNet (ColorVidNet.py:96-144).  in0: padded NHWC, 8 channels (7 used), P=1, zero border.
+// ------------------------------------------------------------------------------------------------
+static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* out_nchw, cudaStream_t s) {
+  const int net = DVC_NET_COLOR;
+  const int B = in0.B, H = in0.H, W = in0.W;
+  int uid = 0;
+  auto conv = [&](const char* name, const Act& x, Act* y, int outP, int act, int dil, const Act* add, double** st,
+                  float slope) -> int {
+    const ConvW* w;
+    DVC_TRY(need_conv(c, net, name, &w));
+    DVC_TRY(get_act(c, tag + "." + name + "#" + std::to_string(uid++), x.B, x.H, x.W, w->cout, outP, y, s));
+    ConvOpt o;
+    o.act = act, o.dil = dil, o.add = add, o.slope = slope;
+    if (st) {
+      DVC_TRY(stats_alloc(c, B, w->cout, st, s));
+      o.stats = *st;
+    }
+    return run_conv(c, w, x, *y, o, s);
+  };
+  auto norm = [&](const char* name, const Act& raw, const double* st, Act* y, int outP, int up, int sub,
+                  const float* scale) -> int {
+    DVC_TRY(get_act(c, tag + "." + name + "#" + std::to_string(uid++), B, ((raw.H + sub - 1) / sub) * up,
+                    ((raw.W + sub - 1) / sub) * up, raw.C, outP, y, s));
+    XfOpt o;
+    o.pad_mode = PAD_ZERO, o.up = up, o.sub = sub, o.stats = st, o.count = (double)raw.H * raw.W, o.scale = scale;
+    return run_xform(c, raw, *y, o, s);
+  };
+  const float *ss1, *ss2, *ss3, *wab, *bab;
+  DVC_TRY(need_vec(c, net, "conv1_2norm_ss", &ss1));
+  DVC_TRY(need_vec(c, net, "conv2_2norm_ss", &ss2));
+  DVC_TRY(need_vec(c, net, "conv3_3norm_ss", &ss3));
+  DVC_TRY(need_vec(c, net, "conv10_ab", &wab));
+  DVC_TRY(need_vec(c, net, "conv10_ab.bias", &bab));
+
+  Act a, b, raw1, n1, d1, raw2, n2, d2, raw3, n3, d3, raw4, n4, raw5, n5, raw6, n6, raw7, n7u, t, u;
+  double *st1, *st2, *st3, *st4, *st5, *st6, *st7, *st8, *st9;
+  DVC_TRY(conv("conv1_1.0", in0, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv1_1.2", a, &b, 1, ACT_RELU, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv1_2", b, &raw1, 0, ACT_RELU, 1, nullptr, &st1, 0));
+  DVC_TRY(norm("n1", raw1, st1, &n1, 1, 1, 1, nullptr));
+  DVC_TRY(norm("d1", raw1, st1, &d1, 1, 1, 2, ss1));
+  DVC_TRY(conv("conv2_1", d1, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv2_2", a, &raw2, 0, ACT_RELU, 1, nullptr, &st2, 0));
+  DVC_TRY(norm("n2", raw2, st2, &n2, 1, 1, 1, nullptr));
+  DVC_TRY(norm("d2", raw2, st2, &d2, 1, 1, 2, ss2));
+  DVC_TRY(conv("conv3_1", d2, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv3_2", a, &b, 1, ACT_RELU, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv3_3", b, &raw3, 0, ACT_RELU, 1, nullptr, &st3, 0));
+  DVC_TRY(norm("n3", raw3, st3, &n3, 1, 1, 1, nullptr));
+  DVC_TRY(norm("d3", raw3, st3, &d3, 1, 1, 2, ss3));
+  DVC_TRY(conv("conv4_1", d3, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv4_2", a, &b, 1, ACT_RELU, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv4_3", b, &raw4, 0, ACT_RELU, 1, nullptr, &st4, 0));
+  DVC_TRY(norm("n4", raw4, st4, &n4, 2, 1, 1, nullptr));
+  DVC_TRY(conv("conv5_1", n4, &a, 2, ACT_RELU, 2, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv5_2", a, &b, 2, ACT_RELU, 2, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv5_3", b, &raw5, 0, ACT_RELU, 2, nullptr, &st5, 0));
+  DVC_TRY(norm("n5", raw5, st5, &n5, 2, 1, 1, nullptr));
+  DVC_TRY(conv("conv6_1", n5, &a, 2, ACT_RELU, 2, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv6_2", a, &b, 2, ACT_RELU, 2, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv6_3", b, &raw6, 0, ACT_RELU, 2, nullptr, &st6, 0));
+  DVC_TRY(norm("n6", raw6, st6, &n6, 1, 1, 1, nullptr));
+  DVC_TRY(conv("conv7_1", n6, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv7_2", a, &b, 1, ACT_RELU, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv7_3", b, &raw7, 0, ACT_RELU, 1, nullptr, &st7, 0));
+  DVC_TRY(norm("n7u", raw7, st7, &n7u, 1, 2, 1, nullptr));
+  // decoder stage 8: relu(conv8_1(up(n7)) + conv3_3_short(n3))
+  DVC_TRY(conv("conv3_3_short", n3, &t, 0, ACT_NONE, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv8_1.1", n7u, &u, 1, ACT_RELU, 1, &t, nullptr, 0));
+  DVC_TRY(conv("conv8_2", u, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv8_3", a, &raw1, 0, ACT_RELU, 1, nullptr, &st8, 0));
+  Act n8u, n9u;
+  DVC_TRY(norm("n8u", raw1, st8, &n8u, 1, 2, 1, nullptr));
+  DVC_TRY(conv("conv2_2_short", n2, &t, 0, ACT_NONE, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv9_1.1", n8u, &u, 1, ACT_RELU, 1, &t, nullptr, 0));
+  DVC_TRY(conv("conv9_2", u, &raw2, 0, ACT_RELU, 1, nullptr, &st9, 0));
+  DVC_TRY(norm("n9u", raw2, st9, &n9u, 1, 2, 1, nullptr));
+  DVC_TRY(conv("conv1_2_short", n1, &t, 0, ACT_NONE, 1, nullptr, nullptr, 0));
+  DVC_TRY(conv("conv10_1.1", n9u, &u, 1, ACT_RELU, 1, &t, nullptr, 0));
+  DVC_TRY(conv("conv10_2", u, &a, 0, ACT_LRELU, 1, nullptr, nullptr, 0.2f));
+  if (a.H != H || a.W != W || a.C != 128) return fail(c, DVC_ERR_SHAPE, "ColorVidNet: decoder shape mismatch");
+  launch_final_ab(a.d, H, W, a.P, a.C, wab, bab, out_nchw, B, s);
+  return check_launch(c, "final_ab");
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static bool legal_shape(int H, int W) { return H >= 16 && W >= 16 && H % 8 == 0 && W % 16 == 0; }
+
+extern "C" const char* dvc_version(void) { return "libdvc 0.1 (sm_100a)"; }
+
+extern "C" int dvc_create(dvc_ctx** out, int device) {
+  if (!out) return DVC_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libdvc has no CPU fallback)";
+    return DVC_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    g_create_err = "device index out of range";
+    return DVC_ERR_ARG;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    g_create_err = cudaGetErrorString(e);
+    return DVC_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_err = "libdvc is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+    return DVC_ERR_CUDA;
+  }
+  dvc_ctx* c = new dvc_ctx();
+  c->device = device;
+  *out = c;
+  return DVC_OK;
+}
+
+extern "C" int dvc_destroy(dvc_ctx* c) {
+  if (!c) return DVC_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : c->bufs)
+    if (kv.second.p) cudaFree(kv.second.p);
+  for (int n = 0; n < 3; ++n) {
+    for (auto& kv : c->conv[n]) {
+      if (kv.second.w) cudaFree(kv.second.w);
+      if (kv.second.b) cudaFree(kv.second.b);
+    }
+    for (auto& kv : c->vec[n])
+      if (kv.second) cudaFree(kv.second);
+  }
+  if (c->stats) cudaFree(c->stats);
+  if (c->ex_phi) cudaFree(c->ex_phi);
+  if (c->ex_V) cudaFree(c->ex_V);
+  for (auto& ev : c->corr_events) cudaEventDestroy(ev.first), cudaEventDestroy(ev.second);
+  delete c;
+  return DVC_OK;
+}
+
+extern "C" const char* dvc_last_error(const dvc_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int dvc_set_math(dvc_ctx* c, int conv_math, int corr_math) {
+  if (!c) return DVC_ERR_ARG;
+  if (conv_math != DVC_MATH_FP32) return fail(c, DVC_ERR_ARG, "conv math: only DVC_MATH_FP32 is available in this build");
+  if (corr_math != DVC_MATH_FP32 && corr_math != DVC_MATH_TF32X3 && corr_math != DVC_MATH_BF16X3)
+    return fail(c, DVC_ERR_ARG, "unknown corr math");
+  c->conv_math = conv_math, c->corr_math = corr_math;
+  return DVC_OK;
+}
+
+extern "C" int64_t dvc_launch_count(dvc_ctx*, int reset) {
+  int64_t v = g_launches.load();
+  if (reset) g_launches.store(0);
+  return v;
+}
+
+extern "C" int dvc_profile_corr(dvc_ctx* c, int enable) {
+  if (!c) return DVC_ERR_ARG;
+  c->prof_corr = enable != 0;
+  return DVC_OK;
+}
+
+extern "C" double dvc_corr_mean_ms(dvc_ctx* c, int reset) {
+  if (!c || c->corr_events.empty()) return 0.0;
+  double tot = 0.0;
+  int n = 0;
+  for (auto& ev : c->corr_events) {
+    if (cudaEventSynchronize(ev.second) != cudaSuccess) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) tot += ms, n++;
+  }
+  if (reset) {
+    for (auto& ev : c->corr_events) cudaEventDestroy(ev.first), cudaEventDestroy(ev.second);
+    c->corr_events.clear();
+  }
+  return n ? tot / n : 0.0;
+}
+
+// ---- VGG19_pytorch.forward ----------------------------------------------------------------------
+extern "C" int dvc_vgg19_forward(dvc_ctx* c, const float* x, int B, int H, int W, int preprocess, const char* const* keys,
+                                 float* const* outs, int n_keys, void* stream) {
+  if (!c || !x || !keys || !outs || B < 1 || n_keys < 1) return c ? fail(c, DVC_ERR_ARG, "vgg19_forward: bad argument") : DVC_ERR_ARG;
+  if (H < 16 || W < 16) return fail(c, DVC_ERR_SHAPE, "vgg19_forward: H, W must be >= 16");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  // deepest requested map decides where the trunk stops (the reference evaluates all 21 stages
+  // regardless, NonlocalNet.py:235-255; the skipped tail is not observable)
+  int deepest = -1;
+  {
+    int block = 1, idx = 1, pos = 0;
+    for (const char* name : kVggSeq) {
+      std::string key = name[0] == 'P' ? "p" + std::to_string(block) : "r" + std::to_string(block) + std::to_string(idx);
+      if (name[0] == 'P') block++, idx = 1; else idx++;
+      for (int i = 0; i < n_keys; ++i)
+        if (keys[i] && key == keys[i] && pos > deepest) deepest = pos;
+      pos++;
+    }
+  }
+  std::string last_key;
+  {
+    int block = 1, idx = 1, pos = 0;
+    for (const char* name : kVggSeq) {
+      std::string key = name[0] == 'P' ? "p" + std::to_string(block) : "r" + std::to_string(block) + std::to_string(idx);
+      if (name[0] == 'P') block++, idx = 1; else idx++;
+      if (pos == deepest) last_key = key;
+      pos++;
+    }
+  }
+  if (deepest < 0) return fail(c, DVC_ERR_ARG, "vgg19_forward: unknown out_key");
+  Act x0;
+  DVC_TRY(get_act(c, "mvgg.x0", B, H, W, 8, 1, &x0, s));
+  launch_nchw_to_act(x, 3, x0.d, B, H, W, 8, 1, PAD_ZERO, preprocess ? 1 : 0, s);
+  DVC_TRY(check_launch(c, "nchw_to_act"));
+  VggMaps maps;
+  DVC_TRY(vgg_trunk(c, "mvgg", x0, last_key, &maps, s));
+  for (int i = 0; i < n_keys; ++i) {
+    auto it = maps.m.find(keys[i] ? keys[i] : "");
+    if (it == maps.m.end()) return fail(c, DVC_ERR_ARG, std::string("vgg19_forward: unknown out_key ") + (keys[i] ? keys[i] : "(null)"));
+    const Act& a = it->second;
+    launch_act_to_nchw(a.d, a.H, a.W, a.P, a.C, 0, a.C, outs[i], B, s);
+    DVC_TRY(check_launch(c, "act_to_nchw"));
+  }
+  return DVC_OK;
+}
+
+// ---- WarpNet.forward -----------------------------------------------------------------------------
+static int features_from_nchw(dvc_ctx* c, const std::string& tag, const float* const* f, int B, int H, int W, Act n[4],
+                              cudaStream_t s) {
+  // dims the VGG trunk produces for an HxW input (floor-mode pools)
+  const int hs[4] = {H / 2, H / 4, H / 8, H / 16}, ws[4] = {W / 2, W / 4, W / 8, W / 16}, cs[4] = {128, 256, 512, 512};
+  for (int k = 0; k < 4; ++k) {
+    DVC_TRY(get_act(c, tag + ".n" + std::to_string(k), B, hs[k], ws[k], cs[k], 1, &n[k], s));
+    launch_nchw_to_act(f[k], cs[k], n[k].d, B, hs[k], ws[k], cs[k], 1, PAD_REFLECT, 0, s);
+    DVC_TRY(check_launch(c, "nchw_to_act"));
+  }
+  return DVC_OK;
+}
+
+extern "C" int dvc_warpnet_forward(dvc_ctx* c, const float* B_lab_map, const float* const* A, const float* const* Bf, int B,
+                                   int H, int W, float temperature, float wta, int reuse_exemplar, float* y, float* sim,
+                                   void* stream) {
+  if (!c || !B_lab_map || !A || !Bf || !y || !sim || B < 1) return c ? fail(c, DVC_ERR_ARG, "warpnet_forward: bad argument") : DVC_ERR_ARG;
+  if (wta != 1.0f) return fail(c, DVC_ERR_ARG, "warpnet_forward: WTA_scale_weight != 1 is not supported (training-only path, NonlocalNet.py:486)");
+  if (!(temperature > 0.f)) return fail(c, DVC_ERR_ARG, "warpnet_forward: temperature must be > 0");
+  if (!legal_shape(H, W)) return fail(c, DVC_ERR_SHAPE, "warpnet_forward: H must be a multiple of 8 and W a multiple of 16 (the reference fails at NonlocalNet.py:464 otherwise)");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  DVC_TRY(stats_begin(c, s));
+  const int h = H / 4, w = W / 4, N = h * w;
+  void *theta, *phi, *V, *yrows, *simrows;
+  DVC_TRY(get_raw(c, "mwarp.theta", (size_t)B * N * 256 * 4, &theta, s));
+  DVC_TRY(get_raw(c, "mwarp.phi", (size_t)B * N * 256 * 4, &phi, s));
+  DVC_TRY(get_raw(c, "mwarp.V", (size_t)B * N * 4 * 4, &V, s));
+  DVC_TRY(get_raw(c, "mwarp.yrows", (size_t)B * N * 4 * 4, &yrows, s));
+  DVC_TRY(get_raw(c, "mwarp.simrows", (size_t)B * N * 4, &simrows, s));
+  Act n[4];
+  DVC_TRY(features_from_nchw(c, "mwarpA", A, B, H, W, n, s));
+  DVC_TRY(warp_side(c, "mwarpA", n, "theta", (float*)theta, h, w, s));
+  const bool can_reuse = reuse_exemplar && c->warp_cache_valid && c->warp_cache_sig[0] == B && c->warp_cache_sig[1] == H &&
+                         c->warp_cache_sig[2] == W;
+  if (!can_reuse) {
+    DVC_TRY(features_from_nchw(c, "mwarpB", Bf, B, H, W, n, s));
+    DVC_TRY(warp_side(c, "mwarpB", n, "phi", (float*)phi, h, w, s));
+    launch_avgpool4_lab(B_lab_map, (float*)V, B, H, W, s);
+    DVC_TRY(check_launch(c, "avgpool4"));
+    c->warp_cache_valid = true;
+    c->warp_cache_sig[0] = B, c->warp_cache_sig[1] = H, c->warp_cache_sig[2] = W;
+  }
+  CorrParams p{};
+  p.theta = (float*)theta, p.phi = (float*)phi, p.V = (float*)V, p.B = B, p.Bphi = B, p.NA = N, p.NB = N, p.C = 256;
+  p.temperature = temperature, p.y = (float*)yrows, p.sim = (float*)simrows, p.argmax = nullptr;
+  DVC_TRY(run_corr(c, p, s));
+  launch_rows_to_nchw_up4((float*)yrows, (float*)simrows, y, sim, B, h, w, s);
+  return check_launch(c, "rows_to_nchw_up4");
+}
+
+// ---- ColorVidNet.forward -------------------------------------------------------------------------
+extern "C" int dvc_colorvidnet_forward(dvc_ctx* c, const float* x, int B, int H, int W, float* out, void* stream) {
+  if (!c || !x || !out || B < 1) return c ? fail(c, DVC_ERR_ARG, "colorvidnet_forward: bad argument") : DVC_ERR_ARG;
+  if (H < 8 || W < 8 || H % 8 || W % 8) return fail(c, DVC_ERR_SHAPE, "colorvidnet_forward: H and W must be multiples of 8 (skip adds at ColorVidNet.py:129,135,140)");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  DVC_TRY(stats_begin(c, s));
+  Act in0;
+  DVC_TRY(get_act(c, "mcolor.in0", B, H, W, 8, 1, &in0, s));
+  launch_nchw_to_act(x, 7, in0.d, B, H, W, 8, 1, PAD_ZERO, 0, s);
+  DVC_TRY(check_launch(c, "nchw_to_act"));
+  return colorvid(c, "mcolor", in0, out, s);
+}
+
+// ---- stand-alone correlation ---------------------------------------------------------------------
+extern "C" int dvc_corr_softmax_warp(dvc_ctx* c, const float* theta_hat, const float* phi_hat, const float* V, int B,
+                                     int Bphi, int NA, int NB, int C, float temperature, float* y, float* sim,
+                                     int32_t* argmax, void* stream) {
+  if (!c || !theta_hat || !phi_hat || !V || !y || !sim) return c ? fail(c, DVC_ERR_ARG, "corr: bad argument") : DVC_ERR_ARG;
+  if (C != 256) return fail(c, DVC_ERR_SHAPE, "corr: C must be 256 (WarpNet.inter_channels)");
+  if (B < 1 || NA < 1 || NB < 1 || (Bphi != B && Bphi != 1)) return fail(c, DVC_ERR_SHAPE, "corr: bad sizes");
+  if (!(temperature > 0.f)) return fail(c, DVC_ERR_ARG, "corr: temperature must be > 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  void *th, *ph, *V4, *y4;
+  DVC_TRY(get_raw(c, "corr.theta", (size_t)B * NA * C * 4, &th, s));
+  DVC_TRY(get_raw(c, "corr.phi", (size_t)Bphi * NB * C * 4, &ph, s));
+  DVC_TRY(get_raw(c, "corr.V4", (size_t)Bphi * NB * 16, &V4, s));
+  DVC_TRY(get_raw(c, "corr.y4", (size_t)B * NA * 16, &y4, s));
+  // channel-major [b][C][N] (the reference's view, NonlocalNet.py:468,473) -> position-major rows
+  launch_transpose_cn(theta_hat, (float*)th, B, C, NA, s);
+  launch_transpose_cn(phi_hat, (float*)ph, Bphi, C, NB, s);
+  CUDA_TRY(c, cudaMemsetAsync(V4, 0, (size_t)Bphi * NB * 16, s));
+  CUDA_TRY(c, cudaMemcpy2DAsync(V4, 16, V, 12, 12, (size_t)Bphi * NB, cudaMemcpyDeviceToDevice, s));
+  CorrParams p{};
+  p.theta = (float*)th, p.phi = (float*)ph, p.V = (float*)V4, p.B = B, p.Bphi = Bphi, p.NA = NA, p.NB = NB, p.C = C;
+  p.temperature = temperature, p.y = (float*)y4, p.sim = sim, p.argmax = argmax;
+  DVC_TRY(run_corr(c, p, s));
+  CUDA_TRY(c, cudaMemcpy2DAsync(y, 12, y4, 16, 12, (size_t)B * NA, cudaMemcpyDeviceToDevice, s));
+  return DVC_OK;
+}
+
+// ---- fused per-frame path ---------------------------------------------------------------------------
+static int normalised_features(dvc_ctx* c, const std::string& tag, VggMaps& maps, Act n[4], cudaStream_t s) {
+  const char* keys[4] = {"r22", "r32", "r42", "r52"};
+  for (int k = 0; k < 4; ++k) {
+    const Act& r = maps.m[keys[k]];
+    DVC_TRY(get_act(c, tag + ".n" + std::to_string(k), r.B, r.H, r.W, r.C, 1, &n[k], s));
+    DVC_TRY(run_pixnorm(c, r, n[k].d, 1, PAD_REFLECT, nullptr, 1.0, s));  // feature_normalize, util.py:155-158
+  }
+  return DVC_OK;
+}
+
+extern "C" int dvc_set_exemplar(dvc_ctx* c, const float* IB_lab, int H, int W, void* stream) {
+  if (!c || !IB_lab) return c ? fail(c, DVC_ERR_ARG, "set_exemplar: bad argument") : DVC_ERR_ARG;
+  if (!legal_shape(H, W)) return fail(c, DVC_ERR_SHAPE, "set_exemplar: H must be a multiple of 8 and W a multiple of 16");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  DVC_TRY(stats_begin(c, s));
+  void* lab;
+  DVC_TRY(get_raw(c, "ex.lab", (size_t)3 * H * W * 4, &lab, s));
+  CUDA_TRY(c, cudaMemcpyAsync(lab, IB_lab, (size_t)3 * H * W * 4, cudaMemcpyDefault, s));
+  Act x0;
+  DVC_TRY(get_act(c, "ex.x0", 1, H, W, 8, 1, &x0, s));
+  launch_nchw_to_act((float*)lab, 3, x0.d, 1, H, W, 8, 1, PAD_ZERO, 3, s);  // test.py:61-65
+  DVC_TRY(check_launch(c, "nchw_to_act"));
+  VggMaps maps;
+  DVC_TRY(vgg_trunk(c, "ex", x0, "r52", &maps, s));
+  Act n[4];
+  DVC_TRY(normalised_features(c, "ex", maps, n, s));
+  const int h = H / 4, w = W / 4, N = h * w;
+  if (c->ex_N != N) {
+    if (c->ex_phi) cudaFree(c->ex_phi);
+    if (c->ex_V) cudaFree(c->ex_V);
+    c->ex_phi = c->ex_V = nullptr;
+    CUDA_TRY(c, cudaMalloc((void**)&c->ex_phi, (size_t)N * 256 * 4));
+    CUDA_TRY(c, cudaMalloc((void**)&c->ex_V, (size_t)N * 16));
+    c->ex_N = N;
+  }
+  DVC_TRY(warp_side(c, "ex", n, "phi", c->ex_phi, h, w, s));
+  launch_avgpool4_lab((float*)lab, c->ex_V, 1, H, W, s);
+  DVC_TRY(check_launch(c, "avgpool4"));
+  c->ex_H = H, c->ex_W = W, c->ex_valid = true;
+  return DVC_OK;
+}
+
+extern "C" int dvc_colorize_frames(dvc_ctx* c, const float* IA_l, const float* IA_last_lab, int B, int H, int W,
+                                   float temperature, float* out_ab, float* out_warp_lab, float* out_sim, void* stream) {
+  if (!c || !IA_l || !IA_last_lab || !out_ab || B < 1) return c ? fail(c, DVC_ERR_ARG, "colorize_frames: bad argument") : DVC_ERR_ARG;
+  if (!c->ex_valid) return fail(c, DVC_ERR_STATE, "colorize_frames: call dvc_set_exemplar first");
+  if (H != c->ex_H || W != c->ex_W) return fail(c, DVC_ERR_SHAPE, "colorize_frames: frame size differs from the exemplar's");
+  if (!(temperature > 0.f)) return fail(c, DVC_ERR_ARG, "colorize_frames: temperature must be > 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  DVC_TRY(stats_begin(c, s));
+  const int h = H / 4, w = W / 4, N = h * w;
+  Act x0;
+  DVC_TRY(get_act(c, "fr.x0", B, H, W, 8, 1, &x0, s));
+  launch_nchw_to_act(IA_l, 1, x0.d, B, H, W, 8, 1, PAD_ZERO, 2, s);  // FrameColor.py:6 + util.py:347-352
+  DVC_TRY(check_launch(c, "nchw_to_act"));
+  VggMaps maps;
+  DVC_TRY(vgg_trunk(c, "fr", x0, "r52", &maps, s));
+  Act n[4];
+  DVC_TRY(normalised_features(c, "fr", maps, n, s));
+  void *theta, *yrows, *simrows;
+  DVC_TRY(get_raw(c, "fr.theta", (size_t)B * N * 256 * 4, &theta, s));
+  DVC_TRY(get_raw(c, "fr.yrows", (size_t)B * N * 16, &yrows, s));
+  DVC_TRY(get_raw(c, "fr.simrows", (size_t)B * N * 4, &simrows, s));
+  DVC_TRY(warp_side(c, "fr", n, "theta", (float*)theta, h, w, s));
+  CorrParams p{};
+  p.theta = (float*)theta, p.phi = c->ex_phi, p.V = c->ex_V, p.B = B, p.Bphi = 1, p.NA = N, p.NB = N, p.C = 256;
+  p.temperature = temperature, p.y = (float*)yrows, p.sim = (float*)simrows, p.argmax = nullptr;
+  DVC_TRY(run_corr(c, p, s));
+  if (out_warp_lab || out_sim) {
+    launch_rows_to_nchw_up4((float*)yrows, (float*)simrows, out_warp_lab, out_sim, B, h, w, s);
+    DVC_TRY(check_launch(c, "rows_to_nchw_up4"));
+  }
+  Act in0;
+  DVC_TRY(get_act(c, "fr.in0", B, H, W, 8, 1, &in0, s));
+  launch_build_color_input(IA_l, (float*)yrows, (float*)simrows, IA_last_lab, in0.d, B, H, W, 1, s);
+  DVC_TRY(check_launch(c, "build_color_input"));
+  return colorvid(c, "fr", in0, out_ab, s);
+}
+
+extern "C" int dvc_colorize_clip(dvc_ctx* c, const float* host_L, int F, int H, int W, float temperature,
+                                 const float* first_last, float* host_ab, void* stream) {
+  if (!c || !host_L || !host_ab || F < 1) return c ? fail(c, DVC_ERR_ARG, "colorize_clip: bad argument") : DVC_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const size_t hw = (size_t)H * W;
+  void *dL, *dlast, *dab;
+  DVC_TRY(get_raw(c, "clip.L", 2 * hw * 4, &dL, s));  // double buffer: frame t+1 uploads while t computes
+  DVC_TRY(get_raw(c, "clip.last", 3 * hw * 4, &dlast, s));
+  DVC_TRY(get_raw(c, "clip.ab", 2 * hw * 4, &dab, s));
+  if (first_last)
+    CUDA_TRY(c, cudaMemcpyAsync(dlast, first_last, 3 * hw * 4, cudaMemcpyDefault, s));
+  else
+    CUDA_TRY(c, cudaMemsetAsync(dlast, 0, 3 * hw * 4, s));  // test.py:80
+  for (int t = 0; t < F; ++t) {
+    float* Lt = (float*)dL + (t & 1) * hw;
+    CUDA_TRY(c, cudaMemcpyAsync(Lt, host_L + (size_t)t * hw, hw * 4, cudaMemcpyDefault, s));
+    DVC_TRY(dvc_colorize_frames(c, Lt, (float*)dlast, 1, H, W, temperature, (float*)dab, nullptr, nullptr, stream));
+    launch_make_last(Lt, (float*)dab, (float*)dlast, 1, H, W, s);  // test.py:96
+    DVC_TRY(check_launch(c, "make_last"));
+    CUDA_TRY(c, cudaMemcpyAsync(host_ab + (size_t)t * 2 * hw, dab, 2 * hw * 4, cudaMemcpyDefault, s));
+  }
+  CUDA_TRY(c, cudaStreamSynchronize(s));
+  return DVC_OK;
+}
+
+// ---- exemplar operands for the NCCL broadcast -----------------------------------------------------
+extern "C" int64_t dvc_exemplar_pack_size(const dvc_ctx*, int H, int W) {
+  const int64_t N = (int64_t)(H / 4) * (W / 4);
+  return N * 256 + N * 4;
+}
+
+extern "C" int dvc_exemplar_export(dvc_ctx* c, float* buf, int64_t n, void* stream) {
+  if (!c || !buf) return c ? fail(c, DVC_ERR_ARG, "exemplar_export: bad argument") : DVC_ERR_ARG;
+  if (!c->ex_valid) return fail(c, DVC_ERR_STATE, "exemplar_export: no exemplar set");
+  const int64_t N = c->ex_N;
+  if (n != N * 260) return fail(c, DVC_ERR_SHAPE, "exemplar_export: buffer size mismatch");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaMemcpyAsync(buf, c->ex_phi, (size_t)N * 256 * 4, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(c, cudaMemcpyAsync(buf + N * 256, c->ex_V, (size_t)N * 16, cudaMemcpyDeviceToDevice, s));
+  return DVC_OK;
+}
+
+extern "C" int dvc_exemplar_import(dvc_ctx* c, const float* buf, int64_t n, int H, int W, void* stream) {
+  if (!c || !buf) return c ? fail(c, DVC_ERR_ARG, "exemplar_import: bad argument") : DVC_ERR_ARG;
+  if (!legal_shape(H, W)) return fail(c, DVC_ERR_SHAPE, "exemplar_import: illegal frame shape");
+  const int64_t N = (int64_t)(H / 4) * (W / 4);
+  if (n != N * 260) return fail(c, DVC_ERR_SHAPE, "exemplar_import: buffer size mismatch");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  if (c->ex_N != N) {
+    if (c->ex_phi) cudaFree(c->ex_phi);
+    if (c->ex_V) cudaFree(c->ex_V);
+    c->ex_phi = c->ex_V = nullptr;
+    CUDA_TRY(c, cudaMalloc((void**)&c->ex_phi, (size_t)N * 256 * 4));
+    CUDA_TRY(c, cudaMalloc((void**)&c->ex_V, (size_t)N * 16));
+    c->ex_N = (int)N;
+  }
+  CUDA_TRY(c, cudaMemcpyAsync(c->ex_phi, buf, (size_t)N * 256 * 4, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(c, cudaMemcpyAsync(c->ex_V, buf + N * 256, (size_t)N * 16, cudaMemcpyDeviceToDevice, s));
+  c->ex_H = H, c->ex_W = W, c->ex_valid = true;
+  return DVC_OK;
+}

@@ -1,0 +1,121 @@
+// Internal declarations shared by the kernels and the host-side layer programs of libdvc.so.
+//
+// Data layout in HBM: every activation is a "padded NHWC" fp32 tensor
+//     [B][H + 2P][W + 2P][C]
+// whose border of width P already holds what the consumer's padding mode would produce (zeros for
+// the VGG / ColorVidNet convolutions, mirrored pixels for WarpNet's ReflectionPad2d).  With that
+// layout a 3x3 (dilated) convolution is a plain GEMM over the flat padded pixel index p:
+//     Y[p, co] = sum_tap sum_ci X[p + off(tap), ci] * Wt[tap][ci][co],  off = (dy*Wp + dx)*dil
+// i.e. nine row-shifted [pixels x Cin] operands that TMA (or float4 loads) can fetch as ordinary
+// 2-D tiles.  Border pixels compute garbage that the epilogue masks out.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dvc {
+
+struct Act {
+  float* d = nullptr;  // pixel (b=0, yp=0, xp=0), channel 0
+  int B = 0, H = 0, W = 0, C = 0, P = 0;
+  int Hp() const { return H + 2 * P; }
+  int Wp() const { return W + 2 * P; }
+  size_t pixels() const { return (size_t)B * Hp() * Wp(); }
+  size_t elems() const { return pixels() * C; }
+};
+
+enum ActFn { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
+enum PadMode { PAD_ZERO = 0, PAD_REFLECT = 1 };
+
+// ---- convolution as flat shifted GEMM --------------------------------------------------------
+struct ConvParams {
+  const float* x;  // input activation (padded NHWC)
+  int Hp, Wp, P, H, W, Cin;
+  const float* w;     // [taps][Cin][CoutPad]
+  const float* bias;  // [CoutPad] (zeros beyond Cout) or nullptr
+  int taps, dil, Cout, CoutPad, stride;
+  int Ho, Wo;
+  float* y;  // destination padded NHWC (interior written) or nullptr
+  int yHp, yWp, yP, yC, yCoff;
+  const float* add;  // optional addend with the output's logical size (skip connections)
+  int aHp, aWp, aP, aC;
+  float* nchw;  // optional second destination [B][Cout][Ho][Wo]
+  int act;
+  float slope;
+  double* stats;  // optional [B][Cout][2] (sum, sum of squares) of the stored values
+};
+
+void launch_conv_simt(const ConvParams& p, int B, cudaStream_t s);
+
+// ---- elementwise gather: InstanceNorm apply / PReLU / pad / up / sub / residual ----------------
+struct XformParams {
+  const float* src;
+  int sH, sW, sP, sC, sCoff;
+  float* dst;
+  int dH, dW, dP, dC, dCoff;
+  int C;
+  int pad_mode, up, sub, rowpad;
+  const double* stats;  // [B][C][2] or nullptr (no normalisation)
+  double count;
+  float eps;
+  const float* scale;  // per-channel multiplier or nullptr
+  const float* res;    // residual (padded NHWC, same logical size as dst) or nullptr
+  int rP, rC;
+  int act;  // 0 none, 1 relu, 2 prelu(slope)
+  float slope;
+};
+void launch_xform(const XformParams& p, int B, cudaStream_t s);
+
+// ---- per-pixel channel L2 normalisation (feature_normalize, theta/phi) --------------------------
+struct PixNormParams {
+  const float* src;
+  int sH, sW, sP, sC;
+  float* dst;
+  int dP, dC;  // destination has the same logical HxW
+  int C, pad_mode;
+  const double* stats;  // optional channel sums [B][C][2] -> subtract mean over positions
+  double count;
+  float eps;
+};
+void launch_pixnorm(const PixNormParams& p, int B, cudaStream_t s);
+
+// ---- small layout / helper kernels -------------------------------------------------------------
+// NCHW [B][Cs][H][W] -> padded NHWC with C channels (extra channels zero); mode: 0 copy,
+// 1 rgb -> vgg_preprocess (util.py:347-352), 2 centred L -> gray -> vgg_preprocess (util.py:97-101),
+// 3 centred Lab -> sRGB (util.py:379-414) -> vgg_preprocess
+void launch_nchw_to_act(const float* src, int Cs, float* dst, int B, int H, int W, int C, int P, int pad_mode,
+                        int mode, cudaStream_t s);
+void launch_act_to_nchw(const float* src, int H, int W, int P, int sC, int sCoff, int C, float* dst, int B,
+                        cudaStream_t s);
+void launch_maxpool2(const float* src, int sH, int sW, int sP, int C, float* dst, int dP, int B, cudaStream_t s);
+// NCHW [B][3][H][W] -> V [B][H/4*W/4][4] (4th lane zero): F.avg_pool2d(.,4), NonlocalNet.py:491-493
+void launch_avgpool4_lab(const float* src, float* V, int B, int H, int W, cudaStream_t s);
+// y rows [B][N][4], sim rows [B][N] at h x w -> nearest x4 NCHW (NonlocalNet.py:499-500)
+void launch_rows_to_nchw_up4(const float* yrows, const float* simrows, float* y, float* sim, int B, int h, int w,
+                             cudaStream_t s);
+// ColorVidNet input (FrameColor.py:64): [L, warped a, warped b, sim, last L, last a, last b, 0]
+void launch_build_color_input(const float* IA_l, const float* yrows, const float* simrows, const float* last_lab,
+                              float* dst, int B, int H, int W, int P, cudaStream_t s);
+// conv10_ab (1x1, 128 -> 2) + tanh * 128 (ColorVidNet.py:143-144) -> NCHW [B][2][H][W]
+void launch_final_ab(const float* x, int H, int W, int P, int C, const float* w /*[2][C]*/, const float* bias,
+                     float* out, int B, cudaStream_t s);
+// next frame's "last" = cat(L, ab) (test.py:96)
+void launch_make_last(const float* IA_l, const float* ab, float* last, int B, int H, int W, cudaStream_t s);
+
+// ---- correlation + softmax + warp (K7) ----------------------------------------------------------
+struct CorrParams {
+  const float* theta;  // [B][NA][C]  (position-major, channels contiguous)
+  const float* phi;    // [Bphi][NB][C]
+  const float* V;      // [Bphi][NB][4]
+  int B, Bphi, NA, NB, C;
+  float temperature;
+  float* y;     // [B][NA][4]
+  float* sim;   // [B][NA]
+  int* argmax;  // [B][NA] or nullptr
+};
+void launch_corr_simt(const CorrParams& p, cudaStream_t s);
+// [B][C][N] -> [B][N][C] and back (the C ABI of the stand-alone correlation entry is channel-major)
+void launch_transpose_cn(const float* src, float* dst, int B, int C, int N, cudaStream_t s);
+
+int64_t launch_counter_add(int64_t n);  // global launch counter (introspection)
+
+}  // namespace dvc

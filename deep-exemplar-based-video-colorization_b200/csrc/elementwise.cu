@@ -1,0 +1,480 @@
+// HBM-bound helper kernels around the GEMM-shaped ones: InstanceNorm apply / PReLU / padding /
+// nearest up-sampling / stride-2 pick / residual add (one gather kernel), per-pixel channel
+// normalisation, max-pool, layout conversion at the NCHW boundary, colour-space prologue.
+// All are coalesced over the channel (innermost) dimension with 128-bit accesses.
+#include <math.h>
+
+#include "dvc_internal.cuh"
+
+namespace dvc {
+
+namespace {
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// ------------------------------------------------------------------------------------ xform
+// dst-driven gather.  grid.y = image, grid.x covers (padded dst pixels) x (C/4) float4 lanes.
+__global__ void __launch_bounds__(256) xform_kernel(const XformParams p) {
+  extern __shared__ float sm[];  // mean[C], rstd[C] when normalising
+  const int b = blockIdx.y;
+  float* s_mean = sm;
+  float* s_rstd = sm + p.C;
+  if (p.stats) {
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      const double su = p.stats[((size_t)b * p.C + c) * 2 + 0];
+      const double sq = p.stats[((size_t)b * p.C + c) * 2 + 1];
+      const double mean = su / p.count;
+      double var = sq / p.count - mean * mean;  // biased variance, F.instance_norm
+      if (var < 0) var = 0;
+      s_mean[c] = (float)mean;
+      s_rstd[c] = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
+    __syncthreads();
+  }
+  const int dHp = p.dH + 2 * p.dP, dWp = p.dW + 2 * p.dP;
+  const int sWp = p.sW + 2 * p.sP, sHp = p.sH + 2 * p.sP;
+  const int c4n = p.C >> 2;
+  const long total = (long)dHp * dWp * c4n;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c4n) * 4;
+    const int pix = (int)(idx / c4n);
+    const int yp = pix / dWp, xp = pix - yp * dWp;
+    int y = yp - p.dP, x = xp - p.dP;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool inside = (y >= 0 && y < p.dH && x >= 0 && x < p.dW);
+    if (!inside && p.pad_mode == PAD_REFLECT) {
+      y = reflect_idx(y, p.dH);
+      x = reflect_idx(x, p.dW);
+      inside = true;
+    }
+    if (inside) {
+      int y1 = y;
+      if (p.rowpad) y1 = min(max(y - 1, 0), p.dH - 3);
+      const int ys = (y1 / p.up) * p.sub, xs = (x / p.up) * p.sub;
+      v = __ldg(reinterpret_cast<const float4*>(
+          p.src + (((size_t)b * sHp + ys + p.sP) * sWp + xs + p.sP) * p.sC + p.sCoff + c));
+      if (p.stats) {
+        v.x = (v.x - s_mean[c + 0]) * s_rstd[c + 0];
+        v.y = (v.y - s_mean[c + 1]) * s_rstd[c + 1];
+        v.z = (v.z - s_mean[c + 2]) * s_rstd[c + 2];
+        v.w = (v.w - s_mean[c + 3]) * s_rstd[c + 3];
+      }
+      if (p.scale) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+        v.x *= sc.x, v.y *= sc.y, v.z *= sc.z, v.w *= sc.w;
+      }
+      if (p.res) {
+        const int rHp = p.dH + 2 * p.rP, rWp = p.dW + 2 * p.rP;
+        const float4 r = __ldg(reinterpret_cast<const float4*>(
+            p.res + (((size_t)b * rHp + y + p.rP) * rWp + x + p.rP) * p.rC + c));
+        v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
+      }
+      if (p.act == 1) {
+        v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+      } else if (p.act == 2) {
+        v.x = v.x > 0.f ? v.x : v.x * p.slope;
+        v.y = v.y > 0.f ? v.y : v.y * p.slope;
+        v.z = v.z > 0.f ? v.z : v.z * p.slope;
+        v.w = v.w > 0.f ? v.w : v.w * p.slope;
+      }
+    }
+    *reinterpret_cast<float4*>(p.dst + (((size_t)b * dHp + yp) * dWp + xp) * p.dC + p.dCoff + c) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------ pixnorm
+// One warp per destination (padded) pixel: out = (v - mean_c) / (||v - mean||_2 + eps).
+template <int VPL>  // float4 per lane: C = 128 * VPL
+__global__ void __launch_bounds__(256) pixnorm_kernel(const PixNormParams p) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int dHp = p.sH + 2 * p.dP, dWp = p.sW + 2 * p.dP;
+  const int sHp = p.sH + 2 * p.sP, sWp = p.sW + 2 * p.sP;
+  const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+  float4 mean[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    mean[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.stats) {
+      const int c = (i * 32 + lane) * 4;
+      const double* st = p.stats + ((size_t)b * p.C + c) * 2;
+      mean[i] = make_float4((float)(st[0] / p.count), (float)(st[2] / p.count), (float)(st[4] / p.count),
+                            (float)(st[6] / p.count));
+    }
+  }
+  for (int pix = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < dHp * dWp; pix += warps_per_grid) {
+    const int yp = pix / dWp, xp = pix - yp * dWp;
+    int y = yp - p.dP, x = xp - p.dP;
+    bool inside = (y >= 0 && y < p.sH && x >= 0 && x < p.sW);
+    if (!inside && p.pad_mode == PAD_REFLECT) {
+      y = reflect_idx(y, p.sH);
+      x = reflect_idx(x, p.sW);
+      inside = true;
+    }
+    float4 v[VPL];
+    float ss = 0.f;
+    const float* sp = p.src + (((size_t)b * sHp + y + p.sP) * sWp + x + p.sP) * p.sC;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (inside) {
+        v[i] = __ldg(reinterpret_cast<const float4*>(sp + (i * 32 + lane) * 4));
+        v[i].x -= mean[i].x, v[i].y -= mean[i].y, v[i].z -= mean[i].z, v[i].w -= mean[i].w;
+      } else {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = 1.0f / (sqrtf(ss) + p.eps);
+    float* dp = p.dst + (((size_t)b * dHp + yp) * dWp + xp) * p.dC;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      // true division like torch.div(x, norm) (util.py:157, NonlocalNet.py:471)
+      const float n = sqrtf(ss) + p.eps;
+      float4 o4 = make_float4(v[i].x / n, v[i].y / n, v[i].z / n, v[i].w / n);
+      (void)inv;
+      *reinterpret_cast<float4*>(dp + (i * 32 + lane) * 4) = o4;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ colour prologue
+__device__ __forceinline__ float3 lab_to_srgb(float L, float a, float bb) {
+  // util.py:379-414 (L un-centred)
+  float fy = (L + 16.0f) / 116.0f;
+  float fx = a / 500.0f + fy;
+  float fz = fy - bb / 200.0f;
+  if (fz < 0.f) fz = 0.f;
+  float f[3] = {fx, fy, fz};
+  float lin[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) lin[i] = f[i] > 0.2068966f ? powf(f[i], 3.0f) : (f[i] - 16.0f / 116.0f) / 7.787f;
+  lin[0] *= 0.95047f;
+  lin[2] *= 1.08883f;
+  const float m[3][3] = {{3.24048134f, -0.96925495f, 0.05564664f},
+                         {-1.53715152f, 1.87599f, -0.20404134f},
+                         {-0.49853633f, 0.04155593f, 1.05731107f}};
+  float rgb[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float r = lin[0] * m[0][j];
+    r = fmaf(lin[1], m[1][j], r);
+    r = fmaf(lin[2], m[2][j], r);
+    r = r > 0.0031308f ? 1.055f * powf(r, 1.0f / 2.4f) - 0.055f : r * 12.92f;
+    rgb[j] = fminf(fmaxf(r, 0.f), 1.f);
+  }
+  return make_float3(rgb[0], rgb[1], rgb[2]);
+}
+
+__global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restrict__ src, int Cs, float* __restrict__ dst,
+                                                          int H, int W, int C, int P, int pad_mode, int mode) {
+  const int b = blockIdx.y;
+  const int Hp = H + 2 * P, Wp = W + 2 * P;
+  const size_t plane = (size_t)H * W;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < Hp * Wp; pix += gridDim.x * blockDim.x) {
+    const int yp = pix / Wp, xp = pix - yp * Wp;
+    int y = yp - P, x = xp - P;
+    bool inside = (y >= 0 && y < H && x >= 0 && x < W);
+    if (!inside && pad_mode == PAD_REFLECT) {
+      y = reflect_idx(y, H), x = reflect_idx(x, W);
+      inside = true;
+    }
+    float* dp = dst + ((size_t)b * Hp * Wp + pix) * C;
+    if (!inside) {
+      for (int c = 0; c < C; ++c) dp[c] = 0.f;
+      continue;
+    }
+    const float* sp = src + (size_t)b * Cs * plane + (size_t)y * W + x;
+    if (mode == 0) {
+      for (int c = 0; c < C; ++c) dp[c] = c < Cs ? __ldg(sp + c * plane) : 0.f;
+    } else {
+      float3 rgb;
+      if (mode == 1) {
+        rgb = make_float3(__ldg(sp), __ldg(sp + plane), __ldg(sp + 2 * plane));
+      } else if (mode == 2) {
+        const float g = (__ldg(sp) * 1.0f + 50.0f) / 100.0f;  // util.py:63,97-101
+        rgb = make_float3(g, g, g);
+      } else {
+        rgb = lab_to_srgb(__ldg(sp) + 50.0f, __ldg(sp + plane), __ldg(sp + 2 * plane));
+      }
+      // util.py:347-352: BGR order, minus mean, times 255
+      dp[0] = (rgb.z - 0.40760392f) * 255.f;
+      dp[1] = (rgb.y - 0.45795686f) * 255.f;
+      dp[2] = (rgb.x - 0.48501961f) * 255.f;
+      for (int c = 3; c < C; ++c) dp[c] = 0.f;
+    }
+  }
+}
+
+// interior of a padded NHWC activation -> NCHW.  One block = 32 pixels x 32 channels via smem transpose.
+__global__ void __launch_bounds__(256) act_to_nchw_kernel(const float* __restrict__ src, int H, int W, int P, int sC,
+                                                          int sCoff, int C, float* __restrict__ dst) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const int Hp = H + 2 * P, Wp = W + 2 * P;
+  const int pix0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
+  for (int r = ty; r < 32; r += 8) {
+    const int pix = pix0 + r;
+    float v = 0.f;
+    if (pix < H * W && c0 + tx < C) {
+      const int y = pix / W, x = pix - y * W;
+      v = __ldg(src + (((size_t)b * Hp + y + P) * Wp + x + P) * sC + sCoff + c0 + tx);
+    }
+    t[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, pix = pix0 + tx;
+    if (c < C && pix < H * W) dst[((size_t)b * C + c) * H * W + pix] = t[tx][r];
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__ src, int sH, int sW, int sP, int C,
+                                                       float* __restrict__ dst, int dP) {
+  const int b = blockIdx.y;
+  const int dH = sH / 2, dW = sW / 2;
+  const int dHp = dH + 2 * dP, dWp = dW + 2 * dP, sHp = sH + 2 * sP, sWp = sW + 2 * sP;
+  const int c4n = C >> 2;
+  const long total = (long)dHp * dWp * c4n;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c4n) * 4;
+    const int pix = (int)(idx / c4n);
+    const int yp = pix / dWp, xp = pix - yp * dWp;
+    const int y = yp - dP, x = xp - dP;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y >= 0 && y < dH && x >= 0 && x < dW) {
+      const float* sp = src + (((size_t)b * sHp + 2 * y + sP) * sWp + 2 * x + sP) * C + c;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(sp));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(sp + C));
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(sp + (size_t)sWp * C));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(sp + (size_t)sWp * C + C));
+      v.x = fmaxf(fmaxf(a.x, b4.x), fmaxf(c4.x, d.x));
+      v.y = fmaxf(fmaxf(a.y, b4.y), fmaxf(c4.y, d.y));
+      v.z = fmaxf(fmaxf(a.z, b4.z), fmaxf(c4.z, d.z));
+      v.w = fmaxf(fmaxf(a.w, b4.w), fmaxf(c4.w, d.w));
+    }
+    *reinterpret_cast<float4*>(dst + ((size_t)b * dHp * dWp + pix) * C + c) = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) avgpool4_lab_kernel(const float* __restrict__ src, float* __restrict__ V, int H,
+                                                           int W) {
+  const int b = blockIdx.y;
+  const int h = H / 4, w = W / 4;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < h * w; n += gridDim.x * blockDim.x) {
+    const int i = n / w, j = n - i * w;
+    float o[3];
+    for (int c = 0; c < 3; ++c) {
+      const float* sp = src + ((size_t)b * 3 + c) * H * W + (size_t)(4 * i) * W + 4 * j;
+      float s = 0.f;
+      for (int dy = 0; dy < 4; ++dy)
+        for (int dx = 0; dx < 4; ++dx) s += __ldg(sp + dy * W + dx);
+      o[c] = s * (1.0f / 16.0f);
+    }
+    *reinterpret_cast<float4*>(V + ((size_t)b * h * w + n) * 4) = make_float4(o[0], o[1], o[2], 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) rows_to_nchw_up4_kernel(const float* __restrict__ yrows,
+                                                               const float* __restrict__ simrows, float* __restrict__ y,
+                                                               float* __restrict__ sim, int h, int w) {
+  const int b = blockIdx.y;
+  const int H = 4 * h, W = 4 * w;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < H * W; pix += gridDim.x * blockDim.x) {
+    const int i = pix / W, j = pix - i * W;
+    const int n = (i >> 2) * w + (j >> 2);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(yrows + ((size_t)b * h * w + n) * 4));
+    if (y) {
+      y[((size_t)b * 3 + 0) * H * W + pix] = v.x;
+      y[((size_t)b * 3 + 1) * H * W + pix] = v.y;
+      y[((size_t)b * 3 + 2) * H * W + pix] = v.z;
+    }
+    if (sim) sim[(size_t)b * H * W + pix] = __ldg(simrows + (size_t)b * h * w + n);
+  }
+}
+
+__global__ void __launch_bounds__(256) build_color_input_kernel(const float* __restrict__ IA_l,
+                                                                const float* __restrict__ yrows,
+                                                                const float* __restrict__ simrows,
+                                                                const float* __restrict__ last, float* __restrict__ dst,
+                                                                int H, int W, int P) {
+  const int b = blockIdx.y;
+  const int Hp = H + 2 * P, Wp = W + 2 * P;
+  const int h = H / 4, w = W / 4;
+  const size_t plane = (size_t)H * W;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < Hp * Wp; pix += gridDim.x * blockDim.x) {
+    const int yp = pix / Wp, xp = pix - yp * Wp;
+    const int y = yp - P, x = xp - P;
+    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const size_t q = (size_t)y * W + x;
+      const int n = (y >> 2) * w + (x >> 2);
+      const float4 yr = __ldg(reinterpret_cast<const float4*>(yrows + ((size_t)b * h * w + n) * 4));
+      o0.x = __ldg(IA_l + (size_t)b * plane + q);
+      o0.y = yr.y;  // warped a (channel 1 of the warped Lab, FrameColor.py:63)
+      o0.z = yr.z;  // warped b
+      o0.w = __ldg(simrows + (size_t)b * h * w + n);
+      o1.x = __ldg(last + ((size_t)b * 3 + 0) * plane + q);
+      o1.y = __ldg(last + ((size_t)b * 3 + 1) * plane + q);
+      o1.z = __ldg(last + ((size_t)b * 3 + 2) * plane + q);
+    }
+    float4* dp = reinterpret_cast<float4*>(dst + ((size_t)b * Hp * Wp + pix) * 8);
+    dp[0] = o0;
+    dp[1] = o1;
+  }
+}
+
+// warp per pixel: 1x1 conv C -> 2, tanh * 128
+__global__ void __launch_bounds__(256) final_ab_kernel(const float* __restrict__ x, int H, int W, int P, int C,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int Hp = H + 2 * P, Wp = W + 2 * P;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  const int nv = C / 128;  // float4 per lane (C = 128 -> 1)
+  for (int pix = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < H * W; pix += warps) {
+    const int y = pix / W, xx = pix - y * W;
+    const float* sp = x + (((size_t)b * Hp + y + P) * Wp + xx + P) * C;
+    float s0 = 0.f, s1 = 0.f;
+    for (int i = 0; i < nv; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(sp + c));
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + C + c));
+      s0 += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
+      s1 += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane == 0) {
+      out[((size_t)b * 2 + 0) * H * W + pix] = tanhf(s0 + bias[0]) * 128.f;
+      out[((size_t)b * 2 + 1) * H * W + pix] = tanhf(s1 + bias[1]) * 128.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) make_last_kernel(const float* __restrict__ IA_l, const float* __restrict__ ab,
+                                                        float* __restrict__ last, int HW) {
+  const int b = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    last[((size_t)b * 3 + 0) * HW + i] = IA_l[(size_t)b * HW + i];
+    last[((size_t)b * 3 + 1) * HW + i] = ab[((size_t)b * 2 + 0) * HW + i];
+    last[((size_t)b * 3 + 2) * HW + i] = ab[((size_t)b * 2 + 1) * HW + i];
+  }
+}
+
+__global__ void __launch_bounds__(256) transpose_cn_kernel(const float* __restrict__ src, float* __restrict__ dst, int R,
+                                                           int Cc) {
+  // src [b][R][Cc] -> dst [b][Cc][R]
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8)
+    t[r][tx] = (r0 + r < R && c0 + tx < Cc) ? src[((size_t)b * R + r0 + r) * Cc + c0 + tx] : 0.f;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (c0 + r < Cc && r0 + tx < R) dst[((size_t)b * Cc + c0 + r) * R + r0 + tx] = t[tx][r];
+}
+
+inline int grid_for(long total, int threads, int cap = 148 * 16) {
+  long g = (total + threads - 1) / threads;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+void launch_xform(const XformParams& p, int B, cudaStream_t s) {
+  const long total = (long)(p.dH + 2 * p.dP) * (p.dW + 2 * p.dP) * (p.C / 4);
+  dim3 grid(grid_for(total, 256), B);
+  const size_t sm = p.stats ? 2 * p.C * sizeof(float) : 0;
+  xform_kernel<<<grid, 256, sm, s>>>(p);
+  launch_counter_add(1);
+}
+
+void launch_pixnorm(const PixNormParams& p, int B, cudaStream_t s) {
+  const long pix = (long)(p.sH + 2 * p.dP) * (p.sW + 2 * p.dP);
+  dim3 grid(grid_for(pix, 8), B);
+  switch (p.C) {
+    case 128: pixnorm_kernel<1><<<grid, 256, 0, s>>>(p); break;
+    case 256: pixnorm_kernel<2><<<grid, 256, 0, s>>>(p); break;
+    case 512: pixnorm_kernel<4><<<grid, 256, 0, s>>>(p); break;
+    default: break;  // validated by the caller
+  }
+  launch_counter_add(1);
+}
+
+void launch_nchw_to_act(const float* src, int Cs, float* dst, int B, int H, int W, int C, int P, int pad_mode,
+                        int mode, cudaStream_t s) {
+  dim3 grid(grid_for((long)(H + 2 * P) * (W + 2 * P), 256), B);
+  nchw_to_act_kernel<<<grid, 256, 0, s>>>(src, Cs, dst, H, W, C, P, pad_mode, mode);
+  launch_counter_add(1);
+}
+
+void launch_act_to_nchw(const float* src, int H, int W, int P, int sC, int sCoff, int C, float* dst, int B,
+                        cudaStream_t s) {
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
+  act_to_nchw_kernel<<<grid, 256, 0, s>>>(src, H, W, P, sC, sCoff, C, dst);
+  launch_counter_add(1);
+}
+
+void launch_maxpool2(const float* src, int sH, int sW, int sP, int C, float* dst, int dP, int B, cudaStream_t s) {
+  const long total = (long)(sH / 2 + 2 * dP) * (sW / 2 + 2 * dP) * (C / 4);
+  dim3 grid(grid_for(total, 256), B);
+  maxpool2_kernel<<<grid, 256, 0, s>>>(src, sH, sW, sP, C, dst, dP);
+  launch_counter_add(1);
+}
+
+void launch_avgpool4_lab(const float* src, float* V, int B, int H, int W, cudaStream_t s) {
+  dim3 grid(grid_for((long)(H / 4) * (W / 4), 256), B);
+  avgpool4_lab_kernel<<<grid, 256, 0, s>>>(src, V, H, W);
+  launch_counter_add(1);
+}
+
+void launch_rows_to_nchw_up4(const float* yrows, const float* simrows, float* y, float* sim, int B, int h, int w,
+                             cudaStream_t s) {
+  dim3 grid(grid_for((long)16 * h * w, 256), B);
+  rows_to_nchw_up4_kernel<<<grid, 256, 0, s>>>(yrows, simrows, y, sim, h, w);
+  launch_counter_add(1);
+}
+
+void launch_build_color_input(const float* IA_l, const float* yrows, const float* simrows, const float* last_lab,
+                              float* dst, int B, int H, int W, int P, cudaStream_t s) {
+  dim3 grid(grid_for((long)(H + 2 * P) * (W + 2 * P), 256), B);
+  build_color_input_kernel<<<grid, 256, 0, s>>>(IA_l, yrows, simrows, last_lab, dst, H, W, P);
+  launch_counter_add(1);
+}
+
+void launch_final_ab(const float* x, int H, int W, int P, int C, const float* w, const float* bias, float* out, int B,
+                     cudaStream_t s) {
+  dim3 grid(grid_for((long)H * W, 8), B);
+  final_ab_kernel<<<grid, 256, 0, s>>>(x, H, W, P, C, w, bias, out);
+  launch_counter_add(1);
+}
+
+void launch_make_last(const float* IA_l, const float* ab, float* last, int B, int H, int W, cudaStream_t s) {
+  dim3 grid(grid_for((long)H * W, 256), B);
+  make_last_kernel<<<grid, 256, 0, s>>>(IA_l, ab, last, H * W);
+  launch_counter_add(1);
+}
+
+void launch_transpose_cn(const float* src, float* dst, int B, int R, int Cc, cudaStream_t s) {
+  // src [B][R][Cc] -> dst [B][Cc][R]
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, B);
+  transpose_cn_kernel<<<grid, 256, 0, s>>>(src, dst, R, Cc);
+  launch_counter_add(1);
+}
+
+}  // namespace dvc

@@ -1,0 +1,279 @@
+"""ctypes binding of libdvc.so (include/dvc.h) -- the only way Python reaches the CUDA kernels.
+
+PyTorch is used for device memory, streams and torch.distributed; every FLOP of the hot path runs
+in hand-written sm_100a kernels inside libdvc.so.  There is no CPU fallback and no torch fallback:
+if the library or a CUDA device is missing, every entry point raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdvc.so")
+
+NET_VGG, NET_WARP, NET_COLOR = 0, 1, 2
+MATH_FP32, MATH_TF32X3, MATH_BF16X3 = 0, 1, 2
+
+EXPORTED = [
+    "dvc_create", "dvc_destroy", "dvc_last_error", "dvc_version", "dvc_set_math", "dvc_set_weight",
+    "dvc_vgg19_forward", "dvc_warpnet_forward", "dvc_colorvidnet_forward", "dvc_corr_softmax_warp",
+    "dvc_set_exemplar", "dvc_colorize_frames", "dvc_colorize_clip", "dvc_exemplar_pack_size",
+    "dvc_exemplar_export", "dvc_exemplar_import", "dvc_launch_count", "dvc_profile_corr", "dvc_corr_mean_ms",
+]
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class DvcError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libdvc.so and declare the prototypes of include/dvc.h.  Fails loudly if it is not built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise DvcError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no fallback implementation)")
+        lib = ctypes.CDLL(LIB_PATH)
+        c_void, c_int, c_float, c_i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int64
+        P = ctypes.POINTER
+        lib.dvc_create.argtypes = [P(c_void), c_int]
+        lib.dvc_destroy.argtypes = [c_void]
+        lib.dvc_last_error.argtypes = [c_void]
+        lib.dvc_last_error.restype = ctypes.c_char_p
+        lib.dvc_version.restype = ctypes.c_char_p
+        lib.dvc_set_math.argtypes = [c_void, c_int, c_int]
+        lib.dvc_set_weight.argtypes = [c_void, c_int, ctypes.c_char_p, c_void, P(c_i64), c_int]
+        lib.dvc_vgg19_forward.argtypes = [c_void, c_void, c_int, c_int, c_int, c_int, P(ctypes.c_char_p), P(c_void),
+                                          c_int, c_void]
+        lib.dvc_warpnet_forward.argtypes = [c_void, c_void, P(c_void), P(c_void), c_int, c_int, c_int, c_float, c_float,
+                                            c_int, c_void, c_void, c_void]
+        lib.dvc_colorvidnet_forward.argtypes = [c_void, c_void, c_int, c_int, c_int, c_void, c_void]
+        lib.dvc_corr_softmax_warp.argtypes = [c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_int, c_int, c_float,
+                                              c_void, c_void, c_void, c_void]
+        lib.dvc_set_exemplar.argtypes = [c_void, c_void, c_int, c_int, c_void]
+        lib.dvc_colorize_frames.argtypes = [c_void, c_void, c_void, c_int, c_int, c_int, c_float, c_void, c_void, c_void,
+                                            c_void]
+        lib.dvc_colorize_clip.argtypes = [c_void, c_void, c_int, c_int, c_int, c_float, c_void, c_void, c_void]
+        lib.dvc_exemplar_pack_size.argtypes = [c_void, c_int, c_int]
+        lib.dvc_exemplar_pack_size.restype = c_i64
+        lib.dvc_exemplar_export.argtypes = [c_void, c_void, c_i64, c_void]
+        lib.dvc_exemplar_import.argtypes = [c_void, c_void, c_i64, c_int, c_int, c_void]
+        lib.dvc_launch_count.argtypes = [c_void, c_int]
+        lib.dvc_launch_count.restype = c_i64
+        lib.dvc_profile_corr.argtypes = [c_void, c_int]
+        lib.dvc_corr_mean_ms.argtypes = [c_void, c_int]
+        lib.dvc_corr_mean_ms.restype = ctypes.c_double
+        _lib = lib
+        return lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dev_f32(t, what):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise DvcError(f"{what}: expected a CUDA tensor (libdvc has no CPU path)")
+    if t.dtype != torch.float32:
+        raise DvcError(f"{what}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+class Context:
+    """One dvc_ctx per CUDA device; owns the weights of all three networks and all workspaces."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise DvcError("no CUDA device visible: libdvc has no CPU fallback")
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        h = ctypes.c_void_p(0)
+        rc = self.lib.dvc_create(ctypes.byref(h), self.device.index)
+        if rc != 0:
+            raise DvcError(f"dvc_create failed ({rc}): {self.lib.dvc_last_error(None).decode()}")
+        self.h = h
+        self._weight_sig = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dvc_destroy(self.h)
+            self.h = None
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise DvcError(f"{what} failed ({rc}): {self.lib.dvc_last_error(self.h).decode()}")
+
+    # ---- configuration / weights -------------------------------------------------------------
+    def set_math(self, conv=MATH_FP32, corr=MATH_FP32):
+        self._check(self.lib.dvc_set_math(self.h, conv, corr), "dvc_set_math")
+
+    def set_weights(self, net, state_dict):
+        """Replaces load_state_dict (test.py:150,158-159) for `net` in {NET_VGG, NET_WARP, NET_COLOR}."""
+        for key, t in state_dict.items():
+            t = t.detach().to(torch.float32).contiguous()
+            shape = (ctypes.c_int64 * t.dim())(*t.shape)
+            self._check(self.lib.dvc_set_weight(self.h, net, key.encode(), _ptr(t), shape, t.dim()),
+                        f"dvc_set_weight({key})")
+
+    def sync_module_weights(self, net, module):
+        """Push a drop-in module's parameters when they changed (load_state_dict / .cuda() / in-place edit)."""
+        sd = module.state_dict()
+        sig = tuple((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in sd.items())
+        if self._weight_sig.get(net) != sig:
+            self.set_weights(net, sd)
+            self._weight_sig[net] = sig
+
+    # ---- module-level drop-ins -----------------------------------------------------------------
+    def vgg19_forward(self, x, out_keys, preprocess=True):
+        x = _dev_f32(x, "VGG19 input")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise DvcError("VGG19 input must be [B,3,H,W]")
+        B, _, H, W = x.shape
+        dims = {}
+        h, w = H, W
+        chans = [64, 128, 256, 512, 512]
+        nconv = [2, 2, 4, 4, 4]
+        for blk in range(5):
+            for i in range(nconv[blk]):
+                dims[f"r{blk + 1}{i + 1}"] = (chans[blk], h, w)
+            h, w = h // 2, w // 2
+            dims[f"p{blk + 1}"] = (chans[blk], h, w)
+        outs = []
+        for k in out_keys:
+            if k not in dims:
+                raise DvcError(f"unknown VGG key {k!r}")
+            c, hh, ww = dims[k]
+            outs.append(torch.empty(B, c, hh, ww, device=x.device, dtype=torch.float32))
+        keys = (ctypes.c_char_p * len(out_keys))(*[k.encode() for k in out_keys])
+        ptrs = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        rc = self.lib.dvc_vgg19_forward(self.h, _ptr(x), B, H, W, 1 if preprocess else 0, keys, ptrs, len(outs),
+                                        _stream(x.device))
+        self._check(rc, "dvc_vgg19_forward")
+        return outs
+
+    def warpnet_forward(self, B_lab_map, A_feats, B_feats, temperature, wta_scale_weight=1.0, reuse_exemplar=False):
+        B_lab_map = _dev_f32(B_lab_map, "B_lab_map")
+        A = [_dev_f32(t, "A feature") for t in A_feats]
+        Bf = [_dev_f32(t, "B feature") for t in B_feats]
+        Bn, ch, H, W = B_lab_map.shape
+        if ch != 3:
+            raise DvcError("B_lab_map must have 3 channels")
+        y = torch.empty(Bn, 3, H, W, device=B_lab_map.device, dtype=torch.float32)
+        sim = torch.empty(Bn, 1, H, W, device=B_lab_map.device, dtype=torch.float32)
+        pa = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in A])
+        pb = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in Bf])
+        rc = self.lib.dvc_warpnet_forward(self.h, _ptr(B_lab_map), pa, pb, Bn, H, W, float(temperature),
+                                          float(wta_scale_weight), 1 if reuse_exemplar else 0, _ptr(y), _ptr(sim),
+                                          _stream(B_lab_map.device))
+        self._check(rc, "dvc_warpnet_forward")
+        return y, sim
+
+    def colorvidnet_forward(self, x):
+        x = _dev_f32(x, "ColorVidNet input")
+        if x.dim() != 4 or x.shape[1] != 7:
+            raise DvcError("ColorVidNet input must be [B,7,H,W]")
+        B, _, H, W = x.shape
+        out = torch.empty(B, 2, H, W, device=x.device, dtype=torch.float32)
+        self._check(self.lib.dvc_colorvidnet_forward(self.h, _ptr(x), B, H, W, _ptr(out), _stream(x.device)),
+                    "dvc_colorvidnet_forward")
+        return out
+
+    def corr_softmax_warp(self, theta_hat, phi_hat, V, temperature, want_argmax=False):
+        """theta_hat [B,C,NA], phi_hat [Bphi,C,NB], V [Bphi,NB,3] -> y [B,NA,3], sim [B,NA] (, argmax)."""
+        theta_hat, phi_hat, V = _dev_f32(theta_hat, "theta_hat"), _dev_f32(phi_hat, "phi_hat"), _dev_f32(V, "V")
+        B, C, NA = theta_hat.shape
+        Bphi, _, NB = phi_hat.shape
+        y = torch.empty(B, NA, 3, device=theta_hat.device, dtype=torch.float32)
+        sim = torch.empty(B, NA, device=theta_hat.device, dtype=torch.float32)
+        am = torch.empty(B, NA, device=theta_hat.device, dtype=torch.int32) if want_argmax else None
+        rc = self.lib.dvc_corr_softmax_warp(self.h, _ptr(theta_hat), _ptr(phi_hat), _ptr(V), B, Bphi, NA, NB, C,
+                                            float(temperature), _ptr(y), _ptr(sim), _ptr(am), _stream(theta_hat.device))
+        self._check(rc, "dvc_corr_softmax_warp")
+        return (y, sim, am) if want_argmax else (y, sim)
+
+    # ---- fused per-frame / per-clip path ---------------------------------------------------------
+    def set_exemplar(self, IB_lab):
+        t = IB_lab.detach().to(torch.float32).contiguous()
+        if t.dim() != 4 or t.shape[0] != 1 or t.shape[1] != 3:
+            raise DvcError("exemplar must be [1,3,H,W]")
+        self._check(self.lib.dvc_set_exemplar(self.h, _ptr(t), t.shape[2], t.shape[3], _stream(self.device)),
+                    "dvc_set_exemplar")
+        if not t.is_cuda:
+            torch.cuda.current_stream(self.device).synchronize()  # the host buffer must outlive the async copy
+
+    def colorize_frames(self, IA_l, IA_last_lab, temperature=1e-10, want_warp=False):
+        IA_l, IA_last_lab = _dev_f32(IA_l, "IA_l"), _dev_f32(IA_last_lab, "IA_last_lab")
+        B, c1, H, W = IA_l.shape
+        if c1 != 1 or tuple(IA_last_lab.shape) != (B, 3, H, W):
+            raise DvcError("IA_l must be [B,1,H,W] and IA_last_lab [B,3,H,W]")
+        ab = torch.empty(B, 2, H, W, device=IA_l.device, dtype=torch.float32)
+        warp = torch.empty(B, 3, H, W, device=IA_l.device, dtype=torch.float32) if want_warp else None
+        sim = torch.empty(B, 1, H, W, device=IA_l.device, dtype=torch.float32) if want_warp else None
+        rc = self.lib.dvc_colorize_frames(self.h, _ptr(IA_l), _ptr(IA_last_lab), B, H, W, float(temperature), _ptr(ab),
+                                          _ptr(warp), _ptr(sim), _stream(IA_l.device))
+        self._check(rc, "dvc_colorize_frames")
+        return (ab, warp, sim) if want_warp else ab
+
+    def colorize_clip(self, host_L, temperature=1e-10, first_last_lab=None, out=None):
+        """host_L: pinned CPU [F,1,H,W] -> pinned CPU [F,2,H,W]; recurrence of test.py:76-96 kept on the device."""
+        if host_L.is_cuda or host_L.dtype != torch.float32:
+            raise DvcError("colorize_clip takes a float32 CPU tensor (pinned for full copy overlap)")
+        host_L = host_L.contiguous()
+        F_, c1, H, W = host_L.shape
+        if out is None:
+            out = torch.empty(F_, 2, H, W, dtype=torch.float32).pin_memory()
+        fl = first_last_lab.contiguous() if first_last_lab is not None else None
+        rc = self.lib.dvc_colorize_clip(self.h, _ptr(host_L), F_, H, W, float(temperature), _ptr(fl), _ptr(out),
+                                        _stream(self.device))
+        self._check(rc, "dvc_colorize_clip")
+        return out
+
+    # ---- multi-GPU: exemplar operands as one flat buffer (broadcast with torch.distributed / NCCL) ----
+    def exemplar_pack_size(self, H, W):
+        return int(self.lib.dvc_exemplar_pack_size(self.h, H, W))
+
+    def exemplar_export(self, H, W):
+        buf = torch.empty(self.exemplar_pack_size(H, W), device=self.device, dtype=torch.float32)
+        self._check(self.lib.dvc_exemplar_export(self.h, _ptr(buf), buf.numel(), _stream(self.device)),
+                    "dvc_exemplar_export")
+        return buf
+
+    def exemplar_import(self, buf, H, W):
+        buf = _dev_f32(buf, "exemplar pack")
+        self._check(self.lib.dvc_exemplar_import(self.h, _ptr(buf), buf.numel(), H, W, _stream(self.device)),
+                    "dvc_exemplar_import")
+
+    # ---- introspection ---------------------------------------------------------------------------
+    def launch_count(self, reset=False):
+        return int(self.lib.dvc_launch_count(self.h, 1 if reset else 0))
+
+    def profile_corr(self, enable=True):
+        self._check(self.lib.dvc_profile_corr(self.h, 1 if enable else 0), "dvc_profile_corr")
+
+    def corr_mean_ms(self, reset=True):
+        return float(self.lib.dvc_corr_mean_ms(self.h, 1 if reset else 0))
+
+
+_contexts = {}
+
+
+def get_context(device=None):
+    """Process-wide context of a device (shared by the three drop-in modules, like test.py:147-166)."""
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    idx = device if isinstance(device, int) else (torch.device(device).index or 0)
+    if idx not in _contexts:
+        _contexts[idx] = Context(idx)
+    return _contexts[idx]

@@ -1,0 +1,144 @@
+/*
+ * libdvc.so -- C ABI of the B200-native exemplar-video-colorization forward path.
+ *
+ * The reference (zhangmozhe/Deep-Exemplar-based-Video-Colorization) has no FFI of its own: its
+ * hot path is three Python nn.Module.forward() methods plus per-frame glue.  Each entry point below
+ * names the reference interface it replaces (file:line relative to the reference root).  The
+ * Python drop-in modules (models/NonlocalNet.py, models/ColorVidNet.py in the package) bind these
+ * symbols with ctypes; INTEGRATION.md shows that binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary.
+ *   - tensors are fp32, contiguous, NCHW unless stated; `dev_*` pointers are device memory on the
+ *     context's device, `host_*` pointers are host memory (pinned for the async paths).
+ *   - every function returns DVC_OK (0) or a negative dvc_status; dvc_last_error() gives the text.
+ *   - all device work is enqueued on the `stream` argument (a cudaStream_t passed as void*); no
+ *     entry point synchronises the device unless stated.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     DVC_ERR_CUDA.
+ *   - legal frame shapes are the reference's: H % 8 == 0, W % 16 == 0, H,W >= 16;
+ *     anything else returns DVC_ERR_SHAPE (the reference raises RuntimeError at NonlocalNet.py:464).
+ */
+#ifndef DVC_H_
+#define DVC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dvc_ctx dvc_ctx;
+
+typedef enum dvc_status {
+  DVC_OK = 0,
+  DVC_ERR_ARG = -1,     /* null pointer, unknown key, unsupported option (pool="avg", WTA_scale_weight != 1) */
+  DVC_ERR_SHAPE = -2,   /* illegal H/W or mismatching tensor shape */
+  DVC_ERR_CUDA = -3,    /* CUDA runtime error (text in dvc_last_error) or no device */
+  DVC_ERR_STATE = -4,   /* weights missing, exemplar not set, ... */
+  DVC_ERR_NCCL = -5
+} dvc_status;
+
+typedef enum dvc_net { DVC_NET_VGG = 0, DVC_NET_WARP = 1, DVC_NET_COLOR = 2 } dvc_net;
+
+/* Arithmetic used by the GEMM-shaped kernels (convolutions, correlation).
+ *   DVC_MATH_FP32    CUDA-core fp32 FMA (exact fp32 products; the parity reference on the GPU)
+ *   DVC_MATH_TF32X3  tcgen05 kind::tf32 on hi/lo split operands, 3 MMAs per product, fp32 TMEM
+ *                    accumulation (fp32-class accuracy; the default once validated)
+ *   DVC_MATH_BF16X3  tcgen05 kind::f16 (bf16) on hi/lo split operands (correlation only; fast mode)
+ */
+typedef enum dvc_math { DVC_MATH_FP32 = 0, DVC_MATH_TF32X3 = 1, DVC_MATH_BF16X3 = 2 } dvc_math;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+
+/* One context per device (reference: test.py:147-166 builds one set of modules on cuda:0).
+ * Not thread-safe per context. */
+int dvc_create(dvc_ctx** out, int device);
+int dvc_destroy(dvc_ctx* ctx);
+const char* dvc_last_error(const dvc_ctx* ctx); /* ctx may be NULL: last create() error */
+const char* dvc_version(void);
+
+/* Select the arithmetic of the conv layers and of the correlation (see dvc_math). */
+int dvc_set_math(dvc_ctx* ctx, int conv_math, int corr_math);
+
+/* ---- weights: replaces nn.Module.load_state_dict (test.py:150,158-159) ----------------------- */
+
+/* `data` holds the tensor for `key` exactly as in the reference state_dict (OIHW fp32 for conv
+ * weights, [C] for biases, [1] for PReLU slopes, [C,1,1,1] for the depthwise *_ss scales).
+ * `data` may be a host or a device pointer (cudaMemcpyDefault).  Synchronous. */
+int dvc_set_weight(dvc_ctx* ctx, int net, const char* key, const float* data, const int64_t* shape, int ndim);
+
+/* ---- module-level drop-ins ------------------------------------------------------------------ */
+
+/* VGG19_pytorch.forward(x, out_keys, preprocess) -- models/NonlocalNet.py:228-256.
+ * dev_x [B,3,H,W] RGB in [0,1].  keys[i] in {"r11".."r54","p1".."p5"}; dev_out[i] receives that map
+ * (NCHW fp32, caller-allocated).  Like the reference, preprocess != 0 applies util.py:347-352. */
+int dvc_vgg19_forward(dvc_ctx* ctx, const float* dev_x, int B, int H, int W, int preprocess,
+                      const char* const* keys, float* const* dev_out, int n_keys, void* stream);
+
+/* WarpNet.forward(B_lab_map, A_relu2_1..5_1, B_relu2_1..5_1, temperature, ...) --
+ * models/NonlocalNet.py:427-502.  dev_A[4]/dev_Bf[4] are the (already feature_normalize()d) r22,r32,r42,r52
+ * maps: [B,128,H/2,W/2], [B,256,H/4,W/4], [B,512,H/8,W/8], [B,512,H/16,W/16].
+ * dev_y [B,3,H,W], dev_sim [B,1,H,W].  reuse_exemplar != 0 skips the B-side recomputation and uses the
+ * phi / pooled-Lab operands cached by the previous call (valid only for identical B tensors).
+ * wta_scale_weight must be 1 (the reference bypasses WTA_scale in that case, NonlocalNet.py:486). */
+int dvc_warpnet_forward(dvc_ctx* ctx, const float* dev_B_lab_map, const float* const* dev_A,
+                        const float* const* dev_Bf, int B, int H, int W, float temperature,
+                        float wta_scale_weight, int reuse_exemplar, float* dev_y, float* dev_sim, void* stream);
+
+/* ColorVidNet.forward(x) -- models/ColorVidNet.py:96-144.  dev_x [B,7,H,W] -> dev_out [B,2,H,W]. */
+int dvc_colorvidnet_forward(dvc_ctx* ctx, const float* dev_x, int B, int H, int W, float* dev_out, void* stream);
+
+/* ---- the correlation kernel on its own (microbench / unit-test entry) ------------------------ */
+
+/* f = theta_hat^T phi_hat; sim = rowmax f; P = softmax_j(f/T); y = P V   (NonlocalNet.py:477-498)
+ * dev_theta_hat [B,C,NA], dev_phi_hat [Bphi,C,NB] (Bphi == B or 1: one exemplar shared by B frames),
+ * dev_V [Bphi,NB,3]; outputs dev_y [B,NA,3], dev_sim [B,NA]; dev_argmax [B,NA] int32 may be NULL.
+ * C must be 256 (WarpNet.inter_channels, NonlocalNet.py:360). */
+int dvc_corr_softmax_warp(dvc_ctx* ctx, const float* dev_theta_hat, const float* dev_phi_hat,
+                          const float* dev_V, int B, int Bphi, int NA, int NB, int C, float temperature,
+                          float* dev_y, float* dev_sim, int32_t* dev_argmax, void* stream);
+
+/* ---- fused per-frame / per-clip path (test.py:57-96 + FrameColor.py:41-67) -------------------- */
+
+/* Exemplar prologue, test.py:57-66: IB_lab [1,3,H,W] (centred L, a, b) -> sRGB -> VGG -> heads ->
+ * phi_hat / pooled Lab, cached in the context.  Host or device pointer. */
+int dvc_set_exemplar(dvc_ctx* ctx, const float* IB_lab, int H, int W, void* stream);
+
+/* frame_colorization (FrameColor.py:41-67) for B frames against the cached exemplar.
+ * IA_l [B,1,H,W] centred luminance; IA_last_lab [B,3,H,W]; out_ab [B,2,H,W];
+ * optional out_warp_lab [B,3,H,W] and out_sim [B,1,H,W] (may be NULL).  All device pointers. */
+int dvc_colorize_frames(dvc_ctx* ctx, const float* dev_IA_l, const float* dev_IA_last_lab, int B, int H, int W,
+                        float temperature, float* dev_out_ab, float* dev_out_warp_lab, float* dev_out_sim,
+                        void* stream);
+
+/* A whole segment with the frame-to-frame recurrence of test.py:76-96 kept on the device:
+ * host_L [F,1,H,W] (pinned) is copied in frame by frame, frame t's predicted ab feeds frame t+1,
+ * host_ab [F,2,H,W] (pinned) receives the predictions.  first_last_lab: NULL = zeros (test.py:80) or a
+ * host [1,3,H,W] tensor (test.py:78, --frame_propagate).  Synchronises `stream` before returning. */
+int dvc_colorize_clip(dvc_ctx* ctx, const float* host_L, int F, int H, int W, float temperature,
+                      const float* host_first_last_lab, float* host_ab, void* stream);
+
+/* ---- multi-GPU: exemplar operands travel once per clip ----------------------- */
+
+/* Size in floats of the packed exemplar operands (phi_hat planes + pooled Lab) for an HxW exemplar. */
+int64_t dvc_exemplar_pack_size(const dvc_ctx* ctx, int H, int W);
+/* Pack the cached exemplar operands into / install them from a flat device buffer, so that the
+ * caller can move them with ncclBroadcast (torch.distributed.broadcast) over NVLink. */
+int dvc_exemplar_export(dvc_ctx* ctx, float* dev_buf, int64_t n_floats, void* stream);
+int dvc_exemplar_import(dvc_ctx* ctx, const float* dev_buf, int64_t n_floats, int H, int W, void* stream);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+
+/* Number of kernels this library launched since the last call with reset != 0. */
+int64_t dvc_launch_count(dvc_ctx* ctx, int reset);
+/* CUDA-event timing of the correlation kernel: mean milliseconds over the launches recorded since
+ * the last reset (0 if none).  Recording is enabled with dvc_profile_corr(ctx, 1). */
+int dvc_profile_corr(dvc_ctx* ctx, int enable);
+double dvc_corr_mean_ms(dvc_ctx* ctx, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVC_H_ */

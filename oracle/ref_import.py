@@ -38,7 +38,10 @@ def load():
     stub = types.ModuleType("models.vgg19_gray")
     stub.vgg19_gray = stub.vgg19_gray_new = object
     sys.modules["models.vgg19_gray"] = stub
-    sys.path.insert(0, REF_ROOT)
+    # the reference's `models/` has no __init__.py (namespace package); a regular `models` package
+    # anywhere on sys.path (the drop-in's) would shadow it, so hide those entries during the import
+    saved_path = list(sys.path)
+    sys.path[:] = [REF_ROOT] + [q for q in saved_path if not os.path.isfile(os.path.join(q or ".", "models", "__init__.py"))]
     try:
         import contextlib
         import io
@@ -54,7 +57,7 @@ def load():
             feature_normalize=feature_normalize, gray2rgb_batch=gray2rgb_batch,
         )
     finally:
-        sys.path.remove(REF_ROOT)
+        sys.path[:] = saved_path
         # leave no `models.*` / `utils.*` entries of the reference behind: the drop-in package uses
         # the same module names
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "utils"

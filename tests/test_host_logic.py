@@ -1,0 +1,118 @@
+"""CPU: host-side logic -- ABI surface, state_dict contract, seeded weights, segment sharding, and the
+world_size-2 exemplar broadcast over gloo.  No compute call into libdvc.so is made without a GPU."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import dvc
+
+    hdr = open(os.path.join(ROOT, "include", "dvc.h")).read()
+    declared = set(re.findall(r"\b(dvc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no prototypes parsed"
+    lib = dvc.load_library()
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"{sym} declared in include/dvc.h but not exported by libdvc.so"
+    assert declared == set(dvc.EXPORTED)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    import dvc
+
+    with pytest.raises(dvc.DvcError):
+        dvc.Context(0)
+    from models.ColorVidNet import ColorVidNet
+
+    with pytest.raises(dvc.DvcError):
+        ColorVidNet(7)(torch.zeros(1, 7, 16, 16))
+
+
+def test_state_dict_contract():
+    from models.ColorVidNet import ColorVidNet
+    from models.NonlocalNet import VGG19_pytorch, WarpNet
+    from oracle.weights import make_state_dict, net_shapes
+
+    for name, m in (("warp", WarpNet(1)), ("color", ColorVidNet(7)), ("vgg", VGG19_pytorch())):
+        sd, ref = m.state_dict(), net_shapes(name)
+        assert list(sd.keys()) == list(ref.keys())
+        assert all(tuple(sd[k].shape) == tuple(ref[k]) for k in ref)
+        m.load_state_dict(make_state_dict(name))  # strict load of the reference-keyed dict
+        m.eval()
+        assert all(isinstance(p, torch.nn.Parameter) for p in m.parameters())
+    assert sum(v.numel() for v in make_state_dict("vgg").values()) == 20024384
+    assert sum(v.numel() for v in make_state_dict("warp").values()) == 6917131
+    assert sum(v.numel() for v in make_state_dict("color").values()) == 32802370
+
+
+def test_seeded_weights_are_reproducible():
+    from oracle.weights import make_lab, make_state_dict
+
+    a, b = make_state_dict("warp", 0), make_state_dict("warp", 0)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    c = make_state_dict("warp", 1)
+    assert not torch.equal(a["theta.weight"], c["theta.weight"])
+    assert torch.equal(make_lab(5, 1, 16, 16), make_lab(5, 1, 16, 16))
+
+
+def test_segment_bounds_cover_clip_contiguously():
+    from dvc.clip import segment_bounds
+
+    for F_ in (0, 1, 7, 8, 64, 65):
+        for world in (1, 2, 3, 8):
+            prev = 0
+            sizes = []
+            for r in range(world):
+                s, e = segment_bounds(F_, world, r)
+                assert s == prev and e >= s
+                prev = e
+                sizes.append(e - s)
+            assert prev == F_ and max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        segment_bounds(8, 2, 2)
+
+
+def test_legal_shapes():
+    from oracle.dvc_oracle import legal_shape
+
+    assert legal_shape(480, 864) and legal_shape(216, 384) and legal_shape(40, 64)
+    assert not legal_shape(480, 854) and not legal_shape(36, 64)
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+from dvc.clip import broadcast_exemplar, segment_bounds
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[3]}", rank=int(sys.argv[4]), world_size=2)
+rank = dist.get_rank()
+n = 96 * 260
+pack = torch.arange(n, dtype=torch.float32) if rank == 0 else torch.zeros(n)
+broadcast_exemplar(pack, src=0)
+assert torch.equal(pack, torch.arange(n, dtype=torch.float32))
+s, e = segment_bounds(9, 2, rank)
+got = [None, None]
+dist.all_gather_object(got, (s, e))
+assert got == [(0, 5), (5, 9)], got
+dist.barrier(); dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_exemplar_broadcast_world2_gloo(tmp_path):
+    """N>1 plumbing on CPU: rank 0's operand pack reaches rank 1 unchanged; segments tile the clip."""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    pkg = os.path.join(ROOT, "deep-exemplar-based-video-colorization_b200")
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, pkg, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "OK" in o, o
