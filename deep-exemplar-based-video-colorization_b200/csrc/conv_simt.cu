@@ -15,7 +15,10 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 8;
 
-template <int BN>
+// TWO_LEVEL: every tap's Cin products are summed in a fresh accumulator that is then folded into the
+// running total, so the rounding-error chain is ~sqrt(Cin) + sqrt(taps) long instead of sqrt(9*Cin)
+// (the CPU reference's vectorised/blocked summation has a similarly short chain).
+template <int BN, bool TWO_LEVEL>
 __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const ConvParams p) {
   constexpr int TN = BN / 16;
   constexpr int BV = BN / 4;  // float4 per weight k-row
@@ -34,10 +37,14 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const ConvParams p)
   const bool b_active = tid < BK * BV;
 
   float acc[8][TN];
+  float tot[TWO_LEVEL ? 8 : 1][TWO_LEVEL ? TN : 1];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) {
+      acc[i][j] = 0.f;
+      if constexpr (TWO_LEVEL) tot[i][j] = 0.f;
+    }
 
   const int kcs = p.Cin / BK;
   const int nk = p.taps * kcs;
@@ -89,8 +96,22 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const ConvParams p)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
+    if constexpr (TWO_LEVEL) {
+      if ((it + 1) % kcs == 0) {  // end of a tap
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) tot[i][j] += acc[i][j], acc[i][j] = 0.f;
+      }
+    }
     if (it + 1 < nk) sstore(cur ^ 1);
     __syncthreads();
+  }
+  if constexpr (TWO_LEVEL) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = tot[i][j];
   }
 
   // ---- epilogue: bias, skip add, activation, masked store, InstanceNorm statistics ----
@@ -165,14 +186,17 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const ConvParams p)
 
 }  // namespace
 
-void launch_conv_simt(const ConvParams& p, int B, cudaStream_t s) {
+void launch_conv_simt(const ConvParams& p, int B, bool two_level, cudaStream_t s) {
   const int npix = p.Hp * p.Wp;
-  if (p.CoutPad % 128 == 0) {
+  if (two_level) {
+    dim3 grid((npix + BM - 1) / BM, p.CoutPad / 64, B);
+    conv_gemm_simt_kernel<64, true><<<grid, 256, 0, s>>>(p);
+  } else if (p.CoutPad % 128 == 0) {
     dim3 grid((npix + BM - 1) / BM, p.CoutPad / 128, B);
-    conv_gemm_simt_kernel<128><<<grid, 256, 0, s>>>(p);
+    conv_gemm_simt_kernel<128, false><<<grid, 256, 0, s>>>(p);
   } else {
     dim3 grid((npix + BM - 1) / BM, p.CoutPad / 64, B);
-    conv_gemm_simt_kernel<64><<<grid, 256, 0, s>>>(p);
+    conv_gemm_simt_kernel<64, false><<<grid, 256, 0, s>>>(p);
   }
   launch_counter_add(1);
 }

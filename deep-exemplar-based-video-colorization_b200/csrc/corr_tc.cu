@@ -1,7 +1,439 @@
+// K7 on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+//   f = theta_hat^T phi_hat  ->  sim = rowmax f  ->  P = softmax_j(f / T)  ->  y = P V      (NonlocalNet.py:477-498)
+//
+// fp32-class accuracy from low-precision MMAs by operand splitting: x = hi + lo with hi, lo exactly
+// representable in the MMA input type (tf32: 2 x 11 significant bits; bf16: 2 x 8), and
+//   f ~= hi_a.hi_b + hi_a.lo_b + lo_a.hi_b           (lo.lo dropped: 2^-22 resp. 2^-16 relative)
+// all three accumulated into the same fp32 TMEM tile.  DVC_MATH_TF32X3 is the parity mode (|df| ~ 1e-7,
+// fp32 class), DVC_MATH_BF16X3 the fast mode (|df| ~ 2e-6).
+//
+// Kernel structure (one CTA = 128 query rows x a range of 256-column tiles of reference positions):
+//   warp 0      TMA producer: per k-block (128 bytes of K) loads A_hi, A_lo [128 x 128B] and B_hi, B_lo [256 x 128B]
+//               with SWIZZLE_128B into a 2-stage shared-memory ring (96 KB per stage), mbarrier expect_tx.
+//   warp 1      TMEM owner + MMA issuer: one elected thread issues 4 k-steps x 3 tcgen05.mma (M128 x N256) per
+//               stage into one of two 256-column fp32 accumulators (all 512 TMEM columns), tcgen05.commit
+//               releases the smem stage and, after the last k-block, publishes the score tile.
+//   warps 2..5  epilogue: thread t owns query row t (TMEM lane t): tcgen05.ld 32 columns at a time, running
+//               (max, argmax) or online softmax (max, sum, 3 colour sums) entirely in registers -- no
+//               cross-thread reduction; overlaps the MMAs of the next tile through the double-buffered TMEM.
+// The N x N score matrix never leaves the SM.  Column-range splits (grid.z) balance the 148 SMs; a small merge
+// kernel combines the per-split row statistics.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cudaTypedefs.h>
+#include <math.h>
+
+#include <mutex>
+
 #include "corr_tc.cuh"
+#include "tc_common.cuh"
+
 namespace dvc {
-int launch_corr_tc(const CorrParams&, int, cudaStream_t, std::string* err) {
-  if (err) *err = "tcgen05 correlation kernel not built yet";
-  return -1;
+
+// ------------------------------------------------------------------------------------------------
+// tensor-map encoding through the driver entry point (no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
+                   int elem_bytes) {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  if (!fn) return -1;
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {cols * (uint64_t)elem_bytes};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
 }
+
+namespace {
+
+constexpr int BM = 128;        // query rows per CTA (= TMEM lanes)
+constexpr int BN = 256;        // reference positions per score tile (= TMEM columns per accumulator)
+constexpr int STAGES = 2;
+constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 98304
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int NTHREADS = 192;
+
+struct SplitOut {  // per (split, row) partial statistics
+  float m, s, a0, a1, a2;
+  int idx;
+  float pad0, pad1;
+};
+
+struct TcParams {
+  int NA, NB, B, Bphi, C;
+  int tiles_per_split;
+  float sc;  // log2(e) / T
+  const float4* V;
+  SplitOut* part;  // [nsplit][B*NA]
+};
+
+// ---- operand split: rows [R][C] fp32 -> hi / lo planes -----------------------------------------------
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, void* __restrict__ hi,
+                                                           void* __restrict__ lo, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    if constexpr (TF32) {
+      float h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = tf32_rna(x[j]), l[j] = tf32_rna(x[j] - h[j]);
+      reinterpret_cast<float4*>(hi)[i] = make_float4(h[0], h[1], h[2], h[3]);
+      reinterpret_cast<float4*>(lo)[i] = make_float4(l[0], l[1], l[2], l[3]);
+    } else {
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = __float2bfloat16_rn(x[j]);
+        l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j]));
+      }
+      reinterpret_cast<uint2*>(hi)[i] = make_uint2(
+          (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16),
+          (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16));
+      reinterpret_cast<uint2*>(lo)[i] = make_uint2(
+          (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16),
+          (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16));
+    }
+  }
+}
+
+// ---- main kernel ---------------------------------------------------------------------------------------
+template <bool TF32, bool SOFTMAX>
+__global__ void __launch_bounds__(NTHREADS, 1)
+    corr_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
+  constexpr int KB = TF32 ? 32 : 64;       // K elements per 128-byte k-block
+  constexpr int UMMA_K_BYTES = 32;         // one MMA consumes 32 bytes of K (8 tf32 / 16 bf16)
+  constexpr uint32_t IDESC = tc::umma_idesc(TF32 ? 2u : 1u, BM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                 // [STAGES]   TMA -> MMA
+  uint64_t* empty = bars + STAGES;       // [STAGES]   MMA -> TMA
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]        MMA -> epilogue
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]    epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int bphi = (p.Bphi == 1) ? 0 : b;
+  const int m0 = blockIdx.x * BM;
+  const int ntiles_all = (p.NB + BN - 1) / BN;
+  const int t0 = blockIdx.z * p.tiles_per_split;
+  const int t1 = min(t0 + p.tiles_per_split, ntiles_all);
+  const int ntiles = max(t1 - t0, 0);
+  const int nkb = p.C / KB;
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmAh);
+    tc::tma_prefetch_desc(&tmAl);
+    tc::tma_prefetch_desc(&tmBh);
+    tc::tma_prefetch_desc(&tmBl);
+    for (int i = 0; i < STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 4);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int col0 = bphi * p.NB + (t0 + t) * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          tc::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          tc::tma_load_2d(st, &tmAh, &full[stage], kb * KB, b * p.NA + m0);
+          tc::tma_load_2d(st + A_BYTES, &tmAl, &full[stage], kb * KB, b * p.NA + m0);
+          tc::tma_load_2d(st + 2 * A_BYTES, &tmBh, &full[stage], kb * KB, col0);
+          tc::tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmBl, &full[stage], kb * KB, col0);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        const uint32_t acc_phase = (t >> 1) & 1;
+        tc::mbar_wait(&tempty[buf], acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t dAh = tc::umma_desc_k128(sa), dAl = tc::umma_desc_k128(sa + A_BYTES);
+          const uint64_t dBh = tc::umma_desc_k128(sa + 2 * A_BYTES), dBl = tc::umma_desc_k128(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 128 / UMMA_K_BYTES; ++kk) {
+            const uint64_t adv = (uint64_t)((kk * UMMA_K_BYTES) >> 4);  // start-address field is in 16-byte units
+            // small cross terms first, the dominant hi.hi term last
+            tc::umma_ss<TF32>(d, dAl + adv, dBh + adv, IDESC, (kb | kk) ? 1u : 0u);
+            tc::umma_ss<TF32>(d, dAh + adv, dBl + adv, IDESC, 1u);
+            tc::umma_ss<TF32>(d, dAh + adv, dBh + adv, IDESC, 1u);
+          }
+          tc::umma_commit(&empty[stage]);  // smem stage reusable once these MMAs have read it
+          if (kb == nkb - 1) tc::umma_commit(&tfull[buf]);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================= epilogue: one query row per thread =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_local = q * 32 + lane;
+    const int row = m0 + row_local;
+    float run_m = -INFINITY, run_s = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    int run_i = 0;
+    const float4* __restrict__ Vg = p.V + (size_t)bphi * p.NB;
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const uint32_t acc_phase = (t >> 1) & 1;
+      tc::mbar_wait(&tfull[buf], acc_phase);
+      tc::tc_fence_after();
+      const int colbase = (t0 + t) * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int cb = colbase + c * 32;
+        if (cb >= p.NB) break;  // warp-uniform
+        uint32_t r[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, r);
+        tc::tmem_ld_wait();
+        const int nvalid = min(32, p.NB - cb);
+        float cm = -INFINITY;
+        if (nvalid == 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nvalid) cm = fmaxf(cm, __uint_as_float(r[i]));
+        }
+        if (!SOFTMAX) {
+          if (cm > run_m) {  // rare once the running maximum has settled
+            run_m = cm;
+#pragma unroll
+            for (int i = 31; i >= 0; --i)
+              if (i < nvalid && __uint_as_float(r[i]) == cm) run_i = cb + i;  // lowest index wins
+          }
+        } else {
+          if (cm > run_m) {
+            const float sc_old = (run_m == -INFINITY) ? 0.f : exp2f((run_m - cm) * p.sc);
+            run_s *= sc_old, a0 *= sc_old, a1 *= sc_old, a2 *= sc_old;
+            run_m = cm;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < nvalid) {
+              const float e = exp2f((__uint_as_float(r[i]) - run_m) * p.sc);
+              const float4 v = __ldg(Vg + cb + i);  // same address across the warp: one broadcast load
+              run_s += e;
+              a0 = fmaf(e, v.x, a0), a1 = fmaf(e, v.y, a1), a2 = fmaf(e, v.z, a2);
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+    }
+    if (row < p.NA) {
+      SplitOut o;
+      o.m = run_m, o.s = run_s, o.a0 = a0, o.a1 = a1, o.a2 = a2, o.idx = run_i, o.pad0 = o.pad1 = 0.f;
+      p.part[((size_t)blockIdx.z * p.B + b) * p.NA + row] = o;
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- merge the column-range splits ----------------------------------------------------------------------
+template <bool SOFTMAX>
+__global__ void __launch_bounds__(256) corr_merge_kernel(const SplitOut* __restrict__ part, int nsplit, int rows, int NA,
+                                                         int NB, int Bphi, float sc, const float4* __restrict__ V,
+                                                         float4* __restrict__ y, float* __restrict__ sim,
+                                                         int* __restrict__ argmax) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int b = r / NA;
+  const float4* Vg = V + (size_t)((Bphi == 1) ? 0 : b) * NB;
+  if (!SOFTMAX) {
+    float m = -INFINITY;
+    int idx = 0;
+    for (int s = 0; s < nsplit; ++s) {
+      const SplitOut o = part[(size_t)s * rows + r];
+      if (o.m > m || (o.m == m && o.idx < idx)) m = o.m, idx = o.idx;
+    }
+    const float4 v = __ldg(Vg + idx);
+    y[r] = make_float4(v.x, v.y, v.z, 0.f);
+    sim[r] = m;
+    if (argmax) argmax[r] = idx;
+  } else {
+    float m = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) m = fmaxf(m, part[(size_t)s * rows + r].m);
+    float ssum = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+      const SplitOut o = part[(size_t)s * rows + r];
+      if (o.m == -INFINITY) continue;
+      const float w = exp2f((o.m - m) * sc);
+      ssum += w * o.s, a0 += w * o.a0, a1 += w * o.a1, a2 += w * o.a2;
+    }
+    y[r] = make_float4(a0 / ssum, a1 / ssum, a2 / ssum, 0.f);
+    sim[r] = m;
+    if (argmax) argmax[r] = -1;
+  }
+}
+
+// workspace cache (planes + partials), grown on demand; one per process/device like the context
+struct TcWorkspace {
+  void* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[5] = {0, 0, 0, 0, 0};
+};
+TcWorkspace g_ws;
+
+int ws_get(int i, size_t bytes, void** out) {
+  if (g_ws.cap[i] < bytes) {
+    if (g_ws.buf[i]) cudaFree(g_ws.buf[i]);
+    g_ws.buf[i] = nullptr;
+    if (cudaMalloc(&g_ws.buf[i], bytes) != cudaSuccess) return -1;
+    g_ws.cap[i] = bytes;
+  }
+  *out = g_ws.buf[i];
+  return 0;
+}
+
+template <bool TF32, bool SOFTMAX>
+int launch_main(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl,
+                const TcParams& tp, dim3 grid, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(corr_tc_kernel<TF32, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+        cudaSuccess)
+      return -1;
+    attr = true;
+  }
+  corr_tc_kernel<TF32, SOFTMAX><<<grid, NTHREADS, SMEM_BYTES, s>>>(mAh, mAl, mBh, mBl, tp);
+  return 0;
+}
+
+}  // namespace
+
+int launch_corr_tc(const CorrParams& p, int math, cudaStream_t s, std::string* err) {
+  auto fail = [&](const char* m) {
+    if (err) *err = m;
+    return -1;
+  };
+  const bool tf32 = (math == 1);
+  if (p.C != 256) return fail("C must be 256");
+  const int eb = tf32 ? 4 : 2;
+  const size_t ea = (size_t)p.B * p.NA * p.C, ephi = (size_t)p.Bphi * p.NB * p.C;
+  void *Ah, *Al, *Bh, *Bl, *part;
+  if (ws_get(0, ea * eb, &Ah) || ws_get(1, ea * eb, &Al) || ws_get(2, ephi * eb, &Bh) || ws_get(3, ephi * eb, &Bl))
+    return fail("workspace allocation failed");
+
+  // column-range splits so that (row blocks x batch x splits) fills the 148 SMs in whole waves
+  const int row_blocks = (p.NA + BM - 1) / BM;
+  const int ntiles = (p.NB + BN - 1) / BN;
+  int nsplit = 1;
+  {
+    const long ctas = (long)row_blocks * p.B;
+    double best = -1.0;
+    for (int sp = 1; sp <= 16 && sp <= ntiles; ++sp) {
+      const int tps = (ntiles + sp - 1) / sp;
+      const int eff_sp = (ntiles + tps - 1) / tps;
+      const long total = ctas * eff_sp;
+      const long waves = (total + 147) / 148;
+      const double eff = (double)total / (double)(waves * 148) * ((double)ntiles / (double)(tps * eff_sp)) -
+                         0.01 * sp;  // mild penalty: every split re-runs the prologue
+      if (eff > best) best = eff, nsplit = eff_sp;
+    }
+  }
+  const int tps = (ntiles + nsplit - 1) / nsplit;
+  nsplit = (ntiles + tps - 1) / tps;
+  if (ws_get(4, (size_t)nsplit * p.B * p.NA * sizeof(SplitOut), &part)) return fail("workspace allocation failed");
+
+  const int grid1 = 148 * 8;
+  if (tf32)
+    split_planes_kernel<true><<<grid1, 256, 0, s>>>(p.theta, Ah, Al, ea / 4);
+  else
+    split_planes_kernel<false><<<grid1, 256, 0, s>>>(p.theta, Ah, Al, ea / 4);
+  launch_counter_add(1);
+  if (tf32)
+    split_planes_kernel<true><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
+  else
+    split_planes_kernel<false><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
+  launch_counter_add(1);
+
+  CUtensorMap mAh, mAl, mBh, mBl;
+  const uint32_t boxk = tf32 ? 32 : 64;
+  if (encode_tmap_2d(&mAh, Ah, (uint64_t)p.B * p.NA, p.C, BM, boxk, eb) || encode_tmap_2d(&mAl, Al, (uint64_t)p.B * p.NA, p.C, BM, boxk, eb) ||
+      encode_tmap_2d(&mBh, Bh, (uint64_t)p.Bphi * p.NB, p.C, BN, boxk, eb) ||
+      encode_tmap_2d(&mBl, Bl, (uint64_t)p.Bphi * p.NB, p.C, BN, boxk, eb))
+    return fail("cuTensorMapEncodeTiled failed");
+
+  TcParams tp;
+  tp.NA = p.NA, tp.NB = p.NB, tp.B = p.B, tp.Bphi = p.Bphi, tp.C = p.C, tp.tiles_per_split = tps;
+  tp.sc = 1.4426950408889634f / p.temperature;
+  tp.V = reinterpret_cast<const float4*>(p.V);
+  tp.part = reinterpret_cast<SplitOut*>(part);
+  dim3 grid(row_blocks, p.B, nsplit);
+  const bool softmax = !(p.temperature <= 2e-10f);
+  int rc;
+  if (tf32)
+    rc = softmax ? launch_main<true, true>(mAh, mAl, mBh, mBl, tp, grid, s) : launch_main<true, false>(mAh, mAl, mBh, mBl, tp, grid, s);
+  else
+    rc = softmax ? launch_main<false, true>(mAh, mAl, mBh, mBl, tp, grid, s) : launch_main<false, false>(mAh, mAl, mBh, mBl, tp, grid, s);
+  if (rc) return fail("cudaFuncSetAttribute(max dynamic smem) failed");
+  launch_counter_add(1);
+  const int rows = p.B * p.NA;
+  if (softmax)
+    corr_merge_kernel<true><<<(rows + 255) / 256, 256, 0, s>>>(tp.part, nsplit, rows, p.NA, p.NB, p.Bphi, tp.sc, tp.V,
+                                                                reinterpret_cast<float4*>(p.y), p.sim, p.argmax);
+  else
+    corr_merge_kernel<false><<<(rows + 255) / 256, 256, 0, s>>>(tp.part, nsplit, rows, p.NA, p.NB, p.Bphi, tp.sc, tp.V,
+                                                                 reinterpret_cast<float4*>(p.y), p.sim, p.argmax);
+  launch_counter_add(1);
+  return 0;
+}
+
 }  // namespace dvc

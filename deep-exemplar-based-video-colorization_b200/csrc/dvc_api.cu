@@ -48,6 +48,7 @@ struct dvc_ctx {
   std::unordered_map<std::string, float*> vec[3];
   std::unordered_map<std::string, std::vector<float>> host_bias[3];  // bias seen before its weight
   int conv_math = DVC_MATH_FP32, corr_math = DVC_MATH_FP32;
+  bool two_level = true;  // fp32 convolutions: per-tap two-level accumulation (see conv_simt.cu)
   std::map<std::string, Buf> bufs;
   // InstanceNorm statistics arena (doubles), bump-allocated per forward call
   double* stats = nullptr;
@@ -283,7 +284,7 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
   }
   p.nchw = nullptr;
   p.act = o.act, p.slope = o.slope, p.stats = o.stats;
-  launch_conv_simt(p, x.B, s);
+  launch_conv_simt(p, x.B, c->two_level, s);
   return check_launch(c, "conv");
 }
 
@@ -653,6 +654,24 @@ extern "C" int dvc_set_math(dvc_ctx* c, int conv_math, int corr_math) {
   if (corr_math != DVC_MATH_FP32 && corr_math != DVC_MATH_TF32X3 && corr_math != DVC_MATH_BF16X3)
     return fail(c, DVC_ERR_ARG, "unknown corr math");
   c->conv_math = conv_math, c->corr_math = corr_math;
+  return DVC_OK;
+}
+
+extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
+  if (!c || !name) return DVC_ERR_ARG;
+  if (!strcmp(name, "two_level")) { c->two_level = value != 0; return DVC_OK; }
+  return fail(c, DVC_ERR_ARG, std::string("unknown debug flag ") + name);
+}
+
+extern "C" int dvc_debug_get_buffer(dvc_ctx* c, const char* name, void** dev_ptr, int64_t* bytes, int* sig5) {
+  if (!c || !name || !dev_ptr || !bytes) return DVC_ERR_ARG;
+  if (!strcmp(name, "ex.phi")) { *dev_ptr = c->ex_phi; *bytes = (int64_t)c->ex_N * 256 * 4; return DVC_OK; }
+  if (!strcmp(name, "ex.V")) { *dev_ptr = c->ex_V; *bytes = (int64_t)c->ex_N * 16; return DVC_OK; }
+  auto it = c->bufs.find(name);
+  if (it == c->bufs.end()) return fail(c, DVC_ERR_ARG, std::string("no such buffer: ") + name);
+  *dev_ptr = it->second.p;
+  *bytes = (int64_t)it->second.bytes;
+  if (sig5) for (int i = 0; i < 5; ++i) sig5[i] = it->second.sig[i];
   return DVC_OK;
 }
 

@@ -44,7 +44,7 @@ struct ConvParams {
   double* stats;  // optional [B][Cout][2] (sum, sum of squares) of the stored values
 };
 
-void launch_conv_simt(const ConvParams& p, int B, cudaStream_t s);
+void launch_conv_simt(const ConvParams& p, int B, bool two_level, cudaStream_t s);
 
 // ---- elementwise gather: InstanceNorm apply / PReLU / pad / up / sub / residual ----------------
 struct XformParams {

@@ -21,6 +21,7 @@ EXPORTED = [
     "dvc_vgg19_forward", "dvc_warpnet_forward", "dvc_colorvidnet_forward", "dvc_corr_softmax_warp",
     "dvc_set_exemplar", "dvc_colorize_frames", "dvc_colorize_clip", "dvc_exemplar_pack_size",
     "dvc_exemplar_export", "dvc_exemplar_import", "dvc_launch_count", "dvc_profile_corr", "dvc_corr_mean_ms",
+    "dvc_debug_set_flag", "dvc_debug_get_buffer",
 ]
 
 _lib = None
@@ -71,6 +72,8 @@ def load_library():
         lib.dvc_profile_corr.argtypes = [c_void, c_int]
         lib.dvc_corr_mean_ms.argtypes = [c_void, c_int]
         lib.dvc_corr_mean_ms.restype = ctypes.c_double
+        lib.dvc_debug_set_flag.argtypes = [c_void, ctypes.c_char_p, c_int]
+        lib.dvc_debug_get_buffer.argtypes = [c_void, ctypes.c_char_p, P(c_void), P(c_i64), P(c_int)]
         _lib = lib
         return lib
 
@@ -255,6 +258,23 @@ class Context:
         self._check(self.lib.dvc_exemplar_import(self.h, _ptr(buf), buf.numel(), H, W, _stream(self.device)),
                     "dvc_exemplar_import")
 
+    # ---- debug hooks ---------------------------------------------------------------------------------
+    def debug_flag(self, name, value):
+        self._check(self.lib.dvc_debug_set_flag(self.h, name.encode(), int(value)), "dvc_debug_set_flag")
+
+    def debug_buffer(self, name, act=True):
+        """Copy of an internal workspace.  act=True: padded NHWC activation -> interior as NCHW [B,C,H,W]."""
+        ptr, nbytes, sig = ctypes.c_void_p(0), ctypes.c_int64(0), (ctypes.c_int * 5)()
+        self._check(self.lib.dvc_debug_get_buffer(self.h, name.encode(), ctypes.byref(ptr), ctypes.byref(nbytes), sig),
+                    "dvc_debug_get_buffer")
+        torch.cuda.synchronize(self.device)
+        flat = _raw_view(ptr.value, nbytes.value // 4, self.device).clone()
+        if not act:
+            return flat
+        B, H, W, C, P = list(sig)
+        t = flat[: B * (H + 2 * P) * (W + 2 * P) * C].view(B, H + 2 * P, W + 2 * P, C)
+        return t[:, P:P + H, P:P + W, :].permute(0, 3, 1, 2).contiguous()
+
     # ---- introspection ---------------------------------------------------------------------------
     def launch_count(self, reset=False):
         return int(self.lib.dvc_launch_count(self.h, 1 if reset else 0))
@@ -264,6 +284,17 @@ class Context:
 
     def corr_mean_ms(self, reset=True):
         return float(self.lib.dvc_corr_mean_ms(self.h, 1 if reset else 0))
+
+
+def _raw_view(ptr, n_floats, device):
+    """float32 tensor aliasing raw device memory (debug only) via the CUDA array interface."""
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(h, device=device)
 
 
 _contexts = {}

@@ -138,6 +138,14 @@ int64_t dvc_launch_count(dvc_ctx* ctx, int reset);
 int dvc_profile_corr(dvc_ctx* ctx, int enable);
 double dvc_corr_mean_ms(dvc_ctx* ctx, int reset);
 
+/* Debug / test hooks (not part of the drop-in surface).
+ *   dvc_debug_set_flag: "two_level" (default 1) selects per-tap two-level fp32 accumulation in the
+ *   CUDA-core convolution (shorter rounding chain; 0 = plain sequential accumulation, faster).
+ *   dvc_debug_get_buffer: device pointer / size of a named internal workspace (padded NHWC activations
+ *   carry their [B,H,W,C,P] signature in sig5) so tests can check intermediate stages. */
+int dvc_debug_set_flag(dvc_ctx* ctx, const char* name, int value);
+int dvc_debug_get_buffer(dvc_ctx* ctx, const char* name, void** dev_ptr, int64_t* bytes, int* sig5);
+
 #ifdef __cplusplus
 }
 #endif
