@@ -134,7 +134,7 @@ def test_warpnet_module_vs_golden(ctx, sds, name):
     if T < 1e-9:
         clear = g["gap64"] > 1e-5
         m = np.broadcast_to(clear[:, None, :], (B, 3, clear.shape[1]))
-        assert np.array_equal(ys.reshape(B, 3, -1)[m], g["warped32"].reshape(B, 3, -1)[m])
+        assert np.abs(ys.reshape(B, 3, -1)[m] - g["warped32"].reshape(B, 3, -1)[m]).max() < 1e-4
     else:
         floor = np.abs(g["warped32"].astype(np.float64) - g["warped64"]).max()
         assert np.abs(ys - g["warped64"]).max() <= max(1e-3, 2 * floor)
@@ -178,7 +178,7 @@ def test_fused_frame_vs_golden(ctx, name):
     if T < 1e-9:
         clear = g["gap64"] > 1e-5
         m = np.broadcast_to(clear[:, None, :], (1, 3, clear.shape[1]))
-        nbad = int((ys.reshape(1, 3, -1)[m] != g["warped32"].reshape(1, 3, -1)[m]).sum())
+        nbad = int((np.abs(ys.reshape(1, 3, -1)[m] - g["warped32"].reshape(1, 3, -1)[m]) > 1e-4).sum())
         assert nbad == 0, nbad
     err, tol = ab_gate(ab.cpu().numpy(), g)
     assert err <= tol, (err, tol)
@@ -270,6 +270,8 @@ def test_oracle_on_the_fly_64x64(ctx, sds):
     ab, warp, sim = ctx.colorize_frames(IA[:, 0:1].cuda(), last.cuda(), want_warp=True)
     assert (sim.cpu().double() - sim64).abs().max() < 2e-5
     clear = (gap > 1e-5).view(1, 1, 16, 16).expand(1, 3, 16, 16)
-    assert torch.equal(warp.cpu()[:, :, ::4, ::4][clear], warped64.float()[:, :, ::4, ::4][clear])
+    # the pooled exemplar colours are fp32 sums on the GPU and fp64 sums in this oracle: compare with a tolerance
+    # far below the distance between two different exemplar colours
+    assert (warp.cpu()[:, :, ::4, ::4][clear].double() - warped64[:, :, ::4, ::4][clear]).abs().max() < 1e-4
     floor = (ab32.double() - ab64).abs().max().item()
     assert (ab.cpu().double() - ab64).abs().max().item() <= max(1e-3, 2 * floor)
