@@ -152,9 +152,24 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const ConvParams p)
         ssum[g * 4 + j] += v[j];
         ssq[g * 4 + j] += v[j] * v[j];
       }
-      if (p.y)
-        *reinterpret_cast<float4*>(p.y + (((size_t)b * p.yHp + yo + p.yP) * p.yWp + xo + p.yP) * p.yC + p.yCoff + c) =
-            make_float4(v[0], v[1], v[2], v[3]);
+      if (p.y) {
+        const size_t o = (((size_t)b * p.yHp + yo + p.yP) * p.yWp + xo + p.yP) * p.yC + p.yCoff + c;
+        if (p.y_lo) {  // feed a tensor-core layer: tf32 hi/lo planes
+          float h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t u;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[j]));
+            h[j] = __uint_as_float(u);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[j] - h[j]));
+            l[j] = __uint_as_float(u);
+          }
+          *reinterpret_cast<float4*>(p.y + o) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(p.y_lo + o) = make_float4(l[0], l[1], l[2], l[3]);
+        } else {
+          *reinterpret_cast<float4*>(p.y + o) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
       if (p.nchw) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) p.nchw[(((size_t)b * p.Cout + c + j) * p.Ho + yo) * p.Wo + xo] = v[j];

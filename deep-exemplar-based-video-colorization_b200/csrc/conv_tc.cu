@@ -1,0 +1,321 @@
+// Convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA): DVC_MATH_TF32X3.
+//
+// Same flat shifted GEMM as conv_simt.cu (Y[p, co] = sum_tap sum_ci X[p + off(tap), ci] W[tap][ci][co] over the
+// padded pixel index p), with fp32-class accuracy from three kind::tf32 MMAs per product on hi/lo split
+// operands (x = hi + lo, both exactly representable in tf32):  hi.hi + hi.lo + lo.hi  -> one fp32 TMEM tile.
+// Activations therefore live in HBM as two padded-NHWC planes (hi, lo); weights are split once at load time.
+//
+// Persistent kernel, one CTA per SM, static round-robin over the (pixel tile, channel tile) grid:
+//   warp 0      TMA producer: per (tap, 32-channel k-block) loads X_hi, X_lo [128 px x 128 B] at row offset
+//               off(tap) -- negative / past-the-end rows are zero-filled by TMA -- and W_hi, W_lo [BN x 128 B],
+//               SWIZZLE_128B, into an mbarrier ring (2/3/4 stages for BN = 256/128/64).
+//   warp 1      TMEM owner + MMA issuer: 4 k-steps x 3 tcgen05.mma (M128 x N=BN x K8) per stage into one of two
+//               TMEM accumulators; tcgen05.commit frees the stage / publishes the tile.
+//   warps 2..5  epilogue (overlaps the next tile's MMAs): thread t owns output pixel t of the tile: tcgen05.ld 32
+//               channels at a time, + bias, + skip addend, activation, InstanceNorm statistics (warp shuffle ->
+//               shared atomics -> one double atomic per channel and tile), masked store of the interior pixel as
+//               fp32 or as hi/lo planes for the next tensor-core layer.
+// Replaces nn.Conv2d (+ReLU/LeakyReLU/skip add) at NonlocalNet.py:235-255,364-423 and ColorVidNet.py:96-143.
+#include <cuda.h>
+#include <math.h>
+
+#include "conv_tc.cuh"
+#include "tc_common.cuh"
+
+namespace dvc {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int A_BYTES = BM * 128;
+constexpr int NTHREADS = 192;
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2 * BN * 4;
+};
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+    conv_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                   const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const ConvTcParams p) {
+  using C = Cfg<BN>;
+  constexpr uint32_t IDESC = tc::umma_idesc(2u, BM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  float* s_stat = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);  // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.Mtot + BM - 1) / BM;
+  const int n_tiles = p.CoutPad / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int kbs = p.Cin / 32;
+  const int nk = p.taps * kbs;
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmXh);
+    tc::tma_prefetch_desc(&tmXl);
+    tc::tma_prefetch_desc(&tmWh);
+    tc::tma_prefetch_desc(&tmWl);
+    for (int i = 0; i < C::STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 4);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        const int m0 = mt * BM, n0 = nt * BN;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          int off = 0;
+          if (p.taps == 9) off = ((tap / 3 - 1) * p.Wp + (tap % 3 - 1)) * p.dil;
+          for (int kb = 0; kb < kbs; ++kb) {
+            tc::mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* st = smem + stage * C::STAGE_BYTES;
+            tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+            tc::tma_load_2d(st, &tmXh, &full[stage], kb * 32, m0 + off);
+            tc::tma_load_2d(st + A_BYTES, &tmXl, &full[stage], kb * 32, m0 + off);
+            tc::tma_load_2d(st + 2 * A_BYTES, &tmWh, &full[stage], kb * 32, tap * p.CoutPad + n0);
+            tc::tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tmWl, &full[stage], kb * 32, tap * p.CoutPad + n0);
+            if (++stage == C::STAGES) stage = 0, phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        tc::mbar_wait(&tempty[buf], acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d = tmem_base + buf * BN;
+        for (int k = 0; k < nk; ++k) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t dXh = tc::umma_desc_k128(sa), dXl = tc::umma_desc_k128(sa + A_BYTES);
+          const uint64_t dWh = tc::umma_desc_k128(sa + 2 * A_BYTES), dWl = tc::umma_desc_k128(sa + 2 * A_BYTES + C::B_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+            tc::umma_ss<true>(d, dXl + adv, dWh + adv, IDESC, (k | kk) ? 1u : 0u);
+            tc::umma_ss<true>(d, dXh + adv, dWl + adv, IDESC, 1u);
+            tc::umma_ss<true>(d, dXh + adv, dWh + adv, IDESC, 1u);
+          }
+          tc::umma_commit(&empty[stage]);
+          if (k == nk - 1) tc::umma_commit(&tfull[buf]);
+          if (++stage == C::STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================= epilogue: one output pixel per thread =================
+    const int q = warp & 3;
+    const int etid = threadIdx.x - 64;  // 0..127
+    const int img = p.Hp * p.Wp;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int m0 = mt * BM, n0 = nt * BN;
+      const int pp = m0 + q * 32 + lane;
+      bool valid = pp < p.Mtot;
+      int b = 0, yo = 0, xo = 0;
+      if (valid) {
+        b = pp / img;
+        const int rem = pp - b * img;
+        const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
+        const int y = yp - p.P, x = xp - p.P;
+        valid = (y >= 0 && y < p.H && x >= 0 && x < p.W);
+        if (p.stride == 2 && ((y | x) & 1)) valid = false;
+        yo = y / p.stride, xo = x / p.stride;
+      }
+      const size_t yoff = valid ? ((((size_t)b * p.yHp + yo + p.yP) * p.yWp + xo + p.yP) * p.yC + p.yCoff) : 0;
+      const size_t aoff = (valid && p.add) ? ((((size_t)b * p.aHp + yo + p.aP) * p.aWp + xo + p.aP) * p.aC) : 0;
+      // statistics are per image: a tile that straddles two images falls back to per-thread atomics
+      const int b_first = m0 / img, b_last = min(m0 + BM - 1, p.Mtot - 1) / img;
+      const bool uniform_img = (b_first == b_last);
+      if (p.stats) {
+        for (int i = etid; i < 2 * BN; i += 128) s_stat[i] = 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      tc::mbar_wait(&tfull[buf], acc_phase);
+      tc::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int ch0 = n0 + c * 32;
+        if (ch0 >= p.Cout) break;  // uniform
+        uint32_t r[32];
+        __syncwarp();
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, r);
+        tc::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[j] = __uint_as_float(r[j]) + bv.x, v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + bv.z, v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
+        }
+        if (p.add && valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 av = __ldg(reinterpret_cast<const float4*>(p.add + aoff + ch0 + j));
+            if (p.add_lo) {
+              const float4 al = __ldg(reinterpret_cast<const float4*>(p.add_lo + aoff + ch0 + j));
+              av.x += al.x, av.y += al.y, av.z += al.z, av.w += al.w;
+            }
+            v[j] += av.x, v[j + 1] += av.y, v[j + 2] += av.z, v[j + 3] += av.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+          if (p.act == ACT_LRELU) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+        }
+        if (valid) {
+          if (p.y_lo) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float h[4], l[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) h[t] = tf32_rna(v[j + t]), l[t] = tf32_rna(v[j + t] - h[t]);
+              *reinterpret_cast<float4*>(p.y + yoff + ch0 + j) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(p.y_lo + yoff + ch0 + j) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(p.y + yoff + ch0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+        if (p.stats) {
+          if (uniform_img) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float s = valid ? v[j] : 0.f, sq = valid ? v[j] * v[j] : 0.f;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                sq += __shfl_xor_sync(0xffffffffu, sq, o);
+              }
+              if (lane == j) {
+                atomicAdd(&s_stat[c * 32 + j], s);
+                atomicAdd(&s_stat[BN + c * 32 + j], sq);
+              }
+            }
+          } else if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              atomicAdd(&p.stats[((size_t)b * p.Cout + ch0 + j) * 2 + 0], (double)v[j]);
+              atomicAdd(&p.stats[((size_t)b * p.Cout + ch0 + j) * 2 + 1], (double)v[j] * (double)v[j]);
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (uniform_img) {
+          for (int i = etid; i < BN; i += 128) {
+            const int ch = n0 + i;
+            if (ch < p.Cout) {
+              atomicAdd(&p.stats[((size_t)b_first * p.Cout + ch) * 2 + 0], (double)s_stat[i]);
+              atomicAdd(&p.stats[((size_t)b_first * p.Cout + ch) * 2 + 1], (double)s_stat[BN + i]);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap& mWh, const CUtensorMap& mWl,
+              const ConvTcParams& p, int num_sms, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES) != cudaSuccess)
+      return -1;
+    attr = true;
+  }
+  const int total = ((p.Mtot + BM - 1) / BM) * (p.CoutPad / BN);
+  const int grid = total < num_sms ? total : num_sms;
+  conv_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, s>>>(mXh, mXl, mWh, mWl, p);
+  return 0;
+}
+
+}  // namespace
+
+int conv_tc_pick_bn(int cout) { return cout >= 256 ? 256 : (cout > 64 ? 128 : 64); }
+
+int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
+                   int num_sms, cudaStream_t s, std::string* err) {
+  auto fail = [&](const char* m) {
+    if (err) *err = m;
+    return -1;
+  };
+  if (p.Cin % 32) return fail("Cin must be a multiple of 32");
+  const int BN = conv_tc_pick_bn(p.Cout);
+  if (p.CoutPad % BN) return fail("CoutPad must be a multiple of the channel tile");
+  CUtensorMap mXh, mXl, mWh, mWl;
+  if (encode_tmap_2d(&mXh, x_hi, (uint64_t)p.Mtot, p.Cin, BM, 32, 4) || encode_tmap_2d(&mXl, x_lo, (uint64_t)p.Mtot, p.Cin, BM, 32, 4) ||
+      encode_tmap_2d(&mWh, w_hi, (uint64_t)p.taps * p.CoutPad, p.Cin, BN, 32, 4) ||
+      encode_tmap_2d(&mWl, w_lo, (uint64_t)p.taps * p.CoutPad, p.Cin, BN, 32, 4))
+    return fail("cuTensorMapEncodeTiled failed");
+  int rc;
+  if (BN == 256)
+    rc = launch_bn<256>(mXh, mXl, mWh, mWl, p, num_sms, s);
+  else if (BN == 128)
+    rc = launch_bn<128>(mXh, mXl, mWh, mWl, p, num_sms, s);
+  else
+    rc = launch_bn<64>(mXh, mXl, mWh, mWl, p, num_sms, s);
+  if (rc) return fail("cudaFuncSetAttribute(max dynamic smem) failed");
+  launch_counter_add(1);
+  return 0;
+}
+
+}  // namespace dvc

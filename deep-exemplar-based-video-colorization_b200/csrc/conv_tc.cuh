@@ -1,0 +1,31 @@
+// tcgen05 (5th-gen tensor core) convolution engine; see conv_tc.cu.
+#pragma once
+#include <string>
+
+#include "dvc_internal.cuh"
+
+namespace dvc {
+
+struct ConvTcParams {
+  int Hp, Wp, P, H, W, Cin;  // input planes: padded NHWC, Cin a multiple of 32
+  int Mtot;                  // B * Hp * Wp
+  int taps, dil, stride;
+  int Cout, CoutPad;         // CoutPad: multiple of the channel tile (weights are zero beyond Cout)
+  const float* bias;
+  float* y;      // destination: fp32 plane, or the hi plane when y_lo != nullptr
+  float* y_lo;
+  int yHp, yWp, yP, yC, yCoff;
+  const float* add;     // optional skip addend (fp32, or hi plane when add_lo != nullptr)
+  const float* add_lo;
+  int aHp, aWp, aP, aC;
+  int act;
+  float slope;
+  double* stats;  // optional [B][Cout][2]
+};
+
+int conv_tc_pick_bn(int cout);  // channel tile (64 / 128 / 256) used for `cout` output channels
+// x_hi/x_lo: activation planes [Mtot][Cin]; w_hi/w_lo: weight planes [taps][CoutPad][Cin] (tf32-rounded fp32 words)
+int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
+                   int num_sms, cudaStream_t s, std::string* err);
+
+}  // namespace dvc

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/dvc.h"
+#include "conv_tc.cuh"
 #include "corr_tc.cuh"
 #include "dvc_internal.cuh"
 
@@ -25,10 +26,22 @@ static std::atomic<int64_t> g_launches{0};
 int64_t launch_counter_add(int64_t n) { return g_launches.fetch_add(n) + n; }
 
 struct ConvW {
-  float* w = nullptr;  // [taps][cin_pad][cout_pad]
+  float* w = nullptr;  // [taps][cin_pad][cout_pad]       (CUDA-core kernel: output channels contiguous)
   float* b = nullptr;  // [cout_pad]
-  int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, k = 0;
+  float* wt_hi = nullptr;  // [taps][cout_pad_tc][cin_pad]  tf32 hi plane (tensor-core kernel: K contiguous)
+  float* wt_lo = nullptr;  //                               tf32 lo plane
+  int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, cout_pad_tc = 0, k = 0;
 };
+
+static inline float host_tf32_rna(float x) {  // cvt.rna.tf32.f32: nearest, ties away, 10 explicit mantissa bits
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u = (u + 0x1000u) & 0xffffe000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
 
 struct Buf {
   void* p = nullptr;
@@ -47,6 +60,7 @@ struct dvc_ctx {
   std::unordered_map<std::string, float> slope[3];
   std::unordered_map<std::string, float*> vec[3];
   std::unordered_map<std::string, std::vector<float>> host_bias[3];  // bias seen before its weight
+  int num_sms = 148;
   int conv_math = DVC_MATH_FP32, corr_math = DVC_MATH_FP32;
   bool two_level = true;  // fp32 convolutions: per-tap two-level accumulation (see conv_simt.cu)
   std::map<std::string, Buf> bufs;
@@ -111,14 +125,18 @@ static int get_buf(dvc_ctx* c, const std::string& name, size_t bytes, void** out
 
 // padded NHWC activation; the zero border is established once per (name, shape) and never written by
 // the convolution epilogues, the gather kernels rewrite their own borders every call.
-static int get_act(dvc_ctx* c, const std::string& name, int B, int H, int W, int C, int P, Act* a, cudaStream_t s) {
+// split: allocate tf32 hi/lo planes (input of a tensor-core convolution)
+static int get_act(dvc_ctx* c, const std::string& name, int B, int H, int W, int C, int P, Act* a, cudaStream_t s,
+                   bool split = false) {
   a->B = B, a->H = H, a->W = W, a->C = C, a->P = P;
-  const int sig[5] = {B, H, W, C, P};
+  const int sig[5] = {B, H, W, C, split ? -1 - P : P};
   void* p = nullptr;
-  DVC_TRY(get_buf(c, name, a->elems() * sizeof(float), &p, sig, true, s));
+  DVC_TRY(get_buf(c, name, a->elems() * sizeof(float) * (split ? 2 : 1), &p, sig, true, s));
   a->d = (float*)p;
+  a->lo = split ? a->d + a->elems() : nullptr;
   return DVC_OK;
 }
+static bool tc_mode(const dvc_ctx* c) { return c->conv_math == DVC_MATH_TF32X3; }
 
 static int get_raw(dvc_ctx* c, const std::string& name, size_t bytes, void** out, cudaStream_t s) {
   const int sig[5] = {(int)(bytes & 0x7fffffff), 0, 0, 0, 0};
@@ -190,7 +208,8 @@ extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const floa
     }
     ConvW& cw = c->conv[net][base];
     const int taps = kh * kw;
-    const int cin_pad = (ci + 7) / 8 * 8, cout_pad = (co + 63) / 64 * 64;
+    const int cin_pad = (ci + 7) / 8 * 8;
+    const int cout_pad = (co + 63) / 64 * 64;
     std::vector<float> packed((size_t)taps * cin_pad * cout_pad, 0.f);
     for (int o = 0; o < co; ++o)
       for (int i = 0; i < ci; ++i)
@@ -205,6 +224,27 @@ extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const floa
       CUDA_TRY(c, cudaMemset(cw.b, 0, cout_pad * sizeof(float)));
     }
     cw.cin = ci, cw.cin_pad = cin_pad, cw.cout = co, cw.cout_pad = cout_pad, cw.k = kh;
+    if (cw.wt_hi) cudaFree(cw.wt_hi);
+    if (cw.wt_lo) cudaFree(cw.wt_lo);
+    cw.wt_hi = cw.wt_lo = nullptr;
+    if (cin_pad % 32 == 0 && co >= 32) {  // tensor-core operand: [tap][cout_pad_tc][cin] hi / lo planes
+      const int bn = conv_tc_pick_bn(co);
+      const int cpt = (co + bn - 1) / bn * bn;
+      std::vector<float> hi((size_t)taps * cpt * cin_pad, 0.f), lo(hi.size(), 0.f);
+      for (int o = 0; o < co; ++o)
+        for (int i = 0; i < ci; ++i)
+          for (int t = 0; t < taps; ++t) {
+            const float v = h[((size_t)o * ci + i) * taps + t];
+            const float vh = host_tf32_rna(v);
+            hi[((size_t)t * cpt + o) * cin_pad + i] = vh;
+            lo[((size_t)t * cpt + o) * cin_pad + i] = host_tf32_rna(v - vh);
+          }
+      CUDA_TRY(c, cudaMalloc((void**)&cw.wt_hi, hi.size() * sizeof(float)));
+      CUDA_TRY(c, cudaMalloc((void**)&cw.wt_lo, lo.size() * sizeof(float)));
+      CUDA_TRY(c, cudaMemcpy(cw.wt_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
+      CUDA_TRY(c, cudaMemcpy(cw.wt_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+      cw.cout_pad_tc = cpt;
+    }
     auto hb = c->host_bias[net].find(base);
     if (hb != c->host_bias[net].end())
       CUDA_TRY(c, cudaMemcpy(cw.b, hb->second.data(), hb->second.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -284,6 +324,20 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
   }
   p.nchw = nullptr;
   p.act = o.act, p.slope = o.slope, p.stats = o.stats;
+  p.y_lo = y.lo;
+  if (x.lo) {  // hi/lo planes: tensor-core engine
+    if (!w->wt_hi) return fail(c, DVC_ERR_STATE, "conv: split input but no tensor-core weights");
+    ConvTcParams t{};
+    t.Hp = p.Hp, t.Wp = p.Wp, t.P = p.P, t.H = p.H, t.W = p.W, t.Cin = p.Cin, t.Mtot = x.B * p.Hp * p.Wp;
+    t.taps = taps, t.dil = o.dil, t.stride = o.stride, t.Cout = w->cout, t.CoutPad = w->cout_pad_tc, t.bias = w->b;
+    t.y = y.d, t.y_lo = y.lo, t.yHp = p.yHp, t.yWp = p.yWp, t.yP = p.yP, t.yC = p.yC, t.yCoff = p.yCoff;
+    t.add = p.add, t.add_lo = o.add ? o.add->lo : nullptr, t.aHp = p.aHp, t.aWp = p.aWp, t.aP = p.aP, t.aC = p.aC;
+    t.act = o.act, t.slope = o.slope, t.stats = o.stats;
+    std::string err;
+    if (launch_conv_tc(t, x.d, x.lo, w->wt_hi, w->wt_lo, c->num_sms, s, &err) != 0) return fail(c, DVC_ERR_CUDA, "conv_tc: " + err);
+    return check_launch(c, "conv_tc");
+  }
+  if (o.add && o.add->lo) return fail(c, DVC_ERR_STATE, "conv: CUDA-core kernel cannot read a split addend");
   launch_conv_simt(p, x.B, c->two_level, s);
   return check_launch(c, "conv");
 }
@@ -306,25 +360,26 @@ static int run_xform(dvc_ctx* c, const Act& src, Act& dst, const XfOpt& o, cudaS
     return fail(c, DVC_ERR_SHAPE, "xform: shape mismatch");
   if (o.pad_mode == PAD_REFLECT && (dst.P >= dst.H || dst.P >= dst.W)) return fail(c, DVC_ERR_SHAPE, "xform: reflect pad too wide");
   XformParams p{};
-  p.src = src.d, p.sH = src.H, p.sW = src.W, p.sP = src.P, p.sC = src.C, p.sCoff = 0;
+  p.src = src.d, p.src_lo = src.lo, p.sH = src.H, p.sW = src.W, p.sP = src.P, p.sC = src.C, p.sCoff = 0;
+  p.dst_lo = dst.lo;
   p.dst = dst.d, p.dH = dst.H, p.dW = dst.W, p.dP = dst.P, p.dC = dst.C, p.dCoff = o.dCoff;
   p.C = C, p.pad_mode = o.pad_mode, p.up = o.up, p.sub = o.sub, p.rowpad = o.rowpad;
   p.stats = o.stats, p.count = o.count, p.eps = 1e-5f, p.scale = o.scale;
   if (o.res) {
     if (o.res->H != dst.H || o.res->W != dst.W || o.res->C < C) return fail(c, DVC_ERR_SHAPE, "xform: residual mismatch");
-    p.res = o.res->d, p.rP = o.res->P, p.rC = o.res->C;
+    p.res = o.res->d, p.res_lo = o.res->lo, p.rP = o.res->P, p.rC = o.res->C;
   }
   p.act = o.act, p.slope = o.slope;
   launch_xform(p, src.B, s);
   return check_launch(c, "xform");
 }
 
-static int run_pixnorm(dvc_ctx* c, const Act& src, float* dst, int dP, int pad_mode, const double* stats, double count,
-                       cudaStream_t s) {
+static int run_pixnorm(dvc_ctx* c, const Act& src, float* dst, float* dst_lo, int dP, int pad_mode, const double* stats,
+                       double count, cudaStream_t s) {
   if (src.C != 128 && src.C != 256 && src.C != 512) return fail(c, DVC_ERR_SHAPE, "pixnorm: channel count");
   PixNormParams p{};
-  p.src = src.d, p.sH = src.H, p.sW = src.W, p.sP = src.P, p.sC = src.C;
-  p.dst = dst, p.dP = dP, p.dC = src.C, p.C = src.C, p.pad_mode = pad_mode;
+  p.src = src.d, p.src_lo = src.lo, p.sH = src.H, p.sW = src.W, p.sP = src.P, p.sC = src.C;
+  p.dst = dst, p.dst_lo = dst_lo, p.dP = dP, p.dC = src.C, p.C = src.C, p.pad_mode = pad_mode;
   p.stats = stats, p.count = count, p.eps = 2.220446049250313e-16f;  // sys.float_info.epsilon
   launch_pixnorm(p, src.B, s);
   return check_launch(c, "pixnorm");
@@ -351,15 +406,15 @@ static int vgg_trunk(dvc_ctx* c, const std::string& tag, const Act& x0, const st
     Act nxt;
     if (name[0] == 'P') {
       key = "p" + std::to_string(block);
-      DVC_TRY(get_act(c, tag + "." + key, cur.B, cur.H / 2, cur.W / 2, cur.C, 1, &nxt, s));
-      launch_maxpool2(cur.d, cur.H, cur.W, cur.P, cur.C, nxt.d, 1, cur.B, s);
+      DVC_TRY(get_act(c, tag + "." + key, cur.B, cur.H / 2, cur.W / 2, cur.C, 1, &nxt, s, tc_mode(c)));
+      launch_maxpool2(cur.d, cur.lo, cur.H, cur.W, cur.P, cur.C, nxt.d, nxt.lo, 1, cur.B, s);
       DVC_TRY(check_launch(c, "maxpool"));
       block++, idx = 1;
     } else {
       key = "r" + std::to_string(block) + std::to_string(idx);
       const ConvW* w;
       DVC_TRY(need_conv(c, DVC_NET_VGG, name, &w));
-      DVC_TRY(get_act(c, tag + "." + key, cur.B, cur.H, cur.W, w->cout, 1, &nxt, s));
+      DVC_TRY(get_act(c, tag + "." + key, cur.B, cur.H, cur.W, w->cout, 1, &nxt, s, tc_mode(c)));
       ConvOpt o;
       o.act = ACT_RELU;
       DVC_TRY(run_conv(c, w, cur, nxt, o, s));
@@ -382,7 +437,8 @@ static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const c
   const int net = DVC_NET_WARP;
   const int B = n[0].B;
   Act cat;
-  DVC_TRY(get_act(c, tag + ".cat", B, h, w, 256, 1, &cat, s));
+  const bool sp = tc_mode(c);
+  DVC_TRY(get_act(c, tag + ".cat", B, h, w, 256, 1, &cat, s, sp));
 
   struct Head {
     const char* c1;
@@ -412,7 +468,7 @@ static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const c
     ConvOpt o1;
     o1.stats = st1;
     DVC_TRY(run_conv(c, w1, x, raw1, o1, s));
-    DVC_TRY(get_act(c, t + ".mid", B, x.H * hd.up_mid, x.W * hd.up_mid, w1->cout, 1, &mid, s));
+    DVC_TRY(get_act(c, t + ".mid", B, x.H * hd.up_mid, x.W * hd.up_mid, w1->cout, 1, &mid, s, sp));
     XfOpt x1;
     x1.pad_mode = PAD_REFLECT, x1.up = hd.up_mid, x1.stats = st1, x1.count = (double)x.H * x.W, x1.act = 2, x1.slope = s1;
     DVC_TRY(run_xform(c, raw1, mid, x1, s));
@@ -437,9 +493,9 @@ static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const c
 
   // three residual blocks (NonlocalNet.py:341-352), ping-pong between two padded buffers
   Act xa = cat, xb, raw, mid;
-  DVC_TRY(get_act(c, tag + ".res_b", B, h, w, 256, 1, &xb, s));
+  DVC_TRY(get_act(c, tag + ".res_b", B, h, w, 256, 1, &xb, s, sp));
   DVC_TRY(get_act(c, tag + ".res_raw", B, h, w, 256, 0, &raw, s));
-  DVC_TRY(get_act(c, tag + ".res_mid", B, h, w, 256, 1, &mid, s));
+  DVC_TRY(get_act(c, tag + ".res_mid", B, h, w, 256, 1, &mid, s, sp));
   for (int i = 0; i < 3; ++i) {
     const std::string base = "layer." + std::to_string(i);
     const ConvW *w1, *w2;
@@ -473,7 +529,7 @@ static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const c
   ConvOpt op;
   op.stats = stp;
   DVC_TRY(run_conv(c, wp, xa, raw, op, s));
-  DVC_TRY(run_pixnorm(c, raw, rows_out, 0, PAD_ZERO, stp, (double)h * w, s));
+  DVC_TRY(run_pixnorm(c, raw, rows_out, nullptr, 0, PAD_ZERO, stp, (double)h * w, s));
   return DVC_OK;
 }
 
@@ -512,7 +568,9 @@ static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* o
                   float slope) -> int {
     const ConvW* w;
     DVC_TRY(need_conv(c, net, name, &w));
-    DVC_TRY(get_act(c, tag + "." + name + "#" + std::to_string(uid++), x.B, x.H, x.W, w->cout, outP, y, s));
+    // outputs with a border (outP > 0) feed another convolution: hi/lo planes in tensor-core mode
+    DVC_TRY(get_act(c, tag + "." + name + "#" + std::to_string(uid++), x.B, x.H, x.W, w->cout, outP, y, s,
+                    tc_mode(c) && outP > 0));
     ConvOpt o;
     o.act = act, o.dil = dil, o.add = add, o.slope = slope;
     if (st) {
@@ -524,7 +582,7 @@ static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* o
   auto norm = [&](const char* name, const Act& raw, const double* st, Act* y, int outP, int up, int sub,
                   const float* scale) -> int {
     DVC_TRY(get_act(c, tag + "." + name + "#" + std::to_string(uid++), B, ((raw.H + sub - 1) / sub) * up,
-                    ((raw.W + sub - 1) / sub) * up, raw.C, outP, y, s));
+                    ((raw.W + sub - 1) / sub) * up, raw.C, outP, y, s, tc_mode(c)));
     XfOpt o;
     o.pad_mode = PAD_ZERO, o.up = up, o.sub = sub, o.stats = st, o.count = (double)raw.H * raw.W, o.scale = scale;
     return run_xform(c, raw, *y, o, s);
@@ -620,6 +678,7 @@ extern "C" int dvc_create(dvc_ctx** out, int device) {
   }
   dvc_ctx* c = new dvc_ctx();
   c->device = device;
+  c->num_sms = prop.multiProcessorCount;
   *out = c;
   return DVC_OK;
 }
@@ -634,6 +693,8 @@ extern "C" int dvc_destroy(dvc_ctx* c) {
     for (auto& kv : c->conv[n]) {
       if (kv.second.w) cudaFree(kv.second.w);
       if (kv.second.b) cudaFree(kv.second.b);
+      if (kv.second.wt_hi) cudaFree(kv.second.wt_hi);
+      if (kv.second.wt_lo) cudaFree(kv.second.wt_lo);
     }
     for (auto& kv : c->vec[n])
       if (kv.second) cudaFree(kv.second);
@@ -650,7 +711,8 @@ extern "C" const char* dvc_last_error(const dvc_ctx* c) { return c ? c->err.c_st
 
 extern "C" int dvc_set_math(dvc_ctx* c, int conv_math, int corr_math) {
   if (!c) return DVC_ERR_ARG;
-  if (conv_math != DVC_MATH_FP32) return fail(c, DVC_ERR_ARG, "conv math: only DVC_MATH_FP32 is available in this build");
+  if (conv_math != DVC_MATH_FP32 && conv_math != DVC_MATH_TF32X3) return fail(c, DVC_ERR_ARG, "conv math must be DVC_MATH_FP32 or DVC_MATH_TF32X3");
+  if (conv_math != c->conv_math) c->ex_valid = false, c->warp_cache_valid = false;
   if (corr_math != DVC_MATH_FP32 && corr_math != DVC_MATH_TF32X3 && corr_math != DVC_MATH_BF16X3)
     return fail(c, DVC_ERR_ARG, "unknown corr math");
   c->conv_math = conv_math, c->corr_math = corr_math;
@@ -736,7 +798,7 @@ extern "C" int dvc_vgg19_forward(dvc_ctx* c, const float* x, int B, int H, int W
   if (deepest < 0) return fail(c, DVC_ERR_ARG, "vgg19_forward: unknown out_key");
   Act x0;
   DVC_TRY(get_act(c, "mvgg.x0", B, H, W, 8, 1, &x0, s));
-  launch_nchw_to_act(x, 3, x0.d, B, H, W, 8, 1, PAD_ZERO, preprocess ? 1 : 0, s);
+  launch_nchw_to_act(x, 3, x0.d, nullptr, B, H, W, 8, 1, PAD_ZERO, preprocess ? 1 : 0, s);
   DVC_TRY(check_launch(c, "nchw_to_act"));
   VggMaps maps;
   DVC_TRY(vgg_trunk(c, "mvgg", x0, last_key, &maps, s));
@@ -744,7 +806,7 @@ extern "C" int dvc_vgg19_forward(dvc_ctx* c, const float* x, int B, int H, int W
     auto it = maps.m.find(keys[i] ? keys[i] : "");
     if (it == maps.m.end()) return fail(c, DVC_ERR_ARG, std::string("vgg19_forward: unknown out_key ") + (keys[i] ? keys[i] : "(null)"));
     const Act& a = it->second;
-    launch_act_to_nchw(a.d, a.H, a.W, a.P, a.C, 0, a.C, outs[i], B, s);
+    launch_act_to_nchw(a.d, a.lo, a.H, a.W, a.P, a.C, 0, a.C, outs[i], B, s);
     DVC_TRY(check_launch(c, "act_to_nchw"));
   }
   return DVC_OK;
@@ -756,8 +818,8 @@ static int features_from_nchw(dvc_ctx* c, const std::string& tag, const float* c
   // dims the VGG trunk produces for an HxW input (floor-mode pools)
   const int hs[4] = {H / 2, H / 4, H / 8, H / 16}, ws[4] = {W / 2, W / 4, W / 8, W / 16}, cs[4] = {128, 256, 512, 512};
   for (int k = 0; k < 4; ++k) {
-    DVC_TRY(get_act(c, tag + ".n" + std::to_string(k), B, hs[k], ws[k], cs[k], 1, &n[k], s));
-    launch_nchw_to_act(f[k], cs[k], n[k].d, B, hs[k], ws[k], cs[k], 1, PAD_REFLECT, 0, s);
+    DVC_TRY(get_act(c, tag + ".n" + std::to_string(k), B, hs[k], ws[k], cs[k], 1, &n[k], s, tc_mode(c)));
+    launch_nchw_to_act(f[k], cs[k], n[k].d, n[k].lo, B, hs[k], ws[k], cs[k], 1, PAD_REFLECT, 0, s);
     DVC_TRY(check_launch(c, "nchw_to_act"));
   }
   return DVC_OK;
@@ -810,7 +872,7 @@ extern "C" int dvc_colorvidnet_forward(dvc_ctx* c, const float* x, int B, int H,
   DVC_TRY(stats_begin(c, s));
   Act in0;
   DVC_TRY(get_act(c, "mcolor.in0", B, H, W, 8, 1, &in0, s));
-  launch_nchw_to_act(x, 7, in0.d, B, H, W, 8, 1, PAD_ZERO, 0, s);
+  launch_nchw_to_act(x, 7, in0.d, nullptr, B, H, W, 8, 1, PAD_ZERO, 0, s);
   DVC_TRY(check_launch(c, "nchw_to_act"));
   return colorvid(c, "mcolor", in0, out, s);
 }
@@ -848,8 +910,8 @@ static int normalised_features(dvc_ctx* c, const std::string& tag, VggMaps& maps
   const char* keys[4] = {"r22", "r32", "r42", "r52"};
   for (int k = 0; k < 4; ++k) {
     const Act& r = maps.m[keys[k]];
-    DVC_TRY(get_act(c, tag + ".n" + std::to_string(k), r.B, r.H, r.W, r.C, 1, &n[k], s));
-    DVC_TRY(run_pixnorm(c, r, n[k].d, 1, PAD_REFLECT, nullptr, 1.0, s));  // feature_normalize, util.py:155-158
+    DVC_TRY(get_act(c, tag + ".n" + std::to_string(k), r.B, r.H, r.W, r.C, 1, &n[k], s, tc_mode(c)));
+    DVC_TRY(run_pixnorm(c, r, n[k].d, n[k].lo, 1, PAD_REFLECT, nullptr, 1.0, s));  // feature_normalize, util.py:155-158
   }
   return DVC_OK;
 }
@@ -865,7 +927,7 @@ extern "C" int dvc_set_exemplar(dvc_ctx* c, const float* IB_lab, int H, int W, v
   CUDA_TRY(c, cudaMemcpyAsync(lab, IB_lab, (size_t)3 * H * W * 4, cudaMemcpyDefault, s));
   Act x0;
   DVC_TRY(get_act(c, "ex.x0", 1, H, W, 8, 1, &x0, s));
-  launch_nchw_to_act((float*)lab, 3, x0.d, 1, H, W, 8, 1, PAD_ZERO, 3, s);  // test.py:61-65
+  launch_nchw_to_act((float*)lab, 3, x0.d, nullptr, 1, H, W, 8, 1, PAD_ZERO, 3, s);  // test.py:61-65
   DVC_TRY(check_launch(c, "nchw_to_act"));
   VggMaps maps;
   DVC_TRY(vgg_trunk(c, "ex", x0, "r52", &maps, s));
@@ -899,7 +961,7 @@ extern "C" int dvc_colorize_frames(dvc_ctx* c, const float* IA_l, const float* I
   const int h = H / 4, w = W / 4, N = h * w;
   Act x0;
   DVC_TRY(get_act(c, "fr.x0", B, H, W, 8, 1, &x0, s));
-  launch_nchw_to_act(IA_l, 1, x0.d, B, H, W, 8, 1, PAD_ZERO, 2, s);  // FrameColor.py:6 + util.py:347-352
+  launch_nchw_to_act(IA_l, 1, x0.d, nullptr, B, H, W, 8, 1, PAD_ZERO, 2, s);  // FrameColor.py:6 + util.py:347-352
   DVC_TRY(check_launch(c, "nchw_to_act"));
   VggMaps maps;
   DVC_TRY(vgg_trunk(c, "fr", x0, "r52", &maps, s));

@@ -15,7 +15,8 @@
 namespace dvc {
 
 struct Act {
-  float* d = nullptr;  // pixel (b=0, yp=0, xp=0), channel 0
+  float* d = nullptr;   // pixel (b=0, yp=0, xp=0), channel 0; the hi plane when lo != nullptr
+  float* lo = nullptr;  // lo plane of a tf32 hi/lo split activation (value = hi + lo), same geometry
   int B = 0, H = 0, W = 0, C = 0, P = 0;
   int Hp() const { return H + 2 * P; }
   int Wp() const { return W + 2 * P; }
@@ -34,7 +35,8 @@ struct ConvParams {
   const float* bias;  // [CoutPad] (zeros beyond Cout) or nullptr
   int taps, dil, Cout, CoutPad, stride;
   int Ho, Wo;
-  float* y;  // destination padded NHWC (interior written) or nullptr
+  float* y;     // destination padded NHWC (interior written) or nullptr
+  float* y_lo;  // when set, the value is stored as tf32 hi/lo planes (y = hi plane)
   int yHp, yWp, yP, yC, yCoff;
   const float* add;  // optional addend with the output's logical size (skip connections)
   int aHp, aWp, aP, aC;
@@ -49,8 +51,11 @@ void launch_conv_simt(const ConvParams& p, int B, bool two_level, cudaStream_t s
 // ---- elementwise gather: InstanceNorm apply / PReLU / pad / up / sub / residual ----------------
 struct XformParams {
   const float* src;
+  const float* src_lo;  // optional lo plane of a split source
   int sH, sW, sP, sC, sCoff;
   float* dst;
+  float* dst_lo;  // optional: store as hi/lo planes
+  const float* res_lo;
   int dH, dW, dP, dC, dCoff;
   int C;
   int pad_mode, up, sub, rowpad;
@@ -68,8 +73,10 @@ void launch_xform(const XformParams& p, int B, cudaStream_t s);
 // ---- per-pixel channel L2 normalisation (feature_normalize, theta/phi) --------------------------
 struct PixNormParams {
   const float* src;
+  const float* src_lo;
   int sH, sW, sP, sC;
   float* dst;
+  float* dst_lo;
   int dP, dC;  // destination has the same logical HxW
   int C, pad_mode;
   const double* stats;  // optional channel sums [B][C][2] -> subtract mean over positions
@@ -82,11 +89,12 @@ void launch_pixnorm(const PixNormParams& p, int B, cudaStream_t s);
 // NCHW [B][Cs][H][W] -> padded NHWC with C channels (extra channels zero); mode: 0 copy,
 // 1 rgb -> vgg_preprocess (util.py:347-352), 2 centred L -> gray -> vgg_preprocess (util.py:97-101),
 // 3 centred Lab -> sRGB (util.py:379-414) -> vgg_preprocess
-void launch_nchw_to_act(const float* src, int Cs, float* dst, int B, int H, int W, int C, int P, int pad_mode,
-                        int mode, cudaStream_t s);
-void launch_act_to_nchw(const float* src, int H, int W, int P, int sC, int sCoff, int C, float* dst, int B,
-                        cudaStream_t s);
-void launch_maxpool2(const float* src, int sH, int sW, int sP, int C, float* dst, int dP, int B, cudaStream_t s);
+void launch_nchw_to_act(const float* src, int Cs, float* dst, float* dst_lo, int B, int H, int W, int C, int P,
+                        int pad_mode, int mode, cudaStream_t s);
+void launch_act_to_nchw(const float* src, const float* src_lo, int H, int W, int P, int sC, int sCoff, int C, float* dst,
+                        int B, cudaStream_t s);
+void launch_maxpool2(const float* src, const float* src_lo, int sH, int sW, int sP, int C, float* dst, float* dst_lo,
+                     int dP, int B, cudaStream_t s);
 // NCHW [B][3][H][W] -> V [B][H/4*W/4][4] (4th lane zero): F.avg_pool2d(.,4), NonlocalNet.py:491-493
 void launch_avgpool4_lab(const float* src, float* V, int B, int H, int W, cudaStream_t s);
 // y rows [B][N][4], sim rows [B][N] at h x w -> nearest x4 NCHW (NonlocalNet.py:499-500)

@@ -10,6 +10,32 @@ namespace dvc {
 
 namespace {
 
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+// value of a (possibly hi/lo split) activation
+__device__ __forceinline__ float4 ld4(const float* __restrict__ p, const float* __restrict__ lo, size_t off) {
+  float4 v = __ldg(reinterpret_cast<const float4*>(p + off));
+  if (lo) {
+    const float4 l = __ldg(reinterpret_cast<const float4*>(lo + off));
+    v.x += l.x, v.y += l.y, v.z += l.z, v.w += l.w;
+  }
+  return v;
+}
+// store as fp32, or as tf32 hi/lo planes for a tensor-core consumer (hi + lo reproduces v to 2^-24 relative)
+__device__ __forceinline__ void st4(float* __restrict__ p, float* __restrict__ lo, size_t off, float4 v) {
+  if (lo) {
+    const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+    *reinterpret_cast<float4*>(p + off) = h;
+    *reinterpret_cast<float4*>(lo + off) =
+        make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z), tf32_rna(v.w - h.w));
+  } else {
+    *reinterpret_cast<float4*>(p + off) = v;
+  }
+}
+
 __device__ __forceinline__ int reflect_idx(int i, int n) {
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;
@@ -55,8 +81,7 @@ __global__ void __launch_bounds__(256) xform_kernel(const XformParams p) {
       int y1 = y;
       if (p.rowpad) y1 = min(max(y - 1, 0), p.dH - 3);
       const int ys = (y1 / p.up) * p.sub, xs = (x / p.up) * p.sub;
-      v = __ldg(reinterpret_cast<const float4*>(
-          p.src + (((size_t)b * sHp + ys + p.sP) * sWp + xs + p.sP) * p.sC + p.sCoff + c));
+      v = ld4(p.src, p.src_lo, (((size_t)b * sHp + ys + p.sP) * sWp + xs + p.sP) * p.sC + p.sCoff + c);
       if (p.stats) {
         v.x = (v.x - s_mean[c + 0]) * s_rstd[c + 0];
         v.y = (v.y - s_mean[c + 1]) * s_rstd[c + 1];
@@ -69,8 +94,7 @@ __global__ void __launch_bounds__(256) xform_kernel(const XformParams p) {
       }
       if (p.res) {
         const int rHp = p.dH + 2 * p.rP, rWp = p.dW + 2 * p.rP;
-        const float4 r = __ldg(reinterpret_cast<const float4*>(
-            p.res + (((size_t)b * rHp + y + p.rP) * rWp + x + p.rP) * p.rC + c));
+        const float4 r = ld4(p.res, p.res_lo, (((size_t)b * rHp + y + p.rP) * rWp + x + p.rP) * p.rC + c);
         v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
       }
       if (p.act == 1) {
@@ -82,7 +106,7 @@ __global__ void __launch_bounds__(256) xform_kernel(const XformParams p) {
         v.w = v.w > 0.f ? v.w : v.w * p.slope;
       }
     }
-    *reinterpret_cast<float4*>(p.dst + (((size_t)b * dHp + yp) * dWp + xp) * p.dC + p.dCoff + c) = v;
+    st4(p.dst, p.dst_lo, (((size_t)b * dHp + yp) * dWp + xp) * p.dC + p.dCoff + c, v);
   }
 }
 
@@ -117,11 +141,11 @@ __global__ void __launch_bounds__(256) pixnorm_kernel(const PixNormParams p) {
     }
     float4 v[VPL];
     float ss = 0.f;
-    const float* sp = p.src + (((size_t)b * sHp + y + p.sP) * sWp + x + p.sP) * p.sC;
+    const size_t so = (((size_t)b * sHp + y + p.sP) * sWp + x + p.sP) * p.sC;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       if (inside) {
-        v[i] = __ldg(reinterpret_cast<const float4*>(sp + (i * 32 + lane) * 4));
+        v[i] = ld4(p.src, p.src_lo, so + (i * 32 + lane) * 4);
         v[i].x -= mean[i].x, v[i].y -= mean[i].y, v[i].z -= mean[i].z, v[i].w -= mean[i].w;
       } else {
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -130,15 +154,12 @@ __global__ void __launch_bounds__(256) pixnorm_kernel(const PixNormParams p) {
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float inv = 1.0f / (sqrtf(ss) + p.eps);
-    float* dp = p.dst + (((size_t)b * dHp + yp) * dWp + xp) * p.dC;
+    const size_t dof = (((size_t)b * dHp + yp) * dWp + xp) * p.dC;
+    const float n = sqrtf(ss) + p.eps;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       // true division like torch.div(x, norm) (util.py:157, NonlocalNet.py:471)
-      const float n = sqrtf(ss) + p.eps;
-      float4 o4 = make_float4(v[i].x / n, v[i].y / n, v[i].z / n, v[i].w / n);
-      (void)inv;
-      *reinterpret_cast<float4*>(dp + (i * 32 + lane) * 4) = o4;
+      st4(p.dst, p.dst_lo, dof + (i * 32 + lane) * 4, make_float4(v[i].x / n, v[i].y / n, v[i].z / n, v[i].w / n));
     }
   }
 }
@@ -172,7 +193,8 @@ __device__ __forceinline__ float3 lab_to_srgb(float L, float a, float bb) {
 }
 
 __global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restrict__ src, int Cs, float* __restrict__ dst,
-                                                          int H, int W, int C, int P, int pad_mode, int mode) {
+                                                          float* __restrict__ dst_lo, int H, int W, int C, int P,
+                                                          int pad_mode, int mode) {
   const int b = blockIdx.y;
   const int Hp = H + 2 * P, Wp = W + 2 * P;
   const size_t plane = (size_t)H * W;
@@ -185,13 +207,25 @@ __global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restric
       inside = true;
     }
     float* dp = dst + ((size_t)b * Hp * Wp + pix) * C;
+    float* lp = dst_lo ? dst_lo + ((size_t)b * Hp * Wp + pix) * C : nullptr;
     if (!inside) {
-      for (int c = 0; c < C; ++c) dp[c] = 0.f;
+      for (int c = 0; c < C; ++c) {
+        dp[c] = 0.f;
+        if (lp) lp[c] = 0.f;
+      }
       continue;
     }
     const float* sp = src + (size_t)b * Cs * plane + (size_t)y * W + x;
     if (mode == 0) {
-      for (int c = 0; c < C; ++c) dp[c] = c < Cs ? __ldg(sp + c * plane) : 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float v = c < Cs ? __ldg(sp + c * plane) : 0.f;
+        if (lp) {
+          const float h = tf32_rna(v);
+          dp[c] = h, lp[c] = tf32_rna(v - h);
+        } else {
+          dp[c] = v;
+        }
+      }
     } else {
       float3 rgb;
       if (mode == 1) {
@@ -212,8 +246,9 @@ __global__ void __launch_bounds__(256) nchw_to_act_kernel(const float* __restric
 }
 
 // interior of a padded NHWC activation -> NCHW.  One block = 32 pixels x 32 channels via smem transpose.
-__global__ void __launch_bounds__(256) act_to_nchw_kernel(const float* __restrict__ src, int H, int W, int P, int sC,
-                                                          int sCoff, int C, float* __restrict__ dst) {
+__global__ void __launch_bounds__(256) act_to_nchw_kernel(const float* __restrict__ src, const float* __restrict__ src_lo,
+                                                          int H, int W, int P, int sC, int sCoff, int C,
+                                                          float* __restrict__ dst) {
   __shared__ float t[32][33];
   const int b = blockIdx.z;
   const int Hp = H + 2 * P, Wp = W + 2 * P;
@@ -224,7 +259,9 @@ __global__ void __launch_bounds__(256) act_to_nchw_kernel(const float* __restric
     float v = 0.f;
     if (pix < H * W && c0 + tx < C) {
       const int y = pix / W, x = pix - y * W;
-      v = __ldg(src + (((size_t)b * Hp + y + P) * Wp + x + P) * sC + sCoff + c0 + tx);
+      const size_t o = (((size_t)b * Hp + y + P) * Wp + x + P) * sC + sCoff + c0 + tx;
+      v = __ldg(src + o);
+      if (src_lo) v += __ldg(src_lo + o);
     }
     t[r][tx] = v;
   }
@@ -235,8 +272,9 @@ __global__ void __launch_bounds__(256) act_to_nchw_kernel(const float* __restric
   }
 }
 
-__global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__ src, int sH, int sW, int sP, int C,
-                                                       float* __restrict__ dst, int dP) {
+__global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__ src, const float* __restrict__ src_lo,
+                                                       int sH, int sW, int sP, int C, float* __restrict__ dst,
+                                                       float* __restrict__ dst_lo, int dP) {
   const int b = blockIdx.y;
   const int dH = sH / 2, dW = sW / 2;
   const int dHp = dH + 2 * dP, dWp = dW + 2 * dP, sHp = sH + 2 * sP, sWp = sW + 2 * sP;
@@ -249,17 +287,17 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__
     const int y = yp - dP, x = xp - dP;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (y >= 0 && y < dH && x >= 0 && x < dW) {
-      const float* sp = src + (((size_t)b * sHp + 2 * y + sP) * sWp + 2 * x + sP) * C + c;
-      const float4 a = __ldg(reinterpret_cast<const float4*>(sp));
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(sp + C));
-      const float4 c4 = __ldg(reinterpret_cast<const float4*>(sp + (size_t)sWp * C));
-      const float4 d = __ldg(reinterpret_cast<const float4*>(sp + (size_t)sWp * C + C));
+      const size_t so = (((size_t)b * sHp + 2 * y + sP) * sWp + 2 * x + sP) * C + c;
+      const float4 a = ld4(src, src_lo, so);
+      const float4 b4 = ld4(src, src_lo, so + C);
+      const float4 c4 = ld4(src, src_lo, so + (size_t)sWp * C);
+      const float4 d = ld4(src, src_lo, so + (size_t)sWp * C + C);
       v.x = fmaxf(fmaxf(a.x, b4.x), fmaxf(c4.x, d.x));
       v.y = fmaxf(fmaxf(a.y, b4.y), fmaxf(c4.y, d.y));
       v.z = fmaxf(fmaxf(a.z, b4.z), fmaxf(c4.z, d.z));
       v.w = fmaxf(fmaxf(a.w, b4.w), fmaxf(c4.w, d.w));
     }
-    *reinterpret_cast<float4*>(dst + ((size_t)b * dHp * dWp + pix) * C + c) = v;
+    st4(dst, dst_lo, ((size_t)b * dHp * dWp + pix) * C + c, v);
   }
 }
 
@@ -416,24 +454,25 @@ void launch_pixnorm(const PixNormParams& p, int B, cudaStream_t s) {
   launch_counter_add(1);
 }
 
-void launch_nchw_to_act(const float* src, int Cs, float* dst, int B, int H, int W, int C, int P, int pad_mode,
-                        int mode, cudaStream_t s) {
+void launch_nchw_to_act(const float* src, int Cs, float* dst, float* dst_lo, int B, int H, int W, int C, int P,
+                        int pad_mode, int mode, cudaStream_t s) {
   dim3 grid(grid_for((long)(H + 2 * P) * (W + 2 * P), 256), B);
-  nchw_to_act_kernel<<<grid, 256, 0, s>>>(src, Cs, dst, H, W, C, P, pad_mode, mode);
+  nchw_to_act_kernel<<<grid, 256, 0, s>>>(src, Cs, dst, dst_lo, H, W, C, P, pad_mode, mode);
   launch_counter_add(1);
 }
 
-void launch_act_to_nchw(const float* src, int H, int W, int P, int sC, int sCoff, int C, float* dst, int B,
-                        cudaStream_t s) {
+void launch_act_to_nchw(const float* src, const float* src_lo, int H, int W, int P, int sC, int sCoff, int C, float* dst,
+                        int B, cudaStream_t s) {
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
-  act_to_nchw_kernel<<<grid, 256, 0, s>>>(src, H, W, P, sC, sCoff, C, dst);
+  act_to_nchw_kernel<<<grid, 256, 0, s>>>(src, src_lo, H, W, P, sC, sCoff, C, dst);
   launch_counter_add(1);
 }
 
-void launch_maxpool2(const float* src, int sH, int sW, int sP, int C, float* dst, int dP, int B, cudaStream_t s) {
+void launch_maxpool2(const float* src, const float* src_lo, int sH, int sW, int sP, int C, float* dst, float* dst_lo,
+                     int dP, int B, cudaStream_t s) {
   const long total = (long)(sH / 2 + 2 * dP) * (sW / 2 + 2 * dP) * (C / 4);
   dim3 grid(grid_for(total, 256), B);
-  maxpool2_kernel<<<grid, 256, 0, s>>>(src, sH, sW, sP, C, dst, dP);
+  maxpool2_kernel<<<grid, 256, 0, s>>>(src, src_lo, sH, sW, sP, C, dst, dst_lo, dP);
   launch_counter_add(1);
 }
 

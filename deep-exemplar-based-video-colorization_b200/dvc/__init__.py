@@ -272,7 +272,12 @@ class Context:
         if not act:
             return flat
         B, H, W, C, P = list(sig)
-        t = flat[: B * (H + 2 * P) * (W + 2 * P) * C].view(B, H + 2 * P, W + 2 * P, C)
+        split = P < 0  # hi/lo planes of a tensor-core activation are stored back to back
+        if split:
+            P = -1 - P
+        n = B * (H + 2 * P) * (W + 2 * P) * C
+        t = flat[:n] + flat[n:2 * n] if split else flat[:n]
+        t = t.view(B, H + 2 * P, W + 2 * P, C)
         return t[:, P:P + H, P:P + W, :].permute(0, 3, 1, 2).contiguous()
 
     # ---- introspection ---------------------------------------------------------------------------

@@ -32,9 +32,22 @@ def ab_gate(ours, g):
     return err, max(1e-3, 2.0 * floor)
 
 
+@pytest.fixture(params=["fp32", "tf32x3"])
+def conv_math(request, ctx):
+    """Convolutions on CUDA cores (exact fp32, two-level accumulation) and on tcgen05 (3xTF32 operand split)."""
+    import dvc
+
+    if request.param == "tf32x3":
+        ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
+    else:
+        ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
+    yield request.param
+    ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
+
+
 # ------------------------------------------------------------------------------------------ VGG19
 @pytest.mark.parametrize("name", ["small_32x48", "padbranch_40x64"])
-def test_vgg19_module_vs_golden(ctx, name):
+def test_vgg19_module_vs_golden(ctx, conv_math, name):
     g = load_golden(name)
     IA = torch.from_numpy(g["IA_lab"])
     x = O.gray2rgb_batch(IA[:, 0:1]).cuda()
@@ -46,7 +59,7 @@ def test_vgg19_module_vs_golden(ctx, name):
         assert err <= 1e-4 * np.abs(ref).max(), (k, err, np.abs(ref).max())
 
 
-def test_vgg19_all_keys_and_no_preprocess(ctx, sds):
+def test_vgg19_all_keys_and_no_preprocess(ctx, conv_math, sds):
     x = torch.rand(2, 3, 32, 48, generator=torch.Generator().manual_seed(5))
     keys = ["r11", "p1", "r21", "r34", "p3", "r44", "r54", "p5"]
     with torch.no_grad():
@@ -113,7 +126,7 @@ def test_corr_golden_operands(ctx):
 
 # ------------------------------------------------------------------------------------------ WarpNet
 @pytest.mark.parametrize("name", ["small_32x48", "padbranch_40x64", "softmax_32x64", "softmax5_48x48", "batch2_32x32"])
-def test_warpnet_module_vs_golden(ctx, sds, name):
+def test_warpnet_module_vs_golden(ctx, conv_math, sds, name):
     g = load_golden(name)
     IA, IB = torch.from_numpy(g["IA_lab"]), torch.from_numpy(g["IB_lab"])
     T = float(g["temperature"])
@@ -154,7 +167,7 @@ def test_warpnet_rejects_illegal_shapes(ctx):
 
 # ------------------------------------------------------------------------------------------ ColorVidNet
 @pytest.mark.parametrize("name", ["small_32x48", "padbranch_40x64", "batch2_32x32"])
-def test_colorvidnet_module_vs_golden(ctx, name):
+def test_colorvidnet_module_vs_golden(ctx, conv_math, name):
     g = load_golden(name)
     IA, last = torch.from_numpy(g["IA_lab"]), torch.from_numpy(g["IA_last_lab"])
     up = lambda a: torch.nn.functional.interpolate(torch.from_numpy(a), scale_factor=4, mode="nearest")
@@ -166,7 +179,7 @@ def test_colorvidnet_module_vs_golden(ctx, name):
 
 # ------------------------------------------------------------------------------------------ fused frame path
 @pytest.mark.parametrize("name", ["small_32x48", "padbranch_40x64", "softmax_32x64", "softmax5_48x48", "default_216x384"])
-def test_fused_frame_vs_golden(ctx, name):
+def test_fused_frame_vs_golden(ctx, conv_math, name):
     g = load_golden(name)
     IA, IB, last = (torch.from_numpy(g[k]) for k in ("IA_lab", "IB_lab", "IA_last_lab"))
     T = float(g["temperature"])
@@ -184,7 +197,7 @@ def test_fused_frame_vs_golden(ctx, name):
     assert err <= tol, (err, tol)
 
 
-def test_fused_clip_recurrence(ctx):
+def test_fused_clip_recurrence(ctx, conv_math):
     """dvc_colorize_clip == chaining dvc_colorize_frames with last = cat(L, ab) (test.py:96), bit for bit, and
     every frame matches the reference under teacher forcing."""
     g = load_golden("clip3_32x48")
@@ -206,7 +219,7 @@ def test_fused_clip_recurrence(ctx):
         last = torch.cat((L, torch.from_numpy(ref[t:t + 1]).cuda()), 1)
 
 
-def test_fused_batch_equals_single(ctx):
+def test_fused_batch_equals_single(ctx, conv_math):
     IB = make_lab(40, 1, 32, 64)
     ctx.set_exemplar(IB)
     L = make_lab(41, 3, 32, 64)[:, 0:1].cuda()
@@ -231,7 +244,7 @@ def test_exemplar_export_import_roundtrip(ctx):
 
 
 # ------------------------------------------------------------------------------------------ full-size properties
-def test_full_size_480x864_properties(ctx):
+def test_full_size_480x864_properties(ctx, conv_math):
     """BASELINE config 2 size (480x854 padded to 480x864, N=25920): properties that need no full oracle run."""
     H, W = 480, 864
     IB = make_lab(60, 1, H, W)
@@ -255,7 +268,7 @@ def test_full_size_480x864_properties(ctx):
     assert torch.equal(ab, ab3)
 
 
-def test_oracle_on_the_fly_64x64(ctx, sds):
+def test_oracle_on_the_fly_64x64(ctx, conv_math, sds):
     """Seeded inputs not in the golden set, checked against the CPU oracle run on this machine."""
     IA, IB, last = make_lab(70, 1, 64, 64), make_lab(71, 1, 64, 64), make_lab(72, 1, 64, 64)
     sds64 = {k: O._cast(v, torch.float64) for k, v in sds.items()}

@@ -15,7 +15,11 @@ for net, key in ((dvc.NET_VGG, "vgg"), (dvc.NET_WARP, "warp"), (dvc.NET_COLOR, "
 G = lambda n: dict(np.load(os.path.join(ROOT, "tests", "golden", n + ".npz")))
 
 def run(H, W, seed, tl):
-    ctx.debug_flag("two_level", tl)
+    if tl == 2:
+        ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
+    else:
+        ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
+        ctx.debug_flag("two_level", tl)
     IA, IB, last = make_lab(seed, 1, H, W), make_lab(seed + 1, 1, H, W), make_lab(seed + 2, 1, H, W)
     ex64, ex32 = {}, {}
     with torch.no_grad():
@@ -27,6 +31,7 @@ def run(H, W, seed, tl):
     ctx.set_exemplar(IB)
     ab, warp, sim = ctx.colorize_frames(IA[:, 0:1].cuda(), last.cuda(), 1e-10, want_warp=True)
     N = (H // 4) * (W // 4)
+    print(f"  (mode {tl}: 0 plain fp32, 1 two-level fp32, 2 tcgen05 tf32x3)")
     th = ctx.debug_buffer("fr.theta", act=False)[: N * 256].view(N, 256).t().cpu().double()
     ph = ctx.debug_buffer("ex.phi", act=False)[: N * 256].view(N, 256).t().cpu().double()
     e_th = (th - ex64["theta_hat"][0]).abs().max().item(); e_th32 = (ex32["theta_hat"][0].double() - ex64["theta_hat"][0]).abs().max().item()
@@ -46,9 +51,14 @@ def run(H, W, seed, tl):
         t = ctx.debug_buffer(nm).cpu().double()
         print(f"    {nm} rel err ours {float((t-ref).abs().max()/ref.abs().max()):.2e}  cpu32 {float((fA32[int(nm[-2])-1].double()-ref).abs().max()/ref.abs().max()):.2e}")
 
-for tl in (0, 1):
+MODES = [int(a) for a in sys.argv[1:]] or [1, 2]
+for tl in MODES:
     for name in ("small_32x48", "padbranch_40x64"):
-        g = G(name); ctx.debug_flag("two_level", tl)
+        g = G(name)
+        if tl == 2:
+            ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
+        else:
+            ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32); ctx.debug_flag("two_level", tl)
         IA, last = torch.from_numpy(g["IA_lab"]), torch.from_numpy(g["IA_last_lab"])
         up = lambda a: torch.nn.functional.interpolate(torch.from_numpy(a), scale_factor=4, mode="nearest")
         x = torch.cat((IA[:, 0:1], up(g["warped32"])[:, 1:3], up(g["sim32"]), last), 1)
@@ -59,8 +69,12 @@ for tl in (0, 1):
 # timing impact
 H, W = 480, 864
 ctx.set_exemplar(make_lab(60, 1, H, W)); L = make_lab(61, 1, H, W)[:, 0:1].cuda(); last = torch.zeros(1, 3, H, W, device="cuda")
-for tl in (0, 1):
-    ctx.debug_flag("two_level", tl)
+for tl in MODES:
+    if tl == 2:
+        ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
+    else:
+        ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32); ctx.debug_flag("two_level", tl)
+    ctx.set_exemplar(make_lab(60, 1, H, W))
     for _ in range(2): ctx.colorize_frames(L, last)
     torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True); e0.record()
     for _ in range(3): ctx.colorize_frames(L, last)
