@@ -28,7 +28,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int A_BYTES = BM * 128;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 template <int BN>
 struct Cfg {
@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                    const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const ConvTcParams p) {
   using C = Cfg<BN>;
   constexpr uint32_t IDESC = tc::umma_idesc(2u, BM, BN);
+  constexpr int CPT = BN / 2;  // output channels per epilogue thread (two warps share a TMEM lane quarter)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -67,6 +68,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const int total_tiles = m_tiles * n_tiles;
   const int kbs = p.Cin / 32;
   const int nk = p.taps * kbs;
+  // The TMEM accumulator truncates on every tcgen05.mma; a chunk of `kc` k-blocks (12*kc accumulations) is
+  // therefore summed in TMEM from zero and then added -- with round-to-nearest fp32 adds -- to a register total
+  // by the epilogue warps (the tensor-core analogue of conv_simt.cu's two-level accumulation).
+  const int kc = p.kc;
+  const int nchunks = (nk + kc - 1) / kc;
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tmXh);
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc::tma_prefetch_desc(&tmWh);
     tc::tma_prefetch_desc(&tmWl);
     for (int i = 0; i < C::STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
-    for (int i = 0; i < 2; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 4);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 8);
     tc::fence_barrier_init();
   }
   if (warp == 1) {
@@ -115,41 +121,43 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        tc::mbar_wait(&tempty[buf], acc_phase ^ 1);
-        tc::tc_fence_after();
-        const uint32_t d = tmem_base + buf * BN;
-        for (int k = 0; k < nk; ++k) {
-          tc::mbar_wait(&full[stage], phase);
+      uint32_t chunk_id = 0;  // global chunk counter: TMEM buffer = chunk_id & 1
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int ch = 0; ch < nchunks; ++ch, ++chunk_id) {
+          const int buf = chunk_id & 1;
+          const uint32_t acc_phase = (chunk_id >> 1) & 1;
+          tc::mbar_wait(&tempty[buf], acc_phase ^ 1);
           tc::tc_fence_after();
-          const uint32_t sa = tc::smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint64_t dXh = tc::umma_desc_k128(sa), dXl = tc::umma_desc_k128(sa + A_BYTES);
-          const uint64_t dWh = tc::umma_desc_k128(sa + 2 * A_BYTES), dWl = tc::umma_desc_k128(sa + 2 * A_BYTES + C::B_BYTES);
+          const uint32_t d = tmem_base + buf * BN;
+          const int k_end = min((ch + 1) * kc, nk);
+          for (int k = ch * kc; k < k_end; ++k) {
+            tc::mbar_wait(&full[stage], phase);
+            tc::tc_fence_after();
+            const uint32_t sa = tc::smem_u32(smem + stage * C::STAGE_BYTES);
+            const uint64_t dXh = tc::umma_desc_k128(sa), dXl = tc::umma_desc_k128(sa + A_BYTES);
+            const uint64_t dWh = tc::umma_desc_k128(sa + 2 * A_BYTES), dWl = tc::umma_desc_k128(sa + 2 * A_BYTES + C::B_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-            tc::umma_ss<true>(d, dXl + adv, dWh + adv, IDESC, (k | kk) ? 1u : 0u);
-            tc::umma_ss<true>(d, dXh + adv, dWl + adv, IDESC, 1u);
-            tc::umma_ss<true>(d, dXh + adv, dWh + adv, IDESC, 1u);
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+              tc::umma_ss<true>(d, dXl + adv, dWh + adv, IDESC, (k > ch * kc || kk) ? 1u : 0u);
+              tc::umma_ss<true>(d, dXh + adv, dWl + adv, IDESC, 1u);
+              tc::umma_ss<true>(d, dXh + adv, dWh + adv, IDESC, 1u);
+            }
+            tc::umma_commit(&empty[stage]);
+            if (k == k_end - 1) tc::umma_commit(&tfull[buf]);
+            if (++stage == C::STAGES) stage = 0, phase ^= 1;
           }
-          tc::umma_commit(&empty[stage]);
-          if (k == nk - 1) tc::umma_commit(&tfull[buf]);
-          if (++stage == C::STAGES) stage = 0, phase ^= 1;
         }
       }
     }
   } else {
-    // ================= epilogue: one output pixel per thread =================
-    const int q = warp & 3;
-    const int etid = threadIdx.x - 64;  // 0..127
+    // ================= epilogue: 8 warps; thread = one output pixel x BN/2 channels =================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;       // which half of the tile's channels
+    const int etid = threadIdx.x - 64;      // 0..255
     const int img = p.Hp * p.Wp;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+    uint32_t chunk_id = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int m0 = mt * BM, n0 = nt * BN;
       const int pp = m0 + q * 32 + lane;
@@ -166,101 +174,120 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       }
       const size_t yoff = valid ? ((((size_t)b * p.yHp + yo + p.yP) * p.yWp + xo + p.yP) * p.yC + p.yCoff) : 0;
       const size_t aoff = (valid && p.add) ? ((((size_t)b * p.aHp + yo + p.aP) * p.aWp + xo + p.aP) * p.aC) : 0;
-      // statistics are per image: a tile that straddles two images falls back to per-thread atomics
       const int b_first = m0 / img, b_last = min(m0 + BM - 1, p.Mtot - 1) / img;
       const bool uniform_img = (b_first == b_last);
       if (p.stats) {
-        for (int i = etid; i < 2 * BN; i += 128) s_stat[i] = 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = etid; i < 2 * BN; i += 256) s_stat[i] = 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      tc::mbar_wait(&tfull[buf], acc_phase);
-      tc::tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int ch0 = n0 + c * 32;
-        if (ch0 >= p.Cout) break;  // uniform
-        uint32_t r[32];
-        __syncwarp();
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, r);
-        tc::tmem_ld_wait();
-        float v[32];
+
+      // ---- chunk sums: TMEM -> registers, fp32 round-to-nearest accumulation ----
+      float tot[CPT];
+      for (int ch = 0; ch < nchunks; ++ch, ++chunk_id) {
+        const int buf = chunk_id & 1;
+        const uint32_t acc_phase = (chunk_id >> 1) & 1;
+        tc::mbar_wait(&tfull[buf], acc_phase);
+        tc::tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[j] = __uint_as_float(r[j]) + bv.x, v[j + 1] = __uint_as_float(r[j + 1]) + bv.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + bv.z, v[j + 3] = __uint_as_float(r[j + 3]) + bv.w;
-        }
-        if (p.add && valid) {
+        for (int c = 0; c < CPT / 32; ++c) {
+          uint32_t r[32];
+          __syncwarp();
+          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * CPT + c * 32, r);
+          tc::tmem_ld_wait();
+          if (ch == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 av = __ldg(reinterpret_cast<const float4*>(p.add + aoff + ch0 + j));
-            if (p.add_lo) {
-              const float4 al = __ldg(reinterpret_cast<const float4*>(p.add_lo + aoff + ch0 + j));
-              av.x += al.x, av.y += al.y, av.z += al.z, av.w += al.w;
-            }
-            v[j] += av.x, v[j + 1] += av.y, v[j + 2] += av.z, v[j + 3] += av.w;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
-          if (p.act == ACT_LRELU) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
-        }
-        if (valid) {
-          if (p.y_lo) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float h[4], l[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) h[t] = tf32_rna(v[j + t]), l[t] = tf32_rna(v[j + t] - h[t]);
-              *reinterpret_cast<float4*>(p.y + yoff + ch0 + j) = make_float4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<float4*>(p.y_lo + yoff + ch0 + j) = make_float4(l[0], l[1], l[2], l[3]);
-            }
+            for (int j = 0; j < 32; ++j) tot[c * 32 + j] = __uint_as_float(r[j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(p.y + yoff + ch0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; ++j) tot[c * 32 + j] += __uint_as_float(r[j]);
           }
         }
-        if (p.stats) {
-          if (uniform_img) {
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+      }
+
+      // ---- bias, skip addend, activation, statistics, masked store ----
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float s = valid ? v[j] : 0.f, sq = valid ? v[j] * v[j] : 0.f;
+      for (int c = 0; c < CPT / 32; ++c) {
+        const int ch0 = n0 + half * CPT + c * 32;
+        if (ch0 < p.Cout) {
+          float v[32];
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + j));
+            v[j] = tot[c * 32 + j] + bv.x, v[j + 1] = tot[c * 32 + j + 1] + bv.y;
+            v[j + 2] = tot[c * 32 + j + 2] + bv.z, v[j + 3] = tot[c * 32 + j + 3] + bv.w;
+          }
+          if (p.add && valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 av = __ldg(reinterpret_cast<const float4*>(p.add + aoff + ch0 + j));
+              if (p.add_lo) {
+                const float4 al = __ldg(reinterpret_cast<const float4*>(p.add_lo + aoff + ch0 + j));
+                av.x += al.x, av.y += al.y, av.z += al.z, av.w += al.w;
               }
-              if (lane == j) {
-                atomicAdd(&s_stat[c * 32 + j], s);
-                atomicAdd(&s_stat[BN + c * 32 + j], sq);
-              }
+              v[j] += av.x, v[j + 1] += av.y, v[j + 2] += av.z, v[j + 3] += av.w;
             }
-          } else if (valid) {
+          }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              atomicAdd(&p.stats[((size_t)b * p.Cout + ch0 + j) * 2 + 0], (double)v[j]);
-              atomicAdd(&p.stats[((size_t)b * p.Cout + ch0 + j) * 2 + 1], (double)v[j] * (double)v[j]);
+          for (int j = 0; j < 32; ++j) {
+            if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+            if (p.act == ACT_LRELU) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+          }
+          if (valid) {
+            if (p.y_lo) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float h[4], l[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) h[t] = tf32_rna(v[j + t]), l[t] = tf32_rna(v[j + t] - h[t]);
+                *reinterpret_cast<float4*>(p.y + yoff + ch0 + j) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(p.y_lo + yoff + ch0 + j) = make_float4(l[0], l[1], l[2], l[3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(p.y + yoff + ch0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          }
+          if (p.stats) {
+            if (uniform_img) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float s = valid ? v[j] : 0.f, sq = valid ? v[j] * v[j] : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                  s += __shfl_xor_sync(0xffffffffu, s, o);
+                  sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                }
+                if (lane == j) {
+                  atomicAdd(&s_stat[half * CPT + c * 32 + j], s);
+                  atomicAdd(&s_stat[BN + half * CPT + c * 32 + j], sq);
+                }
+              }
+            } else if (valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                atomicAdd(&p.stats[((size_t)b * p.Cout + ch0 + j) * 2 + 0], (double)v[j]);
+                atomicAdd(&p.stats[((size_t)b * p.Cout + ch0 + j) * 2 + 1], (double)v[j] * (double)v[j]);
+              }
             }
           }
         }
       }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tempty[buf]);
       if (p.stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (uniform_img) {
-          for (int i = etid; i < BN; i += 128) {
-            const int ch = n0 + i;
-            if (ch < p.Cout) {
-              atomicAdd(&p.stats[((size_t)b_first * p.Cout + ch) * 2 + 0], (double)s_stat[i]);
-              atomicAdd(&p.stats[((size_t)b_first * p.Cout + ch) * 2 + 1], (double)s_stat[BN + i]);
+          for (int i = etid; i < BN; i += 256) {
+            const int chn = n0 + i;
+            if (chn < p.Cout) {
+              atomicAdd(&p.stats[((size_t)b_first * p.Cout + chn) * 2 + 0], (double)s_stat[i]);
+              atomicAdd(&p.stats[((size_t)b_first * p.Cout + chn) * 2 + 1], (double)s_stat[BN + i]);
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
   }
@@ -299,6 +326,7 @@ int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, 
     return -1;
   };
   if (p.Cin % 32) return fail("Cin must be a multiple of 32");
+  if (p.kc < 1) return fail("kc must be >= 1");
   const int BN = conv_tc_pick_bn(p.Cout);
   if (p.CoutPad % BN) return fail("CoutPad must be a multiple of the channel tile");
   CUtensorMap mXh, mXl, mWh, mWl;

@@ -21,6 +21,7 @@ struct ConvTcParams {
   int act;
   float slope;
   double* stats;  // optional [B][Cout][2]
+  int kc;         // k-blocks (32 input channels each) summed in TMEM before promotion to fp32 registers
 };
 
 int conv_tc_pick_bn(int cout);  // channel tile (64 / 128 / 256) used for `cout` output channels

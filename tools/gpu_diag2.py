@@ -15,8 +15,8 @@ for net, key in ((dvc.NET_VGG, "vgg"), (dvc.NET_WARP, "warp"), (dvc.NET_COLOR, "
 G = lambda n: dict(np.load(os.path.join(ROOT, "tests", "golden", n + ".npz")))
 
 def run(H, W, seed, tl):
-    if tl == 2:
-        ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
+    if tl >= 20:
+        ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3); ctx.debug_flag("tc_kc", tl - 20)
     else:
         ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
         ctx.debug_flag("two_level", tl)
@@ -31,7 +31,7 @@ def run(H, W, seed, tl):
     ctx.set_exemplar(IB)
     ab, warp, sim = ctx.colorize_frames(IA[:, 0:1].cuda(), last.cuda(), 1e-10, want_warp=True)
     N = (H // 4) * (W // 4)
-    print(f"  (mode {tl}: 0 plain fp32, 1 two-level fp32, 2 tcgen05 tf32x3)")
+    print(f"  (mode {tl}: 0 plain fp32, 1 two-level fp32, 2x tcgen05 tf32x3 with kc = x)")
     th = ctx.debug_buffer("fr.theta", act=False)[: N * 256].view(N, 256).t().cpu().double()
     ph = ctx.debug_buffer("ex.phi", act=False)[: N * 256].view(N, 256).t().cpu().double()
     e_th = (th - ex64["theta_hat"][0]).abs().max().item(); e_th32 = (ex32["theta_hat"][0].double() - ex64["theta_hat"][0]).abs().max().item()
@@ -55,8 +55,8 @@ MODES = [int(a) for a in sys.argv[1:]] or [1, 2]
 for tl in MODES:
     for name in ("small_32x48", "padbranch_40x64"):
         g = G(name)
-        if tl == 2:
-            ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
+        if tl >= 20:
+            ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3); ctx.debug_flag("tc_kc", tl - 20)
         else:
             ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32); ctx.debug_flag("two_level", tl)
         IA, last = torch.from_numpy(g["IA_lab"]), torch.from_numpy(g["IA_last_lab"])
@@ -70,8 +70,8 @@ for tl in MODES:
 H, W = 480, 864
 ctx.set_exemplar(make_lab(60, 1, H, W)); L = make_lab(61, 1, H, W)[:, 0:1].cuda(); last = torch.zeros(1, 3, H, W, device="cuda")
 for tl in MODES:
-    if tl == 2:
-        ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
+    if tl >= 20:
+        ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3); ctx.debug_flag("tc_kc", tl - 20)
     else:
         ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32); ctx.debug_flag("two_level", tl)
     ctx.set_exemplar(make_lab(60, 1, H, W))
