@@ -154,6 +154,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--corr-math", default=os.environ.get("DVC_CORR_MATH", "tf32x3"), choices=["fp32", "tf32x3", "bf16x3"])
+    ap.add_argument("--conv-math", default=os.environ.get("DVC_CONV_MATH", "tf32x3"), choices=["fp32", "tf32x3"])
+    ap.add_argument("--tc-kc", type=int, default=int(os.environ.get("DVC_TC_KC", "1")),
+                    help="k-blocks summed in TMEM before promotion to fp32 registers (1 = parity mode)")
     ap.add_argument("--cpu-sample", type=int, default=2, help="frames timed for cpu_baseline (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
@@ -181,7 +184,8 @@ def main():
     for net, key in ((dvc.NET_VGG, "vgg"), (dvc.NET_WARP, "warp"), (dvc.NET_COLOR, "color")):
         ctx.set_weights(net, make_state_dict(key, seed=0))
     corr_mode = {"fp32": dvc.MATH_FP32, "tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3}[args.corr_math]
-    ctx.set_math(corr=corr_mode)
+    ctx.set_math(conv=dvc.MATH_TF32X3 if args.conv_math == "tf32x3" else dvc.MATH_FP32, corr=corr_mode)
+    ctx.debug_flag("tc_kc", args.tc_kc)
 
     K, Wm = args.steps, args.warmup
     # every rank owns its own contiguous segment of synthetic frames (distinct content per rank and per step)
@@ -257,7 +261,10 @@ def main():
         "config": {
             "workload": "480x854 frame padded to 480x864 + 1 exemplar, full forward path (FrameColor.py:41-67), T=1e-10, "
                         "batch 1 with the frame recurrence of test.py:96; one contiguous K-frame segment per GPU",
-            "N_positions": N_POS, "conv_math": "fp32 CUDA-core (two-level accumulation)", "corr_math": args.corr_math,
+            "N_positions": N_POS,
+            "conv_math": (f"tcgen05 3xTF32 operand split, TMEM chunk = {args.tc_kc} k-block(s) promoted to fp32 registers"
+                          if args.conv_math == "tf32x3" else "fp32 CUDA-core (two-level accumulation)"),
+            "corr_math": args.corr_math,
             "weights": "seeded random (dvc/synth.py), no checkpoint available",
             "l2": "distinct frame per step; per-frame activation working set (>2 GB) exceeds the 126 MB L2",
             "exemplar_prepare_and_broadcast_ms": exemplar_ms,

@@ -28,13 +28,14 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int A_BYTES = BM * 128;
-constexpr int NTHREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int NTHREADS = 384;  // warpgroup 0: warp 0 TMA, warp 1 MMA (2, 3 idle); warpgroups 1, 2: epilogue
 
 template <int BN>
 struct Cfg {
   static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int NBUF = 512 / BN;  // TMEM accumulators (2 / 4 / 8): deeper ring hides the flush round trip
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2 * BN * 4;
 };
 
@@ -57,9 +58,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
-  uint64_t* tfull = bars + 2 * C::STAGES;
-  uint64_t* tempty = bars + 2 * C::STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* tfull = bars + 2 * C::STAGES;                  // [NBUF]
+  uint64_t* tempty = bars + 2 * C::STAGES + C::NBUF;       // [NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 2 * C::NBUF);
   float* s_stat = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);  // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc::tma_prefetch_desc(&tmWh);
     tc::tma_prefetch_desc(&tmWl);
     for (int i = 0; i < C::STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
-    for (int i = 0; i < 2; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 8);
+    for (int i = 0; i < C::NBUF; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 8);
     tc::fence_barrier_init();
   }
   if (warp == 1) {
@@ -92,6 +93,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // register budget: the control warpgroup (warps 0-3) gives its registers to the two epilogue warpgroups
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
@@ -121,11 +125,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t chunk_id = 0;  // global chunk counter: TMEM buffer = chunk_id & 1
+      uint32_t chunk_id = 0;  // global chunk counter: TMEM buffer = chunk_id % NBUF
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         for (int ch = 0; ch < nchunks; ++ch, ++chunk_id) {
-          const int buf = chunk_id & 1;
-          const uint32_t acc_phase = (chunk_id >> 1) & 1;
+          const int buf = chunk_id % C::NBUF;
+          const uint32_t acc_phase = (chunk_id / C::NBUF) & 1;
           tc::mbar_wait(&tempty[buf], acc_phase ^ 1);
           tc::tc_fence_after();
           const uint32_t d = tmem_base + buf * BN;
@@ -150,11 +154,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         }
       }
     }
+  }
   } else {
     // ================= epilogue: 8 warps; thread = one output pixel x BN/2 channels =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;       // which half of the tile's channels
-    const int etid = threadIdx.x - 64;      // 0..255
+    const int half = (warp - 4) >> 2;       // which half of the tile's channels
+    const int etid = threadIdx.x - 128;     // 0..255
     const int img = p.Hp * p.Wp;
     uint32_t chunk_id = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -184,22 +190,38 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       // ---- chunk sums: TMEM -> registers, fp32 round-to-nearest accumulation ----
       float tot[CPT];
       for (int ch = 0; ch < nchunks; ++ch, ++chunk_id) {
-        const int buf = chunk_id & 1;
-        const uint32_t acc_phase = (chunk_id >> 1) & 1;
+        const int buf = chunk_id % C::NBUF;
+        const uint32_t acc_phase = (chunk_id / C::NBUF) & 1;
         tc::mbar_wait(&tfull[buf], acc_phase);
         tc::tc_fence_after();
+        const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * CPT;
+        if constexpr (CPT >= 64) {
 #pragma unroll
-        for (int c = 0; c < CPT / 32; ++c) {
+          for (int c = 0; c < CPT / 64; ++c) {  // two loads in flight per wait
+            uint32_t r0[32], r1[32];
+            __syncwarp();
+            tc::tmem_ld_32x32(tsrc + c * 64, r0);
+            tc::tmem_ld_32x32(tsrc + c * 64 + 32, r1);
+            tc::tmem_ld_wait();
+            if (ch == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) tot[c * 64 + j] = __uint_as_float(r0[j]), tot[c * 64 + 32 + j] = __uint_as_float(r1[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) tot[c * 64 + j] += __uint_as_float(r0[j]), tot[c * 64 + 32 + j] += __uint_as_float(r1[j]);
+            }
+          }
+        } else {
           uint32_t r[32];
           __syncwarp();
-          tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * CPT + c * 32, r);
+          tc::tmem_ld_32x32(tsrc, r);
           tc::tmem_ld_wait();
           if (ch == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) tot[c * 32 + j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) tot[j] = __uint_as_float(r[j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) tot[c * 32 + j] += __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) tot[j] += __uint_as_float(r[j]);
           }
         }
         tc::tc_fence_before();
