@@ -21,6 +21,7 @@ struct ConvTcParams {
   int act;
   float slope;
   double* stats;  // optional [B][Cout][2]
+  int transposed;  // allow the channel-major kernel for 128-output-channel layers
   int kc;         // k-blocks (32 input channels each) summed in TMEM before promotion to fp32 registers
 };
 

@@ -62,12 +62,17 @@ struct dvc_ctx {
   std::unordered_map<std::string, std::vector<float>> host_bias[3];  // bias seen before its weight
   int num_sms = 148;
   int conv_math = DVC_MATH_FP32, corr_math = DVC_MATH_FP32;
+  int tc_transposed = 1;  // channel-major kernel for 128-output-channel layers (see conv_tc.cu)
   int tc_kc = 1;          // tensor-core convolutions: k-blocks per TMEM chunk (see conv_tc.cu)
   bool two_level = true;  // fp32 convolutions: per-tap two-level accumulation (see conv_simt.cu)
   std::map<std::string, Buf> bufs;
   // InstanceNorm statistics arena (doubles), bump-allocated per forward call
   double* stats = nullptr;
-  size_t stats_cap = 0, stats_used = 0;
+  size_t stats_cap = 0, stats_used = 0, stats_lo = 0, stats_hi = 0;
+  // clip driver: frame t+1's VGG/WarpNet/correlation overlaps frame t's ColorVidNet on two internal streams
+  cudaStream_t sA = nullptr, sC = nullptr;
+  cudaEvent_t evA[4] = {nullptr, nullptr, nullptr, nullptr}, evC[4] = {nullptr, nullptr, nullptr, nullptr}, evFork = nullptr,
+              evJoinA = nullptr, evJoinC = nullptr;
   // exemplar cache
   float* ex_phi = nullptr;  // [N][256]
   float* ex_V = nullptr;    // [N][4]
@@ -144,19 +149,23 @@ static int get_raw(dvc_ctx* c, const std::string& name, size_t bytes, void** out
   return get_buf(c, name, bytes, out, sig, false, s);
 }
 
-static int stats_begin(dvc_ctx* c, cudaStream_t s) {
-  const size_t need = 1 << 20;  // doubles (8 MB): far above the ~60 K used per forward at B <= 8
+// Two halves: [0] the frame-independent phase (VGG / WarpNet / correlation), [1] ColorVidNet -- the clip driver
+// runs them concurrently on two streams, so they must not share statistics slots.
+static int stats_begin(dvc_ctx* c, cudaStream_t s, int arena = 0) {
+  const size_t need = 1 << 21;  // doubles (16 MB): far above the ~60 K used per forward at B <= 8
   if (c->stats_cap < need) {
     if (c->stats) CUDA_TRY(c, cudaFree(c->stats));
     CUDA_TRY(c, cudaMalloc((void**)&c->stats, need * sizeof(double)));
     c->stats_cap = need;
   }
-  c->stats_used = 0;
+  c->stats_lo = arena ? need / 2 : 0;
+  c->stats_hi = arena ? need : need / 2;
+  c->stats_used = c->stats_lo;
   return DVC_OK;
 }
 static int stats_alloc(dvc_ctx* c, int B, int C, double** out, cudaStream_t s) {
   const size_t n = (size_t)B * C * 2;
-  if (c->stats_used + n > c->stats_cap) return fail(c, DVC_ERR_STATE, "statistics arena exhausted (batch too large)");
+  if (c->stats_used + n > c->stats_hi) return fail(c, DVC_ERR_STATE, "statistics arena exhausted (batch too large)");
   *out = c->stats + c->stats_used;
   c->stats_used += n;
   CUDA_TRY(c, cudaMemsetAsync(*out, 0, n * sizeof(double), s));
@@ -333,7 +342,7 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     t.taps = taps, t.dil = o.dil, t.stride = o.stride, t.Cout = w->cout, t.CoutPad = w->cout_pad_tc, t.bias = w->b;
     t.y = y.d, t.y_lo = y.lo, t.yHp = p.yHp, t.yWp = p.yWp, t.yP = p.yP, t.yC = p.yC, t.yCoff = p.yCoff;
     t.add = p.add, t.add_lo = o.add ? o.add->lo : nullptr, t.aHp = p.aHp, t.aWp = p.aWp, t.aP = p.aP, t.aC = p.aC;
-    t.act = o.act, t.slope = o.slope, t.stats = o.stats, t.kc = c->tc_kc;
+    t.act = o.act, t.slope = o.slope, t.stats = o.stats, t.kc = c->tc_kc, t.transposed = c->tc_transposed;
     std::string err;
     if (launch_conv_tc(t, x.d, x.lo, w->wt_hi, w->wt_lo, c->num_sms, s, &err) != 0) return fail(c, DVC_ERR_CUDA, "conv_tc: " + err);
     return check_launch(c, "conv_tc");
@@ -701,6 +710,15 @@ extern "C" int dvc_destroy(dvc_ctx* c) {
       if (kv.second) cudaFree(kv.second);
   }
   if (c->stats) cudaFree(c->stats);
+  if (c->sA) cudaStreamDestroy(c->sA);
+  if (c->sC) cudaStreamDestroy(c->sC);
+  for (int i = 0; i < 4; ++i) {
+    if (c->evA[i]) cudaEventDestroy(c->evA[i]);
+    if (c->evC[i]) cudaEventDestroy(c->evC[i]);
+  }
+  if (c->evFork) cudaEventDestroy(c->evFork);
+  if (c->evJoinA) cudaEventDestroy(c->evJoinA);
+  if (c->evJoinC) cudaEventDestroy(c->evJoinC);
   if (c->ex_phi) cudaFree(c->ex_phi);
   if (c->ex_V) cudaFree(c->ex_V);
   for (auto& ev : c->corr_events) cudaEventDestroy(ev.first), cudaEventDestroy(ev.second);
@@ -724,6 +742,7 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!c || !name) return DVC_ERR_ARG;
   if (!strcmp(name, "two_level")) { c->two_level = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_kc")) { c->tc_kc = value < 1 ? 1 : value; return DVC_OK; }
+  if (!strcmp(name, "tc_transposed")) { c->tc_transposed = value; return DVC_OK; }  // 0 off, 1 auto, 2 force
   return fail(c, DVC_ERR_ARG, std::string("unknown debug flag ") + name);
 }
 
@@ -951,66 +970,125 @@ extern "C" int dvc_set_exemplar(dvc_ctx* c, const float* IB_lab, int H, int W, v
   return DVC_OK;
 }
 
-extern "C" int dvc_colorize_frames(dvc_ctx* c, const float* IA_l, const float* IA_last_lab, int B, int H, int W,
-                                   float temperature, float* out_ab, float* out_warp_lab, float* out_sim, void* stream) {
-  if (!c || !IA_l || !IA_last_lab || !out_ab || B < 1) return c ? fail(c, DVC_ERR_ARG, "colorize_frames: bad argument") : DVC_ERR_ARG;
-  if (!c->ex_valid) return fail(c, DVC_ERR_STATE, "colorize_frames: call dvc_set_exemplar first");
-  if (H != c->ex_H || W != c->ex_W) return fail(c, DVC_ERR_SHAPE, "colorize_frames: frame size differs from the exemplar's");
-  if (!(temperature > 0.f)) return fail(c, DVC_ERR_ARG, "colorize_frames: temperature must be > 0");
-  cudaStream_t s = (cudaStream_t)stream;
-  CUDA_TRY(c, cudaSetDevice(c->device));
-  DVC_TRY(stats_begin(c, s));
+// Phase A (independent of the previous frame): VGG19 -> feature_normalize -> WarpNet A side -> correlation.
+static int frames_phaseA(dvc_ctx* c, const std::string& tag, const float* IA_l, int B, int H, int W, float temperature,
+                         float* yrows, float* simrows, cudaStream_t s) {
+  DVC_TRY(stats_begin(c, s, 0));
   const int h = H / 4, w = W / 4, N = h * w;
   Act x0;
-  DVC_TRY(get_act(c, "fr.x0", B, H, W, 8, 1, &x0, s));
+  DVC_TRY(get_act(c, tag + ".x0", B, H, W, 8, 1, &x0, s));
   launch_nchw_to_act(IA_l, 1, x0.d, nullptr, B, H, W, 8, 1, PAD_ZERO, 2, s);  // FrameColor.py:6 + util.py:347-352
   DVC_TRY(check_launch(c, "nchw_to_act"));
   VggMaps maps;
-  DVC_TRY(vgg_trunk(c, "fr", x0, "r52", &maps, s));
+  DVC_TRY(vgg_trunk(c, tag, x0, "r52", &maps, s));
   Act n[4];
-  DVC_TRY(normalised_features(c, "fr", maps, n, s));
-  void *theta, *yrows, *simrows;
-  DVC_TRY(get_raw(c, "fr.theta", (size_t)B * N * 256 * 4, &theta, s));
-  DVC_TRY(get_raw(c, "fr.yrows", (size_t)B * N * 16, &yrows, s));
-  DVC_TRY(get_raw(c, "fr.simrows", (size_t)B * N * 4, &simrows, s));
-  DVC_TRY(warp_side(c, "fr", n, "theta", (float*)theta, h, w, s));
+  DVC_TRY(normalised_features(c, tag, maps, n, s));
+  void* theta;
+  DVC_TRY(get_raw(c, tag + ".theta", (size_t)B * N * 256 * 4, &theta, s));
+  DVC_TRY(warp_side(c, tag, n, "theta", (float*)theta, h, w, s));
   CorrParams p{};
   p.theta = (float*)theta, p.phi = c->ex_phi, p.V = c->ex_V, p.B = B, p.Bphi = 1, p.NA = N, p.NB = N, p.C = 256;
-  p.temperature = temperature, p.y = (float*)yrows, p.sim = (float*)simrows, p.argmax = nullptr;
-  DVC_TRY(run_corr(c, p, s));
+  p.temperature = temperature, p.y = yrows, p.sim = simrows, p.argmax = nullptr;
+  return run_corr(c, p, s);
+}
+
+// Phase C (the recurrent part): ColorVidNet on [L, warped ab, similarity, previous Lab] (FrameColor.py:63-65).
+static int frames_phaseC(dvc_ctx* c, const std::string& tag, const float* IA_l, const float* yrows, const float* simrows,
+                         const float* IA_last_lab, int B, int H, int W, float* out_ab, cudaStream_t s) {
+  DVC_TRY(stats_begin(c, s, 1));
+  Act in0;
+  DVC_TRY(get_act(c, tag + ".in0", B, H, W, 8, 1, &in0, s));
+  launch_build_color_input(IA_l, yrows, simrows, IA_last_lab, in0.d, B, H, W, 1, s);
+  DVC_TRY(check_launch(c, "build_color_input"));
+  return colorvid(c, tag, in0, out_ab, s);
+}
+
+static int check_frame_args(dvc_ctx* c, int H, int W, float temperature) {
+  if (!c->ex_valid) return fail(c, DVC_ERR_STATE, "colorize: call dvc_set_exemplar first");
+  if (H != c->ex_H || W != c->ex_W) return fail(c, DVC_ERR_SHAPE, "colorize: frame size differs from the exemplar's");
+  if (!(temperature > 0.f)) return fail(c, DVC_ERR_ARG, "colorize: temperature must be > 0");
+  return DVC_OK;
+}
+
+extern "C" int dvc_colorize_frames(dvc_ctx* c, const float* IA_l, const float* IA_last_lab, int B, int H, int W,
+                                   float temperature, float* out_ab, float* out_warp_lab, float* out_sim, void* stream) {
+  if (!c || !IA_l || !IA_last_lab || !out_ab || B < 1) return c ? fail(c, DVC_ERR_ARG, "colorize_frames: bad argument") : DVC_ERR_ARG;
+  DVC_TRY(check_frame_args(c, H, W, temperature));
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const int h = H / 4, w = W / 4, N = h * w;
+  void *yrows, *simrows;
+  DVC_TRY(get_raw(c, "fr.yrows", (size_t)B * N * 16, &yrows, s));
+  DVC_TRY(get_raw(c, "fr.simrows", (size_t)B * N * 4, &simrows, s));
+  DVC_TRY(frames_phaseA(c, "fr", IA_l, B, H, W, temperature, (float*)yrows, (float*)simrows, s));
   if (out_warp_lab || out_sim) {
     launch_rows_to_nchw_up4((float*)yrows, (float*)simrows, out_warp_lab, out_sim, B, h, w, s);
     DVC_TRY(check_launch(c, "rows_to_nchw_up4"));
   }
-  Act in0;
-  DVC_TRY(get_act(c, "fr.in0", B, H, W, 8, 1, &in0, s));
-  launch_build_color_input(IA_l, (float*)yrows, (float*)simrows, IA_last_lab, in0.d, B, H, W, 1, s);
-  DVC_TRY(check_launch(c, "build_color_input"));
-  return colorvid(c, "fr", in0, out_ab, s);
+  return frames_phaseC(c, "fr", IA_l, (float*)yrows, (float*)simrows, IA_last_lab, B, H, W, out_ab, s);
 }
 
-extern "C" int dvc_colorize_clip(dvc_ctx* c, const float* host_L, int F, int H, int W, float temperature,
-                                 const float* first_last, float* host_ab, void* stream) {
-  if (!c || !host_L || !host_ab || F < 1) return c ? fail(c, DVC_ERR_ARG, "colorize_clip: bad argument") : DVC_ERR_ARG;
+static int clip_streams(dvc_ctx* c) {
+  if (c->sA) return DVC_OK;
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->sA, cudaStreamNonBlocking));
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->sC, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i) {
+    CUDA_TRY(c, cudaEventCreateWithFlags(&c->evA[i], cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&c->evC[i], cudaEventDisableTiming));
+  }
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->evJoinA, cudaEventDisableTiming));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->evJoinC, cudaEventDisableTiming));
+  return DVC_OK;
+}
+
+// test.py:68-96 for one contiguous segment.  Frame t+1's frame-independent phase (VGG / WarpNet / correlation)
+// runs on stream A while frame t's ColorVidNet -- which needs frame t-1's prediction -- runs on stream C; the
+// low-resolution layers of either leave SMs idle that the other fills.  L / ab may be host (pinned) or device.
+extern "C" int dvc_colorize_clip(dvc_ctx* c, const float* L_in, int F, int H, int W, float temperature,
+                                 const float* first_last, float* ab_out, void* stream) {
+  if (!c || !L_in || !ab_out || F < 1) return c ? fail(c, DVC_ERR_ARG, "colorize_clip: bad argument") : DVC_ERR_ARG;
+  DVC_TRY(check_frame_args(c, H, W, temperature));
   cudaStream_t s = (cudaStream_t)stream;
   CUDA_TRY(c, cudaSetDevice(c->device));
+  DVC_TRY(clip_streams(c));
   const size_t hw = (size_t)H * W;
-  void *dL, *dlast, *dab;
-  DVC_TRY(get_raw(c, "clip.L", 2 * hw * 4, &dL, s));  // double buffer: frame t+1 uploads while t computes
+  const int N = (H / 4) * (W / 4);
+  void *dL, *dlast, *dab, *yrows, *simrows;
+  DVC_TRY(get_raw(c, "clip.L", 2 * hw * 4, &dL, s));
   DVC_TRY(get_raw(c, "clip.last", 3 * hw * 4, &dlast, s));
   DVC_TRY(get_raw(c, "clip.ab", 2 * hw * 4, &dab, s));
+  DVC_TRY(get_raw(c, "clip.yrows", (size_t)2 * N * 16, &yrows, s));
+  DVC_TRY(get_raw(c, "clip.simrows", (size_t)2 * N * 4, &simrows, s));
   if (first_last)
     CUDA_TRY(c, cudaMemcpyAsync(dlast, first_last, 3 * hw * 4, cudaMemcpyDefault, s));
   else
     CUDA_TRY(c, cudaMemsetAsync(dlast, 0, 3 * hw * 4, s));  // test.py:80
+  CUDA_TRY(c, cudaEventRecord(c->evFork, s));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evFork, 0));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evFork, 0));
   for (int t = 0; t < F; ++t) {
-    float* Lt = (float*)dL + (t & 1) * hw;
-    CUDA_TRY(c, cudaMemcpyAsync(Lt, host_L + (size_t)t * hw, hw * 4, cudaMemcpyDefault, s));
-    DVC_TRY(dvc_colorize_frames(c, Lt, (float*)dlast, 1, H, W, temperature, (float*)dab, nullptr, nullptr, stream));
-    launch_make_last(Lt, (float*)dab, (float*)dlast, 1, H, W, s);  // test.py:96
+    const int slot = t & 1;
+    float* Lt = (float*)dL + slot * hw;
+    float* yr = (float*)yrows + (size_t)slot * N * 4;
+    float* sr = (float*)simrows + (size_t)slot * N;
+    // ---- stream A: upload + frame-independent phase; slot reuse waits for frame t-2's ColorVidNet ----
+    if (t >= 2) CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evC[(t - 2) & 3], 0));
+    CUDA_TRY(c, cudaMemcpyAsync(Lt, L_in + (size_t)t * hw, hw * 4, cudaMemcpyDefault, c->sA));
+    DVC_TRY(frames_phaseA(c, "clipA", Lt, 1, H, W, temperature, yr, sr, c->sA));
+    CUDA_TRY(c, cudaEventRecord(c->evA[t & 3], c->sA));
+    // ---- stream C: the recurrent phase ----
+    CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evA[t & 3], 0));
+    DVC_TRY(frames_phaseC(c, "clipC", Lt, yr, sr, (float*)dlast, 1, H, W, (float*)dab, c->sC));
+    launch_make_last(Lt, (float*)dab, (float*)dlast, 1, H, W, c->sC);  // test.py:96
     DVC_TRY(check_launch(c, "make_last"));
-    CUDA_TRY(c, cudaMemcpyAsync(host_ab + (size_t)t * 2 * hw, dab, 2 * hw * 4, cudaMemcpyDefault, s));
+    CUDA_TRY(c, cudaMemcpyAsync(ab_out + (size_t)t * 2 * hw, dab, 2 * hw * 4, cudaMemcpyDefault, c->sC));
+    CUDA_TRY(c, cudaEventRecord(c->evC[t & 3], c->sC));
   }
+  CUDA_TRY(c, cudaEventRecord(c->evJoinA, c->sA));
+  CUDA_TRY(c, cudaEventRecord(c->evJoinC, c->sC));
+  CUDA_TRY(c, cudaStreamWaitEvent(s, c->evJoinA, 0));
+  CUDA_TRY(c, cudaStreamWaitEvent(s, c->evJoinC, 0));
   CUDA_TRY(c, cudaStreamSynchronize(s));
   return DVC_OK;
 }

@@ -229,16 +229,23 @@ class Context:
         self._check(rc, "dvc_colorize_frames")
         return (ab, warp, sim) if want_warp else ab
 
-    def colorize_clip(self, host_L, temperature=1e-10, first_last_lab=None, out=None):
-        """host_L: pinned CPU [F,1,H,W] -> pinned CPU [F,2,H,W]; recurrence of test.py:76-96 kept on the device."""
-        if host_L.is_cuda or host_L.dtype != torch.float32:
-            raise DvcError("colorize_clip takes a float32 CPU tensor (pinned for full copy overlap)")
-        host_L = host_L.contiguous()
-        F_, c1, H, W = host_L.shape
+    def colorize_clip(self, L, temperature=1e-10, first_last_lab=None, out=None):
+        """L [F,1,H,W] -> ab [F,2,H,W] with the recurrence of test.py:76-96 kept on the device.
+
+        L may be a pinned CPU tensor (one host->device copy of L and one device->host copy of ab per frame inside
+        the call) or a CUDA tensor (frames already resident in HBM); `out` lives where L lives."""
+        if L.dtype != torch.float32 or L.dim() != 4 or L.shape[1] != 1:
+            raise DvcError("colorize_clip takes a float32 [F,1,H,W] tensor")
+        L = L.contiguous()
+        F_, _, H, W = L.shape
         if out is None:
-            out = torch.empty(F_, 2, H, W, dtype=torch.float32).pin_memory()
+            out = torch.empty(F_, 2, H, W, dtype=torch.float32, device=L.device)
+            if not L.is_cuda:
+                out = out.pin_memory()
+        if out.is_cuda != L.is_cuda or not out.is_contiguous() or tuple(out.shape) != (F_, 2, H, W):
+            raise DvcError("colorize_clip: `out` must be a contiguous [F,2,H,W] tensor on the same side as L")
         fl = first_last_lab.contiguous() if first_last_lab is not None else None
-        rc = self.lib.dvc_colorize_clip(self.h, _ptr(host_L), F_, H, W, float(temperature), _ptr(fl), _ptr(out),
+        rc = self.lib.dvc_colorize_clip(self.h, _ptr(L), F_, H, W, float(temperature), _ptr(fl), _ptr(out),
                                         _stream(self.device))
         self._check(rc, "dvc_colorize_clip")
         return out
