@@ -570,7 +570,7 @@ int conv_tc_pick_bn(int cout) { return cout >= 256 ? 256 : (cout > 64 ? 128 : 64
 static int pick_bn_for_launch(const ConvTcParams& p, int num_sms) {
   const int m_tiles = (p.Mtot + BM - 1) / BM;
   int bn = conv_tc_pick_bn(p.Cout);
-  while (bn > 64 && m_tiles * (p.CoutPad / bn) < (num_sms * 3) / 4) bn >>= 1;
+  while (bn > 64 && m_tiles * (p.CoutPad / bn) < num_sms / 2) bn >>= 1;
   return bn;
 }
 

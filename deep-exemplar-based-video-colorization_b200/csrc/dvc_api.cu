@@ -62,7 +62,8 @@ struct dvc_ctx {
   std::unordered_map<std::string, std::vector<float>> host_bias[3];  // bias seen before its weight
   int num_sms = 148;
   int conv_math = DVC_MATH_FP32, corr_math = DVC_MATH_FP32;
-  int tc_transposed = 1;  // channel-major kernel for 128-output-channel layers (see conv_tc.cu)
+  int tc_transposed = 0;  // channel-major kernel for 128-output-channel layers: measured slower than the pixel-major
+                          // tile so far (profiles/), kept behind this flag (1 = auto, 2 = force) and under test
   int tc_kc = 1;          // tensor-core convolutions: k-blocks per TMEM chunk (see conv_tc.cu)
   bool two_level = true;  // fp32 convolutions: per-tap two-level accumulation (see conv_simt.cu)
   std::map<std::string, Buf> bufs;
