@@ -41,11 +41,11 @@ def conv_math(request, ctx):
 
     if request.param.startswith("tf32x3"):
         ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
-        ctx.debug_flag("tc_transposed", 2 if request.param.endswith("chmajor") else 1)
+        ctx.debug_flag("tc_transposed", 2 if request.param.endswith("chmajor") else 0)
     else:
         ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
     yield request.param
-    ctx.debug_flag("tc_transposed", 1)
+    ctx.debug_flag("tc_transposed", 0)
     ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
 
 
@@ -231,8 +231,10 @@ def test_fused_batch_equals_single(ctx, conv_math):
     ab, warp, sim = ctx.colorize_frames(L, last, want_warp=True)
     for b in range(3):
         ab1, warp1, sim1 = ctx.colorize_frames(L[b:b + 1], last[b:b + 1], want_warp=True)
-        assert torch.equal(warp[b:b + 1], warp1) and torch.equal(sim[b:b + 1], sim1)
-        assert (ab[b:b + 1] - ab1).abs().max() < 5e-3  # statistics reduce in a different order per batch size
+        # the pixel tiles of a batched call straddle image boundaries differently, so InstanceNorm statistics are
+        # summed in a different order: same argmax, scores / ab equal up to that fp32 noise
+        assert torch.equal(warp[b:b + 1], warp1) and (sim[b:b + 1] - sim1).abs().max() < 2e-6
+        assert (ab[b:b + 1] - ab1).abs().max() < 5e-3
 
 
 def test_exemplar_export_import_roundtrip(ctx):
