@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
 
     def stop(self):
         self._halt.set()
@@ -234,8 +234,6 @@ def main():
     dev_out = torch.empty(K, 2, H, W, device="cuda")
     ctx.colorize_clip(dev_L[:Wm].contiguous(), TEMPERATURE)  # W warm-up frames
     barrier()
-    ctx.profile_corr(True)
-    ctx.corr_mean_ms(True)
     ctx.launch_count(True)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -247,8 +245,6 @@ def main():
     barrier()
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count(True)
-    corr_ms = ctx.corr_mean_ms(True)
-    ctx.profile_corr(False)
     clocks = sampler.stop() if sampler else None
 
     # ---------------- leg 2: end to end through the clip API with host buffers ----------------
@@ -263,6 +259,32 @@ def main():
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
 
+    # ---------------- leg 3: per-kernel durations, one stream, no overlap (for the roofline objects) ----------------
+    # The clip API overlaps two streams, so a kernel's event-bracketed time there includes its neighbours; the
+    # roofline needs the kernel's own duration: same frames through dvc_colorize_frames on one stream, CUDA events
+    # around every correlation / tensor-core convolution launch (on the launching stream), live in this run.
+    KP = min(K, 5)
+    last = torch.zeros(1, 3, H, W, device="cuda")
+    ctx.colorize_frames(dev_L[0:1], last, TEMPERATURE)
+    ctx.profile_corr(True)
+    ctx.profile_conv(True)
+    ctx.corr_mean_ms(True)
+    ctx.conv_profile(0, reset=True)
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for t in range(Wm, Wm + KP):
+        ab1 = ctx.colorize_frames(dev_L[t:t + 1], last, TEMPERATURE)
+        last = torch.cat((dev_L[t:t + 1], ab1), 1)
+    e5.record()
+    torch.cuda.synchronize()
+    ms_serial = e4.elapsed_time(e5) / KP
+    corr_ms = ctx.corr_mean_ms(True)
+    conv_all = ctx.conv_profile(0)
+    conv_by = {v: ctx.conv_profile(v) for v in (256, 128, 64, 1)}
+    ctx.conv_profile(0, reset=True)
+    ctx.profile_corr(False)
+    ctx.profile_conv(False)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -270,6 +292,10 @@ def main():
 
     peak, peak_src = measured_peak()
     achieved = CORR_FLOP / (corr_ms * 1e-3) / 1e12 if corr_ms > 0 else 0.0
+    n256, ms256, fl256 = conv_by[256]
+    conv_ach = fl256 / (ms256 * 1e-3) / 1e12 if ms256 > 0 else 0.0
+    conv_detail = {str(v): {"launches_per_frame": n / KP, "ms_per_frame": ms / KP,
+                            "tflops": (fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0)} for v, (n, ms, fl) in conv_by.items() if n}
     line = {
         "metric": METRIC, "value": world * K / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -289,10 +315,23 @@ def main():
                 "d2h_bytes_per_step": 2 * H * W * 4},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": f"corr_softmax_warp ({args.corr_math})", "bound": "tensor", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
-                     "peak_source": peak_src, "launch_ms": corr_ms,
-                     "note": "algorithmic 2*N*N*(256+3) FLOP per launch (3x MMA passes of the operand split not counted)"},
+        # dominant kernel by device time (profiles/launches_r1.md: conv_tc_kernel<256> ~ 50 % of a frame)
+        "roofline": {"kernel": "conv_tc_kernel<256> (3xTF32 flat shifted GEMM, all launches of a frame)", "bound": "tensor",
+                     "achieved": conv_ach, "peak": peak, "unit": "TFLOP/s", "frac": conv_ach / peak if peak else None,
+                     "traffic": None, "peak_source": peak_src,
+                     "launches_per_frame": n256 / KP, "ms_per_frame": ms256 / KP,
+                     "note": "sum of algorithmic FLOPs (2 x output pixels x 9 x Cin x Cout) / sum of CUDA-event launch times, "
+                             "single-stream pass of %d frames inside this run; the 3 MMA passes of the operand split are not "
+                             "counted, so frac is bounded by 1/6 of the dense-bf16 peak" % KP,
+                     "other_variants": conv_detail},
+        # the north-star kernel (BASELINE metric: correlation tensor-pipe fraction)
+        "roofline_corr": {"kernel": f"corr_tc_kernel ({args.corr_math}) incl. operand split + merge", "bound": "tensor",
+                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                          "traffic": None, "peak_source": peak_src, "launch_ms": corr_ms,
+                          "note": "algorithmic 2*N*N*(256+3) FLOP per launch; ceiling 1/6 (tf32x3) or 1/3 (bf16x3) of the bf16 peak"},
+        "serial_ms_per_frame": ms_serial,
+        "conv_tc_all": {"launches_per_frame": conv_all[0] / KP, "ms_per_frame": conv_all[1] / KP,
+                        "tflops": conv_all[2] / (conv_all[1] * 1e-3) / 1e12 if conv_all[1] > 0 else 0.0},
     }
     if args.cpu_sample > 0:
         tb = time.perf_counter()

@@ -575,7 +575,7 @@ static int pick_bn_for_launch(const ConvTcParams& p, int num_sms) {
 }
 
 int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
-                   int num_sms, cudaStream_t s, std::string* err) {
+                   int num_sms, cudaStream_t s, std::string* err, int* variant) {
   auto fail = [&](const char* m) {
     if (err) *err = m;
     return -1;
@@ -598,9 +598,11 @@ int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, 
     const int total = (p.Mtot + T_PX - 1) / T_PX;
     conv_tc_t_kernel<<<total < num_sms ? total : num_sms, NTHREADS, T_SMEM, s>>>(mXh, mXl, mWh, mWl, p);
     launch_counter_add(1);
+    if (variant) *variant = 1;
     return 0;
   }
   const int BN = pick_bn_for_launch(p, num_sms);
+  if (variant) *variant = BN;
   CUtensorMap mXh, mXl, mWh, mWl;
   if (encode_tmap_2d(&mXh, x_hi, (uint64_t)p.Mtot, p.Cin, BM, 32, 4) || encode_tmap_2d(&mXl, x_lo, (uint64_t)p.Mtot, p.Cin, BM, 32, 4) ||
       encode_tmap_2d(&mWh, w_hi, (uint64_t)p.taps * p.CoutPad, p.Cin, BN, 32, 4) ||

@@ -27,7 +27,8 @@ struct ConvTcParams {
 
 int conv_tc_pick_bn(int cout);  // channel tile (64 / 128 / 256) used for `cout` output channels
 // x_hi/x_lo: activation planes [Mtot][Cin]; w_hi/w_lo: weight planes [taps][CoutPad][Cin] (tf32-rounded fp32 words)
+// *variant receives the kernel chosen: 64 / 128 / 256 = pixel-major channel tile, 1 = channel-major kernel
 int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
-                   int num_sms, cudaStream_t s, std::string* err);
+                   int num_sms, cudaStream_t s, std::string* err, int* variant = nullptr);
 
 }  // namespace dvc

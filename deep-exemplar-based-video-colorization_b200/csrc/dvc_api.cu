@@ -85,6 +85,10 @@ struct dvc_ctx {
   // correlation profiling
   bool prof_corr = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> corr_events;
+  // convolution profiling: per launch (start, stop, algorithmic FLOPs, kernel variant)
+  bool prof_conv = false;
+  struct ConvEv { cudaEvent_t e0, e1; double flops; int variant; };
+  std::vector<ConvEv> conv_events;
 };
 
 static std::string g_create_err;
@@ -345,7 +349,19 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     t.add = p.add, t.add_lo = o.add ? o.add->lo : nullptr, t.aHp = p.aHp, t.aWp = p.aWp, t.aP = p.aP, t.aC = p.aC;
     t.act = o.act, t.slope = o.slope, t.stats = o.stats, t.kc = c->tc_kc, t.transposed = c->tc_transposed;
     std::string err;
-    if (launch_conv_tc(t, x.d, x.lo, w->wt_hi, w->wt_lo, c->num_sms, s, &err) != 0) return fail(c, DVC_ERR_CUDA, "conv_tc: " + err);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->prof_conv) {
+      CUDA_TRY(c, cudaEventCreate(&e0));
+      CUDA_TRY(c, cudaEventCreate(&e1));
+      CUDA_TRY(c, cudaEventRecord(e0, s));
+    }
+    int variant = 0;
+    if (launch_conv_tc(t, x.d, x.lo, w->wt_hi, w->wt_lo, c->num_sms, s, &err, &variant) != 0) return fail(c, DVC_ERR_CUDA, "conv_tc: " + err);
+    if (c->prof_conv) {
+      CUDA_TRY(c, cudaEventRecord(e1, s));
+      // algorithmic FLOPs: 2 x output pixels x taps x Cin x Cout (padding channels and masked border pixels excluded)
+      c->conv_events.push_back({e0, e1, 2.0 * x.B * p.Ho * p.Wo * taps * (double)w->cin * w->cout, variant});
+    }
     return check_launch(c, "conv_tc");
   }
   if (o.add && o.add->lo) return fail(c, DVC_ERR_STATE, "conv: CUDA-core kernel cannot read a split addend");
@@ -723,6 +739,7 @@ extern "C" int dvc_destroy(dvc_ctx* c) {
   if (c->ex_phi) cudaFree(c->ex_phi);
   if (c->ex_V) cudaFree(c->ex_V);
   for (auto& ev : c->corr_events) cudaEventDestroy(ev.first), cudaEventDestroy(ev.second);
+  for (auto& ev : c->conv_events) cudaEventDestroy(ev.e0), cudaEventDestroy(ev.e1);
   delete c;
   return DVC_OK;
 }
@@ -769,6 +786,33 @@ extern "C" int dvc_profile_corr(dvc_ctx* c, int enable) {
   if (!c) return DVC_ERR_ARG;
   c->prof_corr = enable != 0;
   return DVC_OK;
+}
+
+extern "C" int dvc_profile_conv(dvc_ctx* c, int enable) {
+  if (!c) return DVC_ERR_ARG;
+  c->prof_conv = enable != 0;
+  return DVC_OK;
+}
+
+// Sum of CUDA-event durations (ms) and of algorithmic FLOPs over the recorded tensor-core convolution launches of
+// one kernel variant (64 / 128 / 256 = pixel-major channel tile, 1 = channel-major, 0 = all).  Returns launches.
+extern "C" int dvc_conv_profile(dvc_ctx* c, int variant, int reset, double* total_ms, double* total_flops) {
+  if (!c) return 0;
+  double ms = 0.0, fl = 0.0;
+  int n = 0;
+  for (auto& ev : c->conv_events) {
+    if (variant && ev.variant != variant) continue;
+    if (cudaEventSynchronize(ev.e1) != cudaSuccess) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ev.e0, ev.e1) == cudaSuccess) ms += t, fl += ev.flops, n++;
+  }
+  if (reset) {
+    for (auto& ev : c->conv_events) cudaEventDestroy(ev.e0), cudaEventDestroy(ev.e1);
+    c->conv_events.clear();
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  return n;
 }
 
 extern "C" double dvc_corr_mean_ms(dvc_ctx* c, int reset) {

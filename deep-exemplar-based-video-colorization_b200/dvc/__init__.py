@@ -21,7 +21,7 @@ EXPORTED = [
     "dvc_vgg19_forward", "dvc_warpnet_forward", "dvc_colorvidnet_forward", "dvc_corr_softmax_warp",
     "dvc_set_exemplar", "dvc_colorize_frames", "dvc_colorize_clip", "dvc_exemplar_pack_size",
     "dvc_exemplar_export", "dvc_exemplar_import", "dvc_launch_count", "dvc_profile_corr", "dvc_corr_mean_ms",
-    "dvc_debug_set_flag", "dvc_debug_get_buffer",
+    "dvc_debug_set_flag", "dvc_debug_get_buffer", "dvc_profile_conv", "dvc_conv_profile",
 ]
 
 _lib = None
@@ -72,6 +72,8 @@ def load_library():
         lib.dvc_profile_corr.argtypes = [c_void, c_int]
         lib.dvc_corr_mean_ms.argtypes = [c_void, c_int]
         lib.dvc_corr_mean_ms.restype = ctypes.c_double
+        lib.dvc_profile_conv.argtypes = [c_void, c_int]
+        lib.dvc_conv_profile.argtypes = [c_void, c_int, c_int, P(ctypes.c_double), P(ctypes.c_double)]
         lib.dvc_debug_set_flag.argtypes = [c_void, ctypes.c_char_p, c_int]
         lib.dvc_debug_get_buffer.argtypes = [c_void, ctypes.c_char_p, P(c_void), P(c_i64), P(c_int)]
         _lib = lib
@@ -293,6 +295,15 @@ class Context:
 
     def profile_corr(self, enable=True):
         self._check(self.lib.dvc_profile_corr(self.h, 1 if enable else 0), "dvc_profile_corr")
+
+    def profile_conv(self, enable=True):
+        self._check(self.lib.dvc_profile_conv(self.h, 1 if enable else 0), "dvc_profile_conv")
+
+    def conv_profile(self, variant=0, reset=False):
+        """(launches, total ms, total algorithmic FLOPs) of the recorded tensor-core conv launches of `variant`."""
+        ms, fl = ctypes.c_double(0), ctypes.c_double(0)
+        n = self.lib.dvc_conv_profile(self.h, variant, 1 if reset else 0, ctypes.byref(ms), ctypes.byref(fl))
+        return int(n), ms.value, fl.value
 
     def corr_mean_ms(self, reset=True):
         return float(self.lib.dvc_corr_mean_ms(self.h, 1 if reset else 0))

@@ -137,6 +137,11 @@ int64_t dvc_launch_count(dvc_ctx* ctx, int reset);
  * the last reset (0 if none).  Recording is enabled with dvc_profile_corr(ctx, 1). */
 int dvc_profile_corr(dvc_ctx* ctx, int enable);
 double dvc_corr_mean_ms(dvc_ctx* ctx, int reset);
+/* Same for the tensor-core convolution launches: dvc_conv_profile sums the CUDA-event durations (ms) and the
+ * algorithmic FLOPs of the recorded launches of one kernel variant (64 / 128 / 256 = pixel-major channel tile,
+ * 1 = channel-major kernel, 0 = all) and returns the number of launches. */
+int dvc_profile_conv(dvc_ctx* ctx, int enable);
+int dvc_conv_profile(dvc_ctx* ctx, int variant, int reset, double* total_ms, double* total_flops);
 
 /* Debug / test hooks (not part of the drop-in surface).
  *   dvc_debug_set_flag: "two_level" (default 1) selects per-tap two-level fp32 accumulation in the
