@@ -105,8 +105,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
         const int m0 = mt * BM, n0 = nt * BN;
         for (int tap = 0; tap < p.taps; ++tap) {
-          int off = 0;
-          if (p.taps == 9) off = ((tap / 3 - 1) * p.Wp + (tap % 3 - 1)) * p.dil;
+          const int off = p.tap_off[tap];
           for (int kb = 0; kb < kbs; ++kb) {
             tc::mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + stage * C::STAGE_BYTES;
@@ -176,7 +175,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         const int y = yp - p.P, x = xp - p.P;
         valid = (y >= 0 && y < p.H && x >= 0 && x < p.W);
         if (p.stride == 2 && ((y | x) & 1)) valid = false;
-        yo = y / p.stride, xo = x / p.stride;
+        yo = (y / p.stride) * p.oscale + p.oa, xo = (x / p.stride) * p.oscale + p.ob;
       }
       const size_t yoff = valid ? ((((size_t)b * p.yHp + yo + p.yP) * p.yWp + xo + p.yP) * p.yC + p.yCoff) : 0;
       const size_t aoff = (valid && p.add) ? ((((size_t)b * p.aHp + yo + p.aP) * p.aWp + xo + p.aP) * p.aC) : 0;
@@ -338,7 +337,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 // ---------------------------------------------------------------------------------------------------
 constexpr int T_PX = 256;                 // pixels per tile
 constexpr int T_STAGE = 2 * 128 * 128 + 2 * T_PX * 128;  // W hi/lo [128 x 128 B] + X hi/lo [256 x 128 B] = 96 KB
-constexpr int T_SMEM = 2 * T_STAGE + 1024 + 256 + 4 * 128 * 4 + T_PX * 8;
+constexpr int T_SMEM = 2 * T_STAGE + 1024 + 256 + 4 * 128 * 4 + T_PX * (8 + 8 + 4);
 
 __global__ void __launch_bounds__(NTHREADS, 1)
     conv_tc_t_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
@@ -354,7 +353,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   uint64_t* tempty = bars + 2 * STAGES + NBUF;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NBUF);
   float* s_stat = reinterpret_cast<float*>(smem + STAGES * T_STAGE + 256);          // [2 halves][2][128]
-  long long* s_off = reinterpret_cast<long long*>(smem + STAGES * T_STAGE + 256 + 4 * 128 * 4);  // [256] or -1
+  long long* s_off = reinterpret_cast<long long*>(smem + STAGES * T_STAGE + 256 + 4 * 128 * 4);  // [256] dst element offset, -1 = masked
+  long long* s_aoff = s_off + T_PX;                                                               // [256] addend element offset
+  int* s_img = reinterpret_cast<int*>(s_aoff + T_PX);                                             // [256] image index
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = (p.Mtot + T_PX - 1) / T_PX;
@@ -390,8 +391,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
           const int m0 = tile * T_PX;
           for (int tap = 0; tap < p.taps; ++tap) {
-            int off = 0;
-            if (p.taps == 9) off = ((tap / 3 - 1) * p.Wp + (tap % 3 - 1)) * p.dil;
+            const int off = p.tap_off[tap];
             for (int kb = 0; kb < kbs; ++kb) {
               tc::mbar_wait(&empty[stage], phase ^ 1);
               uint8_t* st = smem + stage * T_STAGE;
@@ -452,15 +452,21 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       const int m0 = tile * T_PX;
       {  // destination offset of each of the tile's 256 pixels (one per epilogue thread), -1 = masked
         const int pp = m0 + etid;
-        long long off = -1;
+        long long off = -1, aoff = 0;
+        int b = 0;
         if (pp < p.Mtot) {
-          const int b = pp / img, rem = pp - b * img;
+          b = pp / img;
+          const int rem = pp - b * img;
           const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
           const int y = yp - p.P, x = xp - p.P;
           const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W && !(p.stride == 2 && ((y | x) & 1));
-          if (ok) off = (long long)b * (1ll << 40) + ((long long)(y / p.stride) << 20) + (x / p.stride);
+          if (ok) {
+            const int yo = (y / p.stride) * p.oscale + p.oa, xo = (x / p.stride) * p.oscale + p.ob;
+            off = (((long long)b * p.yHp + yo + p.yP) * p.yWp + xo + p.yP) * p.yC + p.yCoff;
+            if (p.add) aoff = (((long long)b * p.aHp + yo + p.aP) * p.aWp + xo + p.aP) * p.aC;
+          }
         }
-        s_off[etid] = off;
+        s_off[etid] = off, s_aoff[etid] = aoff, s_img[etid] = b;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int b_first = m0 / img, b_last = min(m0 + T_PX - 1, p.Mtot - 1) / img;
@@ -498,16 +504,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       for (int j = 0; j < 128; ++j) {
         const long long code = s_off[half * 128 + j];  // same address for the whole warp: broadcast
         if (code >= 0) {
-          const int b = (int)(code >> 40), yo = (int)((code >> 20) & 0xfffff), xo = (int)(code & 0xfffff);
           float v = tot[j] + bias;
           if (p.add) {
-            const size_t ao = (((size_t)b * p.aHp + yo + p.aP) * p.aWp + xo + p.aP) * p.aC + chn;
+            const long long ao = s_aoff[half * 128 + j] + chn;
             v += __ldg(p.add + ao);
             if (p.add_lo) v += __ldg(p.add_lo + ao);
           }
           if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
           if (p.act == ACT_LRELU) v = v > 0.f ? v : v * p.slope;
-          const size_t yo_ = (((size_t)b * p.yHp + yo + p.yP) * p.yWp + xo + p.yP) * p.yC + p.yCoff + chn;
+          const long long yo_ = code + chn;
           if (p.y_lo) {
             const float h = tf32_rna(v);
             p.y[yo_] = h;
@@ -519,6 +524,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             if (uniform_img) {
               ssum += v, ssq += v * v;
             } else {
+              const int b = s_img[half * 128 + j];
               atomicAdd(&p.stats[((size_t)b * p.Cout + chn) * 2 + 0], (double)v);
               atomicAdd(&p.stats[((size_t)b * p.Cout + chn) * 2 + 1], (double)v * (double)v);
             }

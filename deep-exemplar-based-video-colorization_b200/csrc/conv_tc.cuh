@@ -9,7 +9,9 @@ namespace dvc {
 struct ConvTcParams {
   int Hp, Wp, P, H, W, Cin;  // input planes: padded NHWC, Cin a multiple of 32
   int Mtot;                  // B * Hp * Wp
-  int taps, dil, stride;
+  int taps, stride;          // taps: number of row-shifted operands (9 for 3x3, 1 for 1x1, 4 for an up-sampling phase)
+  int tap_off[9];            // their offsets in padded input pixels
+  int oscale, oa, ob;        // output pixel = (y / stride) * oscale + oa, (x / stride) * oscale + ob
   int Cout, CoutPad;         // CoutPad: multiple of the channel tile (weights are zero beyond Cout)
   const float* bias;
   float* y;      // destination: fp32 plane, or the hi plane when y_lo != nullptr

@@ -259,6 +259,41 @@ extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const floa
       CUDA_TRY(c, cudaMemcpy(cw.wt_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
       CUDA_TRY(c, cudaMemcpy(cw.wt_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
       cw.cout_pad_tc = cpt;
+      if (net == DVC_NET_COLOR && taps == 9 && (base == "conv8_1.1" || base == "conv9_1.1" || base == "conv10_1.1")) {
+        // ColorVidNet.py:81-83: Upsample(2, nearest) + Conv2d(3x3, pad 1).  Phase (a, b) of the output sees a 2x2
+        // low-resolution neighbourhood whose weights are sums of the 3x3 taps that land on the same source pixel.
+        for (int ph = 0; ph < 4; ++ph) {
+          const int a = ph >> 1, b2 = ph & 1;
+          ConvW& pw = c->conv[net][base + "#p" + std::to_string(ph)];
+          std::vector<float> phi_((size_t)4 * cpt * cin_pad, 0.f), plo(phi_.size(), 0.f);
+          for (int o = 0; o < co; ++o)
+            for (int i = 0; i < ci; ++i)
+              for (int r = 0; r < 2; ++r)
+                for (int cc = 0; cc < 2; ++cc) {
+                  float v = 0.f;
+                  for (int ky = 0; ky < 3; ++ky) {
+                    const bool rin = a ? (r == 0 ? ky <= 1 : ky == 2) : (r == 0 ? ky == 0 : ky >= 1);
+                    if (!rin) continue;
+                    for (int kx = 0; kx < 3; ++kx) {
+                      const bool cin_ = b2 ? (cc == 0 ? kx <= 1 : kx == 2) : (cc == 0 ? kx == 0 : kx >= 1);
+                      if (cin_) v += h[((size_t)o * ci + i) * 9 + ky * 3 + kx];
+                    }
+                  }
+                  const float vh = host_tf32_rna(v);
+                  phi_[((size_t)(r * 2 + cc) * cpt + o) * cin_pad + i] = vh;
+                  plo[((size_t)(r * 2 + cc) * cpt + o) * cin_pad + i] = host_tf32_rna(v - vh);
+                }
+          if (pw.wt_hi) cudaFree(pw.wt_hi);
+          if (pw.wt_lo) cudaFree(pw.wt_lo);
+          CUDA_TRY(c, cudaMalloc((void**)&pw.wt_hi, phi_.size() * sizeof(float)));
+          CUDA_TRY(c, cudaMalloc((void**)&pw.wt_lo, plo.size() * sizeof(float)));
+          CUDA_TRY(c, cudaMemcpy(pw.wt_hi, phi_.data(), phi_.size() * sizeof(float), cudaMemcpyHostToDevice));
+          CUDA_TRY(c, cudaMemcpy(pw.wt_lo, plo.data(), plo.size() * sizeof(float), cudaMemcpyHostToDevice));
+          pw.cin = ci, pw.cin_pad = cin_pad, pw.cout = co, pw.cout_pad = cout_pad, pw.cout_pad_tc = cpt, pw.k = 2;
+          pw.b = nullptr;  // shares the bias of the 3x3 convolution (resolved at launch)
+          pw.w = nullptr;
+        }
+      }
     }
     auto hb = c->host_bias[net].find(base);
     if (hb != c->host_bias[net].end())
@@ -315,6 +350,7 @@ static int need_vec(dvc_ctx* c, int net, const char* name, const float** out) {
 // ------------------------------------------------------------------------------------------------
 struct ConvOpt {
   int dil = 1, stride = 1, act = ACT_NONE;
+  int phase = -1;  // >= 0: phase (a*2+b) of a nearest-x2 + 3x3 convolution evaluated on the low-resolution input
   float slope = 0.f;
   const Act* add = nullptr;
   double* stats = nullptr;
@@ -323,13 +359,15 @@ struct ConvOpt {
 
 static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const ConvOpt& o, cudaStream_t s) {
   if (x.C != w->cin_pad) return fail(c, DVC_ERR_SHAPE, "conv: input channel mismatch");
-  const int taps = w->k * w->k;
+  const int taps = o.phase >= 0 ? 4 : w->k * w->k;
+  if (o.phase >= 0 && !x.lo) return fail(c, DVC_ERR_STATE, "conv: phase convolution needs the tensor-core engine");
   if (taps == 9 && x.P < o.dil) return fail(c, DVC_ERR_STATE, "conv: input border narrower than the dilation");
   ConvParams p{};
   p.x = x.d, p.Hp = x.Hp(), p.Wp = x.Wp(), p.P = x.P, p.H = x.H, p.W = x.W, p.Cin = x.C;
   p.w = w->w, p.bias = w->b, p.taps = taps, p.dil = o.dil, p.Cout = w->cout, p.CoutPad = w->cout_pad;
   p.stride = o.stride;
   p.Ho = (x.H + o.stride - 1) / o.stride, p.Wo = (x.W + o.stride - 1) / o.stride;
+  if (o.phase >= 0) p.Ho = 2 * x.H, p.Wo = 2 * x.W;
   if (y.H != p.Ho || y.W != p.Wo || y.B != x.B || o.yCoff + w->cout > y.C)
     return fail(c, DVC_ERR_SHAPE, "conv: output shape mismatch");
   p.y = y.d, p.yHp = y.Hp(), p.yWp = y.Wp(), p.yP = y.P, p.yC = y.C, p.yCoff = o.yCoff;
@@ -344,7 +382,21 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     if (!w->wt_hi) return fail(c, DVC_ERR_STATE, "conv: split input but no tensor-core weights");
     ConvTcParams t{};
     t.Hp = p.Hp, t.Wp = p.Wp, t.P = p.P, t.H = p.H, t.W = p.W, t.Cin = p.Cin, t.Mtot = x.B * p.Hp * p.Wp;
-    t.taps = taps, t.dil = o.dil, t.stride = o.stride, t.Cout = w->cout, t.CoutPad = w->cout_pad_tc, t.bias = w->b;
+    t.taps = taps, t.stride = o.stride, t.Cout = w->cout, t.CoutPad = w->cout_pad_tc, t.bias = w->b;
+    t.oscale = 1, t.oa = 0, t.ob = 0;
+    if (o.phase >= 0) {
+      // nearest-x2 then 3x3 (zero pad 1) == four 2x2 convolutions on the low-resolution map, one per output parity
+      // (a, b): rows {-1, 0} for a = 0 and {0, +1} for a = 1, same for columns (weights pre-summed at load time)
+      const int a = o.phase >> 1, b2 = o.phase & 1;
+      const int r0 = a ? 0 : -1, c0 = b2 ? 0 : -1;
+      for (int r = 0; r < 2; ++r)
+        for (int cc = 0; cc < 2; ++cc) t.tap_off[r * 2 + cc] = (r0 + r) * p.Wp + (c0 + cc);
+      t.taps = 4, t.oscale = 2, t.oa = a, t.ob = b2;
+    } else if (taps == 9) {
+      for (int k = 0; k < 9; ++k) t.tap_off[k] = ((k / 3 - 1) * p.Wp + (k % 3 - 1)) * o.dil;
+    } else {
+      t.tap_off[0] = 0;
+    }
     t.y = y.d, t.y_lo = y.lo, t.yHp = p.yHp, t.yWp = p.yWp, t.yP = p.yP, t.yC = p.yC, t.yCoff = p.yCoff;
     t.add = p.add, t.add_lo = o.add ? o.add->lo : nullptr, t.aHp = p.aHp, t.aWp = p.aWp, t.aP = p.aP, t.aC = p.aC;
     t.act = o.act, t.slope = o.slope, t.stats = o.stats, t.kc = c->tc_kc, t.transposed = c->tc_transposed;
@@ -360,7 +412,7 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     if (c->prof_conv) {
       CUDA_TRY(c, cudaEventRecord(e1, s));
       // algorithmic FLOPs: 2 x output pixels x taps x Cin x Cout (padding channels and masked border pixels excluded)
-      c->conv_events.push_back({e0, e1, 2.0 * x.B * p.Ho * p.Wo * taps * (double)w->cin * w->cout, variant});
+      c->conv_events.push_back({e0, e1, 2.0 * x.B * (o.phase >= 0 ? x.H * x.W : p.Ho * p.Wo) * taps * (double)w->cin * w->cout, variant});
     }
     return check_launch(c, "conv_tc");
   }
@@ -614,6 +666,33 @@ static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* o
     o.pad_mode = PAD_ZERO, o.up = up, o.sub = sub, o.stats = st, o.count = (double)raw.H * raw.W, o.scale = scale;
     return run_xform(c, raw, *y, o, s);
   };
+  // decoder "deconv" = nearest x2 + 3x3 conv (ColorVidNet.py:81-83) + skip add + ReLU.  Tensor-core mode evaluates
+  // it as four 2x2 phase convolutions on the low-resolution map (2.25x fewer MACs, no up-sampled activation in HBM);
+  // the CUDA-core mode keeps the literal formulation.
+  auto upconv = [&](const char* name, const Act& raw, const double* st, const Act* add, Act* y) -> int {
+    const ConvW* w;
+    DVC_TRY(need_conv(c, net, name, &w));
+    DVC_TRY(get_act(c, tag + "." + name + "#" + std::to_string(uid++), B, raw.H * 2, raw.W * 2, w->cout, 1, y, s, tc_mode(c)));
+    if (tc_mode(c)) {
+      Act nl;
+      DVC_TRY(norm((std::string(name) + ".in").c_str(), raw, st, &nl, 1, 1, 1, nullptr));
+      for (int ph = 0; ph < 4; ++ph) {
+        auto it = c->conv[net].find(std::string(name) + "#p" + std::to_string(ph));
+        if (it == c->conv[net].end() || !it->second.wt_hi) return fail(c, DVC_ERR_STATE, std::string("phase weights missing: ") + name);
+        ConvW pw = it->second;
+        pw.b = w->b;
+        ConvOpt o;
+        o.act = ACT_RELU, o.add = add, o.phase = ph;
+        DVC_TRY(run_conv(c, &pw, nl, *y, o, s));
+      }
+      return DVC_OK;
+    }
+    Act nu;
+    DVC_TRY(norm((std::string(name) + ".in").c_str(), raw, st, &nu, 1, 2, 1, nullptr));
+    ConvOpt o;
+    o.act = ACT_RELU, o.add = add;
+    return run_conv(c, w, nu, *y, o, s);
+  };
   const float *ss1, *ss2, *ss3, *wab, *bab;
   DVC_TRY(need_vec(c, net, "conv1_2norm_ss", &ss1));
   DVC_TRY(need_vec(c, net, "conv2_2norm_ss", &ss2));
@@ -621,7 +700,7 @@ static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* o
   DVC_TRY(need_vec(c, net, "conv10_ab", &wab));
   DVC_TRY(need_vec(c, net, "conv10_ab.bias", &bab));
 
-  Act a, b, raw1, n1, d1, raw2, n2, d2, raw3, n3, d3, raw4, n4, raw5, n5, raw6, n6, raw7, n7u, t, u;
+  Act a, b, raw1, n1, d1, raw2, n2, d2, raw3, n3, d3, raw4, n4, raw5, n5, raw6, n6, raw7, t, u;
   double *st1, *st2, *st3, *st4, *st5, *st6, *st7, *st8, *st9;
   DVC_TRY(conv("conv1_1.0", in0, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
   DVC_TRY(conv("conv1_1.2", a, &b, 1, ACT_RELU, 1, nullptr, nullptr, 0));
@@ -652,20 +731,16 @@ static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* o
   DVC_TRY(conv("conv7_1", n6, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
   DVC_TRY(conv("conv7_2", a, &b, 1, ACT_RELU, 1, nullptr, nullptr, 0));
   DVC_TRY(conv("conv7_3", b, &raw7, 0, ACT_RELU, 1, nullptr, &st7, 0));
-  DVC_TRY(norm("n7u", raw7, st7, &n7u, 1, 2, 1, nullptr));
   // decoder stage 8: relu(conv8_1(up(n7)) + conv3_3_short(n3))
   DVC_TRY(conv("conv3_3_short", n3, &t, 0, ACT_NONE, 1, nullptr, nullptr, 0));
-  DVC_TRY(conv("conv8_1.1", n7u, &u, 1, ACT_RELU, 1, &t, nullptr, 0));
+  DVC_TRY(upconv("conv8_1.1", raw7, st7, &t, &u));
   DVC_TRY(conv("conv8_2", u, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
   DVC_TRY(conv("conv8_3", a, &raw1, 0, ACT_RELU, 1, nullptr, &st8, 0));
-  Act n8u, n9u;
-  DVC_TRY(norm("n8u", raw1, st8, &n8u, 1, 2, 1, nullptr));
   DVC_TRY(conv("conv2_2_short", n2, &t, 0, ACT_NONE, 1, nullptr, nullptr, 0));
-  DVC_TRY(conv("conv9_1.1", n8u, &u, 1, ACT_RELU, 1, &t, nullptr, 0));
+  DVC_TRY(upconv("conv9_1.1", raw1, st8, &t, &u));
   DVC_TRY(conv("conv9_2", u, &raw2, 0, ACT_RELU, 1, nullptr, &st9, 0));
-  DVC_TRY(norm("n9u", raw2, st9, &n9u, 1, 2, 1, nullptr));
   DVC_TRY(conv("conv1_2_short", n1, &t, 0, ACT_NONE, 1, nullptr, nullptr, 0));
-  DVC_TRY(conv("conv10_1.1", n9u, &u, 1, ACT_RELU, 1, &t, nullptr, 0));
+  DVC_TRY(upconv("conv10_1.1", raw2, st9, &t, &u));
   DVC_TRY(conv("conv10_2", u, &a, 0, ACT_LRELU, 1, nullptr, nullptr, 0.2f));
   if (a.H != H || a.W != W || a.C != 128) return fail(c, DVC_ERR_SHAPE, "ColorVidNet: decoder shape mismatch");
   launch_final_ab(a.d, H, W, a.P, a.C, wab, bab, out_nchw, B, s);
