@@ -217,3 +217,94 @@ void launch_conv_simt(const ConvParams& p, int B, bool two_level, cudaStream_t s
 }
 
 }  // namespace dvc
+
+// ---------------------------------------------------------------------------------------------------
+// First-layer convolution (3 or 7 real input channels padded to 8; VGG conv1_1, ColorVidNet conv1_1.0):
+// K = 27 / 63 is far too short for the GEMM tiling above, so one thread computes one output pixel for all output
+// channels with the weights staged in shared memory (broadcast reads).  FFMA-bound: ~50 us at 480x864.
+// ---------------------------------------------------------------------------------------------------
+namespace dvc {
+namespace {
+
+template <int COUT>
+__global__ void __launch_bounds__(128) conv_first_kernel(const ConvParams p, int cin_real) {
+  __shared__ __align__(16) float ws[9 * 8 * COUT];
+  __shared__ float bs[COUT];
+  for (int i = threadIdx.x; i < 9 * 8 * COUT; i += 128) {
+    const int co = i % COUT, k = i / COUT;  // k = tap * 8 + ci
+    ws[i] = __ldg(p.w + (size_t)k * p.CoutPad + co);
+  }
+  for (int i = threadIdx.x; i < COUT; i += 128) bs[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * 128 + threadIdx.x;
+  if (pix >= p.H * p.W) return;
+  const int y = pix / p.W, x = pix - y * p.W;
+  float acc[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+  const float* xb = p.x + (size_t)b * p.Hp * p.Wp * 8;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const float* px = xb + ((size_t)(y + p.P + tap / 3 - 1) * p.Wp + (x + p.P + tap % 3 - 1)) * 8;
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(px)), v1 = __ldg(reinterpret_cast<const float4*>(px + 4));
+    const float in[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) {
+      if (ci < cin_real) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + (tap * 8 + ci) * COUT);
+#pragma unroll
+        for (int c4 = 0; c4 < COUT / 4; ++c4) {
+          const float4 w4 = wr[c4];
+          acc[c4 * 4 + 0] = fmaf(in[ci], w4.x, acc[c4 * 4 + 0]);
+          acc[c4 * 4 + 1] = fmaf(in[ci], w4.y, acc[c4 * 4 + 1]);
+          acc[c4 * 4 + 2] = fmaf(in[ci], w4.z, acc[c4 * 4 + 2]);
+          acc[c4 * 4 + 3] = fmaf(in[ci], w4.w, acc[c4 * 4 + 3]);
+        }
+      }
+    }
+  }
+  const size_t o = (((size_t)b * p.yHp + y + p.yP) * p.yWp + x + p.yP) * p.yC + p.yCoff;
+#pragma unroll
+  for (int c4 = 0; c4 < COUT / 4; ++c4) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = acc[c4 * 4 + j] + bs[c4 * 4 + j];
+      if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+      if (p.act == ACT_LRELU) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+    }
+    if (p.y_lo) {
+      float h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[j]));
+        h[j] = __uint_as_float(u);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[j] - h[j]));
+        l[j] = __uint_as_float(u);
+      }
+      *reinterpret_cast<float4*>(p.y + o + c4 * 4) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(p.y_lo + o + c4 * 4) = make_float4(l[0], l[1], l[2], l[3]);
+    } else {
+      *reinterpret_cast<float4*>(p.y + o + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+}  // namespace
+
+bool launch_conv_first(const ConvParams& p, int B, int cin_real, cudaStream_t s) {
+  if (p.Cin != 8 || p.taps != 9 || p.dil != 1 || p.stride != 1 || p.add || p.stats || p.P < 1) return false;
+  dim3 grid((p.H * p.W + 127) / 128, B);
+  if (p.Cout == 64)
+    conv_first_kernel<64><<<grid, 128, 0, s>>>(p, cin_real);
+  else if (p.Cout == 32)
+    conv_first_kernel<32><<<grid, 128, 0, s>>>(p, cin_real);
+  else
+    return false;
+  launch_counter_add(1);
+  return true;
+}
+
+}  // namespace dvc

@@ -417,6 +417,9 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     return check_launch(c, "conv_tc");
   }
   if (o.add && o.add->lo) return fail(c, DVC_ERR_STATE, "conv: CUDA-core kernel cannot read a split addend");
+  // tensor-core mode: the two K = 27 / 63 first layers use the per-pixel kernel (the fp32 parity mode keeps the
+  // two-level GEMM kernel for every layer)
+  if (tc_mode(c) && launch_conv_first(p, x.B, w->cin, s)) return check_launch(c, "conv_first");
   launch_conv_simt(p, x.B, c->two_level, s);
   return check_launch(c, "conv");
 }

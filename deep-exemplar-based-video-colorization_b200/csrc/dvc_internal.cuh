@@ -47,6 +47,8 @@ struct ConvParams {
 };
 
 void launch_conv_simt(const ConvParams& p, int B, bool two_level, cudaStream_t s);
+// first layers (Cin padded to 8): one thread per output pixel; returns false if the shape is not covered
+bool launch_conv_first(const ConvParams& p, int B, int cin_real, cudaStream_t s);
 
 // ---- elementwise gather: InstanceNorm apply / PReLU / pad / up / sub / residual ----------------
 struct XformParams {
