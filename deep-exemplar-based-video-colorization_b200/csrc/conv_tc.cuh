@@ -7,7 +7,7 @@
 namespace dvc {
 
 struct ConvTcParams {
-  int Hp, Wp, P, H, W, Cin;  // input: padded NHWC fp32, Cin a multiple of 32
+  int Hp, Wp, P, H, W, Cin;  // input planes: padded NHWC, Cin a multiple of 32
   int Mtot;                  // B * Hp * Wp
   int taps, stride;          // taps: number of row-shifted operands (9 for 3x3, 1 for 1x1, 4 for an up-sampling phase)
   int tap_off[9];            // their offsets in padded input pixels
@@ -23,13 +23,14 @@ struct ConvTcParams {
   int act;
   float slope;
   double* stats;  // optional [B][Cout][2]
+  int transposed;  // allow the channel-major kernel for 128-output-channel layers
   int kc;         // k-blocks (32 input channels each) summed in TMEM before promotion to fp32 registers
 };
 
 int conv_tc_pick_bn(int cout);  // channel tile (64 / 128 / 256) used for `cout` output channels
-// x: activation [Mtot][Cin] fp32; w_hi/w_lo: weight planes [taps][CoutPad][Cin] (tf32-rounded fp32 words)
-// *variant receives the channel tile chosen (64 / 128 / 256)
-int launch_conv_tc(const ConvTcParams& p, const float* x, const float* w_hi, const float* w_lo, int num_sms, cudaStream_t s,
-                   std::string* err, int* variant = nullptr);
+// x_hi/x_lo: activation planes [Mtot][Cin]; w_hi/w_lo: weight planes [taps][CoutPad][Cin] (tf32-rounded fp32 words)
+// *variant receives the kernel chosen: 64 / 128 / 256 = pixel-major channel tile, 1 = channel-major kernel
+int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
+                   int num_sms, cudaStream_t s, std::string* err, int* variant = nullptr);
 
 }  // namespace dvc

@@ -62,6 +62,8 @@ struct dvc_ctx {
   std::unordered_map<std::string, std::vector<float>> host_bias[3];  // bias seen before its weight
   int num_sms = 148;
   int conv_math = DVC_MATH_FP32, corr_math = DVC_MATH_FP32;
+  int tc_transposed = 0;  // channel-major kernel for 128-output-channel layers: measured slower than the pixel-major
+                          // tile so far (profiles/), kept behind this flag (1 = auto, 2 = force) and under test
   int tc_kc = 1;          // tensor-core convolutions: k-blocks per TMEM chunk (see conv_tc.cu)
   bool two_level = true;  // fp32 convolutions: per-tap two-level accumulation (see conv_simt.cu)
   std::map<std::string, Buf> bufs;
@@ -137,7 +139,6 @@ static int get_buf(dvc_ctx* c, const std::string& name, size_t bytes, void** out
 // split: allocate tf32 hi/lo planes (input of a tensor-core convolution)
 static int get_act(dvc_ctx* c, const std::string& name, int B, int H, int W, int C, int P, Act* a, cudaStream_t s,
                    bool split = false) {
-  split = false;  // activations are single fp32 planes: the tensor-core kernel splits hi/lo inside the SM
   a->B = B, a->H = H, a->W = W, a->C = C, a->P = P;
   const int sig[5] = {B, H, W, C, split ? -1 - P : P};
   void* p = nullptr;
@@ -359,7 +360,7 @@ struct ConvOpt {
 static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const ConvOpt& o, cudaStream_t s) {
   if (x.C != w->cin_pad) return fail(c, DVC_ERR_SHAPE, "conv: input channel mismatch");
   const int taps = o.phase >= 0 ? 4 : w->k * w->k;
-  if (o.phase >= 0 && !(tc_mode(c) && w->wt_hi)) return fail(c, DVC_ERR_STATE, "conv: phase convolution needs the tensor-core engine");
+  if (o.phase >= 0 && !x.lo) return fail(c, DVC_ERR_STATE, "conv: phase convolution needs the tensor-core engine");
   if (taps == 9 && x.P < o.dil) return fail(c, DVC_ERR_STATE, "conv: input border narrower than the dilation");
   ConvParams p{};
   p.x = x.d, p.Hp = x.Hp(), p.Wp = x.Wp(), p.P = x.P, p.H = x.H, p.W = x.W, p.Cin = x.C;
@@ -377,7 +378,8 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
   p.nchw = nullptr;
   p.act = o.act, p.slope = o.slope, p.stats = o.stats;
   p.y_lo = y.lo;
-  if (tc_mode(c) && w->wt_hi && x.C % 32 == 0 && !x.lo) {  // tensor-core engine (3xTF32)
+  if (x.lo) {  // hi/lo planes: tensor-core engine
+    if (!w->wt_hi) return fail(c, DVC_ERR_STATE, "conv: split input but no tensor-core weights");
     ConvTcParams t{};
     t.Hp = p.Hp, t.Wp = p.Wp, t.P = p.P, t.H = p.H, t.W = p.W, t.Cin = p.Cin, t.Mtot = x.B * p.Hp * p.Wp;
     t.taps = taps, t.stride = o.stride, t.Cout = w->cout, t.CoutPad = w->cout_pad_tc, t.bias = w->b;
@@ -397,7 +399,7 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     }
     t.y = y.d, t.y_lo = y.lo, t.yHp = p.yHp, t.yWp = p.yWp, t.yP = p.yP, t.yC = p.yC, t.yCoff = p.yCoff;
     t.add = p.add, t.add_lo = o.add ? o.add->lo : nullptr, t.aHp = p.aHp, t.aWp = p.aWp, t.aP = p.aP, t.aC = p.aC;
-    t.act = o.act, t.slope = o.slope, t.stats = o.stats, t.kc = c->tc_kc;
+    t.act = o.act, t.slope = o.slope, t.stats = o.stats, t.kc = c->tc_kc, t.transposed = c->tc_transposed;
     std::string err;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->prof_conv) {
@@ -406,7 +408,7 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
       CUDA_TRY(c, cudaEventRecord(e0, s));
     }
     int variant = 0;
-    if (launch_conv_tc(t, x.d, w->wt_hi, w->wt_lo, c->num_sms, s, &err, &variant) != 0) return fail(c, DVC_ERR_CUDA, "conv_tc: " + err);
+    if (launch_conv_tc(t, x.d, x.lo, w->wt_hi, w->wt_lo, c->num_sms, s, &err, &variant) != 0) return fail(c, DVC_ERR_CUDA, "conv_tc: " + err);
     if (c->prof_conv) {
       CUDA_TRY(c, cudaEventRecord(e1, s));
       // algorithmic FLOPs: 2 x output pixels x taps x Cin x Cout (padding channels and masked border pixels excluded)
@@ -836,6 +838,7 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!c || !name) return DVC_ERR_ARG;
   if (!strcmp(name, "two_level")) { c->two_level = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_kc")) { c->tc_kc = value < 1 ? 1 : value; return DVC_OK; }
+  if (!strcmp(name, "tc_transposed")) { c->tc_transposed = value; return DVC_OK; }  // 0 off, 1 auto, 2 force
   return fail(c, DVC_ERR_ARG, std::string("unknown debug flag ") + name);
 }
 
