@@ -178,8 +178,6 @@ def main():
     ap.add_argument("--conv-math", default=os.environ.get("DVC_CONV_MATH", "tf32x3"), choices=["fp32", "tf32x3"])
     ap.add_argument("--tc-kc", type=int, default=int(os.environ.get("DVC_TC_KC", "1")),
                     help="k-blocks summed in TMEM before promotion to fp32 registers (1 = parity mode)")
-    ap.add_argument("--tc-transposed", type=int, default=int(os.environ.get("DVC_TC_T", "0")),
-                    help="channel-major kernel for the 128-channel layers: 0 off, 1 auto")
     ap.add_argument("--cpu-sample", type=int, default=2, help="frames timed for cpu_baseline (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
@@ -209,7 +207,6 @@ def main():
     corr_mode = {"fp32": dvc.MATH_FP32, "tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3}[args.corr_math]
     ctx.set_math(conv=dvc.MATH_TF32X3 if args.conv_math == "tf32x3" else dvc.MATH_FP32, corr=corr_mode)
     ctx.debug_flag("tc_kc", args.tc_kc)
-    ctx.debug_flag("tc_transposed", args.tc_transposed)
 
     K, Wm = args.steps, args.warmup
     # every rank owns its own contiguous segment of synthetic frames (distinct content per rank and per step)
@@ -283,7 +280,7 @@ def main():
     ms_serial = e4.elapsed_time(e5) / KP
     corr_ms = ctx.corr_mean_ms(True)
     conv_all = ctx.conv_profile(0)
-    conv_by = {v: ctx.conv_profile(v) for v in (256, 128, 64, 1)}
+    conv_by = {v: ctx.conv_profile(v) for v in (256, 128, 64)}
     ctx.conv_profile(0, reset=True)
     ctx.profile_corr(False)
     ctx.profile_conv(False)

@@ -327,231 +327,6 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Transposed variant for 128-output-channel layers:  D[co, px] = sum_k W[co, k] X[px, k]
-// The weights are the M = 128 operand (TMEM lane = output channel) and 256 pixels the N operand, so every MMA is
-// the M128 x N256 shape whose operand fetch (12 KB per 128 clk) fits the 128 B/clk shared-memory port; the pixel-
-// major M128 x N128 form of conv_tc_kernel<128> needs 8 KB per 64 clk and is shared-memory bound.  Epilogue:
-// thread = one channel x 128 pixels; per-channel bias / statistics need no cross-lane traffic, and for each pixel
-// the 32 lanes of a warp store 32 consecutive channels (one 128-byte line).
-// ---------------------------------------------------------------------------------------------------
-constexpr int T_PX = 256;                 // pixels per tile
-constexpr int T_STAGE = 2 * 128 * 128 + 2 * T_PX * 128;  // W hi/lo [128 x 128 B] + X hi/lo [256 x 128 B] = 96 KB
-constexpr int T_SMEM = 2 * T_STAGE + 1024 + 256 + 4 * 128 * 4 + T_PX * (8 + 8 + 4);
-
-__global__ void __launch_bounds__(NTHREADS, 1)
-    conv_tc_t_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
-                     const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const ConvTcParams p) {
-  constexpr uint32_t IDESC = tc::umma_idesc(2u, 128, T_PX);
-  constexpr int STAGES = 2, NBUF = 2;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * T_STAGE);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tfull = bars + 2 * STAGES;
-  uint64_t* tempty = bars + 2 * STAGES + NBUF;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NBUF);
-  float* s_stat = reinterpret_cast<float*>(smem + STAGES * T_STAGE + 256);          // [2 halves][2][128]
-  long long* s_off = reinterpret_cast<long long*>(smem + STAGES * T_STAGE + 256 + 4 * 128 * 4);  // [256] dst element offset, -1 = masked
-  long long* s_aoff = s_off + T_PX;                                                               // [256] addend element offset
-  int* s_img = reinterpret_cast<int*>(s_aoff + T_PX);                                             // [256] image index
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = (p.Mtot + T_PX - 1) / T_PX;
-  const int kbs = p.Cin / 32;
-  const int nk = p.taps * kbs;
-  const int kc = p.kc;
-  const int nchunks = (nk + kc - 1) / kc;
-
-  if (threadIdx.x == 0) {
-    tc::tma_prefetch_desc(&tmXh);
-    tc::tma_prefetch_desc(&tmXl);
-    tc::tma_prefetch_desc(&tmWh);
-    tc::tma_prefetch_desc(&tmWl);
-    for (int i = 0; i < STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
-    for (int i = 0; i < NBUF; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 8);
-    tc::fence_barrier_init();
-  }
-  if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, 512);
-    tc::tmem_relinquish();
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0) {
-      if (lane == 0) {  // ---- TMA producer ----
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-          const int m0 = tile * T_PX;
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const int off = p.tap_off[tap];
-            for (int kb = 0; kb < kbs; ++kb) {
-              tc::mbar_wait(&empty[stage], phase ^ 1);
-              uint8_t* st = smem + stage * T_STAGE;
-              tc::mbar_arrive_expect_tx(&full[stage], T_STAGE);
-              tc::tma_load_2d(st, &tmWh, &full[stage], kb * 32, tap * p.CoutPad);
-              tc::tma_load_2d(st + 16384, &tmWl, &full[stage], kb * 32, tap * p.CoutPad);
-              tc::tma_load_2d(st + 32768, &tmXh, &full[stage], kb * 32, m0 + off);
-              tc::tma_load_2d(st + 32768 + T_PX * 128, &tmXl, &full[stage], kb * 32, m0 + off);
-              if (++stage == STAGES) stage = 0, phase ^= 1;
-            }
-          }
-        }
-      }
-    } else if (warp == 1) {
-      if (lane == 0) {  // ---- MMA issuer ----
-        int stage = 0;
-        uint32_t phase = 0, chunk_id = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-          for (int ch = 0; ch < nchunks; ++ch, ++chunk_id) {
-            const int buf = chunk_id % NBUF;
-            const uint32_t acc_phase = (chunk_id / NBUF) & 1;
-            tc::mbar_wait(&tempty[buf], acc_phase ^ 1);
-            tc::tc_fence_after();
-            const uint32_t d = tmem_base + buf * T_PX;
-            const int k_end = min((ch + 1) * kc, nk);
-            for (int k = ch * kc; k < k_end; ++k) {
-              tc::mbar_wait(&full[stage], phase);
-              tc::tc_fence_after();
-              const uint32_t sa = tc::smem_u32(smem + stage * T_STAGE);
-              const uint64_t dWh = tc::umma_desc_k128(sa), dWl = tc::umma_desc_k128(sa + 16384);
-              const uint64_t dXh = tc::umma_desc_k128(sa + 32768), dXl = tc::umma_desc_k128(sa + 32768 + T_PX * 128);
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-                tc::umma_ss<true>(d, dWl + adv, dXh + adv, IDESC, (k > ch * kc || kk) ? 1u : 0u);
-                tc::umma_ss<true>(d, dWh + adv, dXl + adv, IDESC, 1u);
-                tc::umma_ss<true>(d, dWh + adv, dXh + adv, IDESC, 1u);
-              }
-              tc::umma_commit(&empty[stage]);
-              if (k == k_end - 1) tc::umma_commit(&tfull[buf]);
-              if (++stage == STAGES) stage = 0, phase ^= 1;
-            }
-          }
-        }
-      }
-    }
-  } else {
-    // ================= epilogue: thread = one output channel x 128 pixels =================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int q = warp & 3;
-    const int half = (warp - 4) >> 2;    // pixel columns [half*128, half*128 + 128)
-    const int etid = threadIdx.x - 128;  // 0..255
-    const int chn = q * 32 + lane;       // output channel (Cout == 128)
-    const int img = p.Hp * p.Wp;
-    const float bias = __ldg(p.bias + chn);
-    uint32_t chunk_id = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = tile * T_PX;
-      {  // destination offset of each of the tile's 256 pixels (one per epilogue thread), -1 = masked
-        const int pp = m0 + etid;
-        long long off = -1, aoff = 0;
-        int b = 0;
-        if (pp < p.Mtot) {
-          b = pp / img;
-          const int rem = pp - b * img;
-          const int yp = rem / p.Wp, xp = rem - yp * p.Wp;
-          const int y = yp - p.P, x = xp - p.P;
-          const bool ok = y >= 0 && y < p.H && x >= 0 && x < p.W && !(p.stride == 2 && ((y | x) & 1));
-          if (ok) {
-            const int yo = (y / p.stride) * p.oscale + p.oa, xo = (x / p.stride) * p.oscale + p.ob;
-            off = (((long long)b * p.yHp + yo + p.yP) * p.yWp + xo + p.yP) * p.yC + p.yCoff;
-            if (p.add) aoff = (((long long)b * p.aHp + yo + p.aP) * p.aWp + xo + p.aP) * p.aC;
-          }
-        }
-        s_off[etid] = off, s_aoff[etid] = aoff, s_img[etid] = b;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int b_first = m0 / img, b_last = min(m0 + T_PX - 1, p.Mtot - 1) / img;
-      const bool uniform_img = (b_first == b_last);
-
-      float tot[128];
-      for (int ch = 0; ch < nchunks; ++ch, ++chunk_id) {
-        const int buf = chunk_id % NBUF;
-        const uint32_t acc_phase = (chunk_id / NBUF) & 1;
-        tc::mbar_wait(&tfull[buf], acc_phase);
-        tc::tc_fence_after();
-        const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * T_PX + half * 128;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r0[32], r1[32];
-          __syncwarp();
-          tc::tmem_ld_32x32(tsrc + c * 64, r0);
-          tc::tmem_ld_32x32(tsrc + c * 64 + 32, r1);
-          tc::tmem_ld_wait();
-          if (ch == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tot[c * 64 + j] = __uint_as_float(r0[j]), tot[c * 64 + 32 + j] = __uint_as_float(r1[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tot[c * 64 + j] += __uint_as_float(r0[j]), tot[c * 64 + 32 + j] += __uint_as_float(r1[j]);
-          }
-        }
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&tempty[buf]);
-      }
-
-      float ssum = 0.f, ssq = 0.f;
-#pragma unroll
-      for (int j = 0; j < 128; ++j) {
-        const long long code = s_off[half * 128 + j];  // same address for the whole warp: broadcast
-        if (code >= 0) {
-          float v = tot[j] + bias;
-          if (p.add) {
-            const long long ao = s_aoff[half * 128 + j] + chn;
-            v += __ldg(p.add + ao);
-            if (p.add_lo) v += __ldg(p.add_lo + ao);
-          }
-          if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
-          if (p.act == ACT_LRELU) v = v > 0.f ? v : v * p.slope;
-          const long long yo_ = code + chn;
-          if (p.y_lo) {
-            const float h = tf32_rna(v);
-            p.y[yo_] = h;
-            p.y_lo[yo_] = tf32_rna(v - h);
-          } else {
-            p.y[yo_] = v;
-          }
-          if (p.stats) {
-            if (uniform_img) {
-              ssum += v, ssq += v * v;
-            } else {
-              const int b = s_img[half * 128 + j];
-              atomicAdd(&p.stats[((size_t)b * p.Cout + chn) * 2 + 0], (double)v);
-              atomicAdd(&p.stats[((size_t)b * p.Cout + chn) * 2 + 1], (double)v * (double)v);
-            }
-          }
-        }
-      }
-      if (p.stats) {
-        s_stat[(half * 2 + 0) * 128 + chn] = ssum;
-        s_stat[(half * 2 + 1) * 128 + chn] = ssq;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // s_off / s_stat consumed before the next tile rewrites them
-      if (p.stats && uniform_img && etid < 128) {
-        atomicAdd(&p.stats[((size_t)b_first * p.Cout + etid) * 2 + 0], (double)s_stat[0 * 128 + etid] + (double)s_stat[2 * 128 + etid]);
-        atomicAdd(&p.stats[((size_t)b_first * p.Cout + etid) * 2 + 1], (double)s_stat[1 * 128 + etid] + (double)s_stat[3 * 128 + etid]);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
-  }
-
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 512);
-  }
-}
-
 template <int BN>
 int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap& mWh, const CUtensorMap& mWl,
               const ConvTcParams& p, int num_sms, cudaStream_t s) {
@@ -589,24 +364,6 @@ int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, 
   if (p.Cin % 32) return fail("Cin must be a multiple of 32");
   if (p.kc < 1) return fail("kc must be >= 1");
   if (p.CoutPad % conv_tc_pick_bn(p.Cout)) return fail("CoutPad must be a multiple of the channel tile");
-  if (p.transposed && p.Cout == 128 && p.CoutPad == 128 && (p.transposed == 2 || (p.Mtot + T_PX - 1) / T_PX >= num_sms)) {
-    CUtensorMap mXh, mXl, mWh, mWl;
-    if (encode_tmap_2d(&mXh, x_hi, (uint64_t)p.Mtot, p.Cin, T_PX, 32, 4) || encode_tmap_2d(&mXl, x_lo, (uint64_t)p.Mtot, p.Cin, T_PX, 32, 4) ||
-        encode_tmap_2d(&mWh, w_hi, (uint64_t)p.taps * p.CoutPad, p.Cin, 128, 32, 4) ||
-        encode_tmap_2d(&mWl, w_lo, (uint64_t)p.taps * p.CoutPad, p.Cin, 128, 32, 4))
-      return fail("cuTensorMapEncodeTiled failed");
-    static bool attr = false;
-    if (!attr) {
-      if (cudaFuncSetAttribute(conv_tc_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) != cudaSuccess)
-        return fail("cudaFuncSetAttribute(max dynamic smem) failed");
-      attr = true;
-    }
-    const int total = (p.Mtot + T_PX - 1) / T_PX;
-    conv_tc_t_kernel<<<total < num_sms ? total : num_sms, NTHREADS, T_SMEM, s>>>(mXh, mXl, mWh, mWl, p);
-    launch_counter_add(1);
-    if (variant) *variant = 1;
-    return 0;
-  }
   const int BN = pick_bn_for_launch(p, num_sms);
   if (variant) *variant = BN;
   CUtensorMap mXh, mXl, mWh, mWl;

@@ -23,13 +23,12 @@ struct ConvTcParams {
   int act;
   float slope;
   double* stats;  // optional [B][Cout][2]
-  int transposed;  // allow the channel-major kernel for 128-output-channel layers
   int kc;         // k-blocks (32 input channels each) summed in TMEM before promotion to fp32 registers
 };
 
 int conv_tc_pick_bn(int cout);  // channel tile (64 / 128 / 256) used for `cout` output channels
 // x_hi/x_lo: activation planes [Mtot][Cin]; w_hi/w_lo: weight planes [taps][CoutPad][Cin] (tf32-rounded fp32 words)
-// *variant receives the kernel chosen: 64 / 128 / 256 = pixel-major channel tile, 1 = channel-major kernel
+// *variant receives the channel tile chosen (64 / 128 / 256)
 int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
                    int num_sms, cudaStream_t s, std::string* err, int* variant = nullptr);
 

@@ -32,20 +32,16 @@ def ab_gate(ours, g):
     return err, max(1e-3, 2.0 * floor)
 
 
-@pytest.fixture(params=["fp32", "tf32x3", "tf32x3-chmajor"])
+@pytest.fixture(params=["fp32", "tf32x3"])
 def conv_math(request, ctx):
-    """Convolutions on CUDA cores (exact fp32, two-level accumulation) and on tcgen05 (3xTF32 operand split);
-    "chmajor" forces the channel-major kernel for the 128-channel layers even on tiny inputs (it is otherwise
-    selected only when a layer has >= 148 pixel tiles)."""
+    """Convolutions on CUDA cores (exact fp32, two-level accumulation) and on tcgen05 (3xTF32 operand split)."""
     import dvc
 
-    if request.param.startswith("tf32x3"):
+    if request.param == "tf32x3":
         ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
-        ctx.debug_flag("tc_transposed", 2 if request.param.endswith("chmajor") else 0)
     else:
         ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
     yield request.param
-    ctx.debug_flag("tc_transposed", 0)
     ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
 
 
