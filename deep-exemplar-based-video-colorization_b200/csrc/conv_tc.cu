@@ -45,7 +45,10 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
-template <int BN>
+// CL = 2: the kernel runs as 2-CTA clusters on adjacent pixel tiles of the same channel tile; each CTA fetches half
+// of every weight tile and TMA-multicasts it to both, which cuts the L2 -> SM operand traffic by a third (BN = 256)
+// to a half (BN = 64).  MMAs stay per-CTA (cta_group::1); a stage is released to both producers by a multicast commit.
+template <int BN, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                    const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const ConvTcParams p) {
@@ -66,7 +69,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.Mtot + BM - 1) / BM;
   const int n_tiles = p.CoutPad / BN;
-  const int total_tiles = m_tiles * n_tiles;
+  const int crank = (CL == 2) ? (int)tc::cluster_ctarank() : 0;
+  const int m_groups = (m_tiles + CL - 1) / CL;          // CL adjacent pixel tiles per work item
+  const int total_items = m_groups * n_tiles;
+  const int item0 = blockIdx.x / CL, item_stride = gridDim.x / CL;
   const int kbs = p.Cin / 32;
   const int nk = p.taps * kbs;
   // The TMEM accumulator truncates on every tcgen05.mma; a chunk of `kc` k-blocks (12*kc accumulations) is
@@ -80,7 +86,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc::tma_prefetch_desc(&tmXl);
     tc::tma_prefetch_desc(&tmWh);
     tc::tma_prefetch_desc(&tmWl);
-    for (int i = 0; i < C::STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
+    for (int i = 0; i < C::STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], CL);
     for (int i = 0; i < C::NBUF; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 8);
     tc::fence_barrier_init();
   }
@@ -90,6 +96,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (CL == 2) tc::cluster_sync_all();  // the peer's barriers must be initialised before any multicast reaches them
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -101,9 +108,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-        const int m0 = mt * BM, n0 = nt * BN;
+      for (int item = item0; item < total_items; item += item_stride) {
+        const int mg = item / n_tiles, nt = item - mg * n_tiles;
+        const int m0 = (mg * CL + crank) * BM, n0 = nt * BN;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int off = p.tap_off[tap];
           for (int kb = 0; kb < kbs; ++kb) {
@@ -112,8 +119,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
             tc::tma_load_2d(st, &tmXh, &full[stage], kb * 32, m0 + off);
             tc::tma_load_2d(st + A_BYTES, &tmXl, &full[stage], kb * 32, m0 + off);
-            tc::tma_load_2d(st + 2 * A_BYTES, &tmWh, &full[stage], kb * 32, tap * p.CoutPad + n0);
-            tc::tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tmWl, &full[stage], kb * 32, tap * p.CoutPad + n0);
+            if (CL == 1) {
+              tc::tma_load_2d(st + 2 * A_BYTES, &tmWh, &full[stage], kb * 32, tap * p.CoutPad + n0);
+              tc::tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tmWl, &full[stage], kb * 32, tap * p.CoutPad + n0);
+            } else {  // my half of the channel rows, delivered to both CTAs
+              const int hrow = crank * (BN / 2);
+              tc::tma_load_2d_mc(st + 2 * A_BYTES + hrow * 128, &tmWh, &full[stage], kb * 32, tap * p.CoutPad + n0 + hrow, 3);
+              tc::tma_load_2d_mc(st + 2 * A_BYTES + C::B_BYTES + hrow * 128, &tmWl, &full[stage], kb * 32,
+                                 tap * p.CoutPad + n0 + hrow, 3);
+            }
             if (++stage == C::STAGES) stage = 0, phase ^= 1;
           }
         }
@@ -125,7 +139,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk_id = 0;  // global chunk counter: TMEM buffer = chunk_id % NBUF
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = item0; item < total_items; item += item_stride) {
         for (int ch = 0; ch < nchunks; ++ch, ++chunk_id) {
           const int buf = chunk_id % C::NBUF;
           const uint32_t acc_phase = (chunk_id / C::NBUF) & 1;
@@ -146,7 +160,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
               tc::umma_ss<true>(d, dXh + adv, dWl + adv, IDESC, 1u);
               tc::umma_ss<true>(d, dXh + adv, dWh + adv, IDESC, 1u);
             }
-            tc::umma_commit(&empty[stage]);
+            if (CL == 1)
+              tc::umma_commit(&empty[stage]);
+            else
+              tc::umma_commit_mc(&empty[stage], 3);
             if (k == k_end - 1) tc::umma_commit(&tfull[buf]);
             if (++stage == C::STAGES) stage = 0, phase ^= 1;
           }
@@ -162,9 +179,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const int etid = threadIdx.x - 128;     // 0..255
     const int img = p.Hp * p.Wp;
     uint32_t chunk_id = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-      const int m0 = mt * BM, n0 = nt * BN;
+    for (int item = item0; item < total_items; item += item_stride) {
+      const int mg = item / n_tiles, nt = item - mg * n_tiles;
+      const int m0 = (mg * CL + crank) * BM, n0 = nt * BN;
       const int pp = m0 + q * 32 + lane;
       bool valid = pp < p.Mtot;
       int b = 0, yo = 0, xo = 0;
@@ -179,7 +196,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       }
       const size_t yoff = valid ? ((((size_t)b * p.yHp + yo + p.yP) * p.yWp + xo + p.yP) * p.yC + p.yCoff) : 0;
       const size_t aoff = (valid && p.add) ? ((((size_t)b * p.aHp + yo + p.aP) * p.aWp + xo + p.aP) * p.aC) : 0;
-      const int b_first = m0 / img, b_last = min(m0 + BM - 1, p.Mtot - 1) / img;
+      const int b_first = min(m0, p.Mtot - 1) / img, b_last = min(m0 + BM - 1, p.Mtot - 1) / img;
       const bool uniform_img = (b_first == b_last);
 
       // ---- chunk sums: TMEM -> registers, fp32 round-to-nearest accumulation ----
@@ -321,25 +338,34 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
   tc::tc_fence_before();
   __syncthreads();
+  if (CL == 2) tc::cluster_sync_all();  // no CTA may exit while the peer can still multicast into its shared memory
   if (warp == 1) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int BN>
+template <int BN, int CL>
 int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap& mWh, const CUtensorMap& mWl,
               const ConvTcParams& p, int num_sms, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES) !=
+        cudaSuccess)
       return -1;
     attr = true;
   }
-  const int total = ((p.Mtot + BM - 1) / BM) * (p.CoutPad / BN);
-  const int grid = total < num_sms ? total : num_sms;
-  conv_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, s>>>(mXh, mXl, mWh, mWl, p);
-  return 0;
+  const int m_tiles = (p.Mtot + BM - 1) / BM;
+  const int items = ((m_tiles + CL - 1) / CL) * (p.CoutPad / BN);
+  const int max_groups = num_sms / CL;
+  const int grid = CL * (items < max_groups ? items : max_groups);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES, cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL>, mXh, mXl, mWh, mWl, p) == cudaSuccess ? 0 : -2;
 }
 
 }  // namespace
@@ -366,19 +392,30 @@ int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, 
   if (p.CoutPad % conv_tc_pick_bn(p.Cout)) return fail("CoutPad must be a multiple of the channel tile");
   const int BN = pick_bn_for_launch(p, num_sms);
   if (variant) *variant = BN;
+  // 2-CTA clusters when there are at least two pixel tiles per SM pair to go around
+  const int CL = (p.cluster == 2 && (p.Mtot + BM - 1) / BM >= 2) ? 2 : 1;
   CUtensorMap mXh, mXl, mWh, mWl;
   if (encode_tmap_2d(&mXh, x_hi, (uint64_t)p.Mtot, p.Cin, BM, 32, 4) || encode_tmap_2d(&mXl, x_lo, (uint64_t)p.Mtot, p.Cin, BM, 32, 4) ||
-      encode_tmap_2d(&mWh, w_hi, (uint64_t)p.taps * p.CoutPad, p.Cin, BN, 32, 4) ||
-      encode_tmap_2d(&mWl, w_lo, (uint64_t)p.taps * p.CoutPad, p.Cin, BN, 32, 4))
+      encode_tmap_2d(&mWh, w_hi, (uint64_t)p.taps * p.CoutPad, p.Cin, BN / CL, 32, 4) ||
+      encode_tmap_2d(&mWl, w_lo, (uint64_t)p.taps * p.CoutPad, p.Cin, BN / CL, 32, 4))
     return fail("cuTensorMapEncodeTiled failed");
   int rc;
-  if (BN == 256)
-    rc = launch_bn<256>(mXh, mXl, mWh, mWl, p, num_sms, s);
-  else if (BN == 128)
-    rc = launch_bn<128>(mXh, mXl, mWh, mWl, p, num_sms, s);
-  else
-    rc = launch_bn<64>(mXh, mXl, mWh, mWl, p, num_sms, s);
-  if (rc) return fail("cudaFuncSetAttribute(max dynamic smem) failed");
+  if (CL == 2) {
+    if (BN == 256)
+      rc = launch_bn<256, 2>(mXh, mXl, mWh, mWl, p, num_sms, s);
+    else if (BN == 128)
+      rc = launch_bn<128, 2>(mXh, mXl, mWh, mWl, p, num_sms, s);
+    else
+      rc = launch_bn<64, 2>(mXh, mXl, mWh, mWl, p, num_sms, s);
+  } else {
+    if (BN == 256)
+      rc = launch_bn<256, 1>(mXh, mXl, mWh, mWl, p, num_sms, s);
+    else if (BN == 128)
+      rc = launch_bn<128, 1>(mXh, mXl, mWh, mWl, p, num_sms, s);
+    else
+      rc = launch_bn<64, 1>(mXh, mXl, mWh, mWl, p, num_sms, s);
+  }
+  if (rc) return fail(rc == -1 ? "cudaFuncSetAttribute(max dynamic smem) failed" : "cudaLaunchKernelEx failed");
   launch_counter_add(1);
   return 0;
 }
