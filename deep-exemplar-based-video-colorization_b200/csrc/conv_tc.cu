@@ -27,16 +27,21 @@ namespace dvc {
 namespace {
 
 constexpr int BM = 128;
-constexpr int A_BYTES = BM * 128;
+
 constexpr int NTHREADS = 384;  // warpgroup 0: warp 0 TMA, warp 1 MMA (2, 3 idle); warpgroups 1, 2: epilogue
 
-template <int BN>
+// KBY = bytes of K per pipeline stage and operand row: 128 (SWIZZLE_128B, 32 tf32) or 64 (SWIZZLE_64B, 16 tf32).
+// A stage can be refilled only after its MMAs retire, so with S stages only S-1 refills are in flight while one
+// stage computes: at ~2.5 us TMA latency two 96 KB stages keep the tensor pipe ~60 % busy; the same shared memory
+// as four 48 KB stages hides the latency.
+template <int BN, int KBY>
 struct Cfg {
-  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGES = (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) * (128 / KBY);
+  static constexpr int A_BYTES = BM * KBY;
+  static constexpr int B_BYTES = BN * KBY;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int NBUF = 512 / BN;  // TMEM accumulators (2 / 4 / 8): deeper ring hides the flush round trip
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * BN * 4;  // + statistics [4][2][BN]
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + 8 * BN * 4;  // + barriers + statistics [4][2][BN]
 };
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -48,11 +53,13 @@ __device__ __forceinline__ float tf32_rna(float x) {
 // CL = 2: the kernel runs as 2-CTA clusters on adjacent pixel tiles of the same channel tile; each CTA fetches half
 // of every weight tile and TMA-multicasts it to both, which cuts the L2 -> SM operand traffic by a third (BN = 256)
 // to a half (BN = 64).  MMAs stay per-CTA (cta_group::1); a stage is released to both producers by a multicast commit.
-template <int BN, int CL>
+template <int BN, int CL, int KBY>
 __global__ void __launch_bounds__(NTHREADS, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                    const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const ConvTcParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, KBY>;
+  constexpr int A_BYTES = C::A_BYTES;
+  constexpr int KE = KBY / 4;  // K elements per stage
   constexpr uint32_t IDESC = tc::umma_idesc(2u, BM, BN);
   constexpr int CPT = BN / 2;  // output channels per epilogue thread (two warps share a TMEM lane quarter)
 
@@ -64,7 +71,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   uint64_t* tfull = bars + 2 * C::STAGES;                  // [NBUF]
   uint64_t* tempty = bars + 2 * C::STAGES + C::NBUF;       // [NBUF]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 2 * C::NBUF);
-  float* s_stat = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);  // [4 lane quarters][2][BN]
+  float* s_stat = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 512);  // [4 lane quarters][2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.Mtot + BM - 1) / BM;
@@ -73,12 +80,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const int m_groups = (m_tiles + CL - 1) / CL;          // CL adjacent pixel tiles per work item
   const int total_items = m_groups * n_tiles;
   const int item0 = blockIdx.x / CL, item_stride = gridDim.x / CL;
-  const int kbs = p.Cin / 32;
+  const int kbs = p.Cin / KE;
   const int nk = p.taps * kbs;
   // The TMEM accumulator truncates on every tcgen05.mma; a chunk of `kc` k-blocks (12*kc accumulations) is
   // therefore summed in TMEM from zero and then added -- with round-to-nearest fp32 adds -- to a register total
   // by the epilogue warps (the tensor-core analogue of conv_simt.cu's two-level accumulation).
-  const int kc = p.kc;
+  const int kc = p.kc * (128 / KBY);  // p.kc counts 32-element k-blocks (12 MMA accumulations each)
   const int nchunks = (nk + kc - 1) / kc;
 
   if (threadIdx.x == 0) {
@@ -117,15 +124,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             tc::mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + stage * C::STAGE_BYTES;
             tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-            tc::tma_load_2d(st, &tmXh, &full[stage], kb * 32, m0 + off);
-            tc::tma_load_2d(st + A_BYTES, &tmXl, &full[stage], kb * 32, m0 + off);
+            tc::tma_load_2d(st, &tmXh, &full[stage], kb * KE, m0 + off);
+            tc::tma_load_2d(st + A_BYTES, &tmXl, &full[stage], kb * KE, m0 + off);
             if (CL == 1) {
-              tc::tma_load_2d(st + 2 * A_BYTES, &tmWh, &full[stage], kb * 32, tap * p.CoutPad + n0);
-              tc::tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tmWl, &full[stage], kb * 32, tap * p.CoutPad + n0);
+              tc::tma_load_2d(st + 2 * A_BYTES, &tmWh, &full[stage], kb * KE, tap * p.CoutPad + n0);
+              tc::tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tmWl, &full[stage], kb * KE, tap * p.CoutPad + n0);
             } else {  // my half of the channel rows, delivered to both CTAs
               const int hrow = crank * (BN / 2);
-              tc::tma_load_2d_mc(st + 2 * A_BYTES + hrow * 128, &tmWh, &full[stage], kb * 32, tap * p.CoutPad + n0 + hrow, 3);
-              tc::tma_load_2d_mc(st + 2 * A_BYTES + C::B_BYTES + hrow * 128, &tmWl, &full[stage], kb * 32,
+              tc::tma_load_2d_mc(st + 2 * A_BYTES + hrow * KBY, &tmWh, &full[stage], kb * KE, tap * p.CoutPad + n0 + hrow, 3);
+              tc::tma_load_2d_mc(st + 2 * A_BYTES + C::B_BYTES + hrow * KBY, &tmWl, &full[stage], kb * KE,
                                  tap * p.CoutPad + n0 + hrow, 3);
             }
             if (++stage == C::STAGES) stage = 0, phase ^= 1;
@@ -151,10 +158,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             tc::mbar_wait(&full[stage], phase);
             tc::tc_fence_after();
             const uint32_t sa = tc::smem_u32(smem + stage * C::STAGE_BYTES);
-            const uint64_t dXh = tc::umma_desc_k128(sa), dXl = tc::umma_desc_k128(sa + A_BYTES);
-            const uint64_t dWh = tc::umma_desc_k128(sa + 2 * A_BYTES), dWl = tc::umma_desc_k128(sa + 2 * A_BYTES + C::B_BYTES);
+            auto mkdesc = [](uint32_t a) { return KBY == 128 ? tc::umma_desc_k128(a) : tc::umma_desc_k64(a); };
+            const uint64_t dXh = mkdesc(sa), dXl = mkdesc(sa + A_BYTES);
+            const uint64_t dWh = mkdesc(sa + 2 * A_BYTES), dWl = mkdesc(sa + 2 * A_BYTES + C::B_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
+            for (int kk = 0; kk < KBY / 32; ++kk) {
               const uint64_t adv = (uint64_t)((kk * 32) >> 4);
               tc::umma_ss<true>(d, dXl + adv, dWh + adv, IDESC, (k > ch * kc || kk) ? 1u : 0u);
               tc::umma_ss<true>(d, dXh + adv, dWl + adv, IDESC, 1u);
@@ -345,12 +353,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
 }
 
-template <int BN, int CL>
+template <int BN, int CL, int KBY>
 int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap& mWh, const CUtensorMap& mWl,
               const ConvTcParams& p, int num_sms, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES) !=
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, CL, KBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, KBY>::SMEM_BYTES) !=
         cudaSuccess)
       return -1;
     attr = true;
@@ -360,12 +368,12 @@ int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap&
   const int max_groups = num_sms / CL;
   const int grid = CL * (items < max_groups ? items : max_groups);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES, cfg.stream = s;
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<BN, KBY>::SMEM_BYTES, cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
   cfg.attrs = at, cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL>, mXh, mXl, mWh, mWl, p) == cudaSuccess ? 0 : -2;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, KBY>, mXh, mXl, mWh, mWl, p) == cudaSuccess ? 0 : -2;
 }
 
 }  // namespace
@@ -388,6 +396,7 @@ int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, 
     return -1;
   };
   if (p.Cin % 32) return fail("Cin must be a multiple of 32");
+  const int KBY = p.kbytes == 128 ? 128 : 64;
   if (p.kc < 1) return fail("kc must be >= 1");
   if (p.CoutPad % conv_tc_pick_bn(p.Cout)) return fail("CoutPad must be a multiple of the channel tile");
   const int BN = pick_bn_for_launch(p, num_sms);
@@ -395,26 +404,21 @@ int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, 
   // 2-CTA clusters when there are at least two pixel tiles per SM pair to go around
   const int CL = (p.cluster == 2 && (p.Mtot + BM - 1) / BM >= 2) ? 2 : 1;
   CUtensorMap mXh, mXl, mWh, mWl;
-  if (encode_tmap_2d(&mXh, x_hi, (uint64_t)p.Mtot, p.Cin, BM, 32, 4) || encode_tmap_2d(&mXl, x_lo, (uint64_t)p.Mtot, p.Cin, BM, 32, 4) ||
-      encode_tmap_2d(&mWh, w_hi, (uint64_t)p.taps * p.CoutPad, p.Cin, BN / CL, 32, 4) ||
-      encode_tmap_2d(&mWl, w_lo, (uint64_t)p.taps * p.CoutPad, p.Cin, BN / CL, 32, 4))
+  if (encode_tmap_2d(&mXh, x_hi, (uint64_t)p.Mtot, p.Cin, BM, KBY / 4, 4, KBY) ||
+      encode_tmap_2d(&mXl, x_lo, (uint64_t)p.Mtot, p.Cin, BM, KBY / 4, 4, KBY) ||
+      encode_tmap_2d(&mWh, w_hi, (uint64_t)p.taps * p.CoutPad, p.Cin, BN / CL, KBY / 4, 4, KBY) ||
+      encode_tmap_2d(&mWl, w_lo, (uint64_t)p.taps * p.CoutPad, p.Cin, BN / CL, KBY / 4, 4, KBY))
     return fail("cuTensorMapEncodeTiled failed");
   int rc;
+#define DVC_LAUNCH(BNv, CLv)                                                              \
+  rc = (KBY == 128) ? launch_bn<BNv, CLv, 128>(mXh, mXl, mWh, mWl, p, num_sms, s)         \
+                    : launch_bn<BNv, CLv, 64>(mXh, mXl, mWh, mWl, p, num_sms, s)
   if (CL == 2) {
-    if (BN == 256)
-      rc = launch_bn<256, 2>(mXh, mXl, mWh, mWl, p, num_sms, s);
-    else if (BN == 128)
-      rc = launch_bn<128, 2>(mXh, mXl, mWh, mWl, p, num_sms, s);
-    else
-      rc = launch_bn<64, 2>(mXh, mXl, mWh, mWl, p, num_sms, s);
+    if (BN == 256) { DVC_LAUNCH(256, 2); } else if (BN == 128) { DVC_LAUNCH(128, 2); } else { DVC_LAUNCH(64, 2); }
   } else {
-    if (BN == 256)
-      rc = launch_bn<256, 1>(mXh, mXl, mWh, mWl, p, num_sms, s);
-    else if (BN == 128)
-      rc = launch_bn<128, 1>(mXh, mXl, mWh, mWl, p, num_sms, s);
-    else
-      rc = launch_bn<64, 1>(mXh, mXl, mWh, mWl, p, num_sms, s);
+    if (BN == 256) { DVC_LAUNCH(256, 1); } else if (BN == 128) { DVC_LAUNCH(128, 1); } else { DVC_LAUNCH(64, 1); }
   }
+#undef DVC_LAUNCH
   if (rc) return fail(rc == -1 ? "cudaFuncSetAttribute(max dynamic smem) failed" : "cudaLaunchKernelEx failed");
   launch_counter_add(1);
   return 0;

@@ -35,7 +35,7 @@ namespace dvc {
 // tensor-map encoding through the driver entry point (no link-time libcuda dependency)
 // ------------------------------------------------------------------------------------------------
 int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
-                   int elem_bytes) {
+                   int elem_bytes, int swizzle_bytes) {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -52,7 +52,7 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
   const cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 

@@ -62,6 +62,7 @@ struct dvc_ctx {
   std::unordered_map<std::string, std::vector<float>> host_bias[3];  // bias seen before its weight
   int num_sms = 148;
   int conv_math = DVC_MATH_FP32, corr_math = DVC_MATH_FP32;
+  int tc_kbytes = 64;     // tensor-core convolutions: K bytes per pipeline stage (64 or 128, see conv_tc.cu)
   int tc_cluster = 1;     // tensor-core convolutions: 2 = 2-CTA clusters with multicast weight tiles
   int tc_kc = 1;          // tensor-core convolutions: k-blocks per TMEM chunk (see conv_tc.cu)
   bool two_level = true;  // fp32 convolutions: per-tap two-level accumulation (see conv_simt.cu)
@@ -398,7 +399,7 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     }
     t.y = y.d, t.y_lo = y.lo, t.yHp = p.yHp, t.yWp = p.yWp, t.yP = p.yP, t.yC = p.yC, t.yCoff = p.yCoff;
     t.add = p.add, t.add_lo = o.add ? o.add->lo : nullptr, t.aHp = p.aHp, t.aWp = p.aWp, t.aP = p.aP, t.aC = p.aC;
-    t.act = o.act, t.slope = o.slope, t.stats = o.stats, t.kc = c->tc_kc, t.cluster = c->tc_cluster;
+    t.act = o.act, t.slope = o.slope, t.stats = o.stats, t.kc = c->tc_kc, t.cluster = c->tc_cluster, t.kbytes = c->tc_kbytes;
     std::string err;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->prof_conv) {
@@ -837,6 +838,7 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!c || !name) return DVC_ERR_ARG;
   if (!strcmp(name, "two_level")) { c->two_level = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_kc")) { c->tc_kc = value < 1 ? 1 : value; return DVC_OK; }
+  if (!strcmp(name, "tc_kbytes")) { c->tc_kbytes = value == 128 ? 128 : 64; return DVC_OK; }
   if (!strcmp(name, "tc_cluster")) { c->tc_cluster = value == 2 ? 2 : 1; return DVC_OK; }
   return fail(c, DVC_ERR_ARG, std::string("unknown debug flag ") + name);
 }

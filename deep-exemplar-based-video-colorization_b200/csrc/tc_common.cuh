@@ -129,6 +129,16 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;           // SWIZZLE_128B
   return d;
 }
+// Same for SWIZZLE_64B tiles (64-byte rows, 8-row groups 512 B apart, layout type 4)
+__device__ __forceinline__ uint64_t umma_desc_k64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+  return d;
+}
 // Instruction descriptor: fp32 accumulate, both operands K-major, dense.  fmt: 0 f16, 1 bf16, 2 tf32.
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -175,6 +185,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // Host: encode a 2-D row-major [rows][cols] tensor map with a [box_rows][box_cols] box and 128-byte swizzle.
 // elem_bytes 4 -> FLOAT32 words (fp32 / pre-rounded tf32), 2 -> BFLOAT16.  Returns 0 on success.
 int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
-                   int elem_bytes);
+                   int elem_bytes, int swizzle_bytes = 128);
 
 }  // namespace dvc
