@@ -178,8 +178,8 @@ def main():
     ap.add_argument("--conv-math", default=os.environ.get("DVC_CONV_MATH", "tf32x3"), choices=["fp32", "tf32x3"])
     ap.add_argument("--tc-kc", type=int, default=int(os.environ.get("DVC_TC_KC", "1")),
                     help="k-blocks summed in TMEM before promotion to fp32 registers (1 = parity mode)")
-    ap.add_argument("--tc-kbytes", type=int, default=int(os.environ.get("DVC_TC_KBYTES", "64")), choices=[64, 128],
-                    help="K bytes per pipeline stage of the conv engine (64 = twice the stages)")
+    ap.add_argument("--tc-kbytes", type=int, default=int(os.environ.get("DVC_TC_KBYTES", "128")), choices=[64, 128],
+                    help="K bytes per pipeline stage of the conv engine (64 = twice the stages, measured slower)")
     ap.add_argument("--tc-cluster", type=int, default=int(os.environ.get("DVC_TC_CLUSTER", "1")), choices=[1, 2],
                     help="2 = 2-CTA clusters with TMA-multicast weight tiles in the conv engine")
     ap.add_argument("--cpu-sample", type=int, default=2, help="frames timed for cpu_baseline (0 = skip)")

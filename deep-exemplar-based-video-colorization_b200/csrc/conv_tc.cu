@@ -396,7 +396,7 @@ int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, 
     return -1;
   };
   if (p.Cin % 32) return fail("Cin must be a multiple of 32");
-  const int KBY = p.kbytes == 128 ? 128 : 64;
+  const int KBY = p.kbytes == 64 ? 64 : 128;
   if (p.kc < 1) return fail("kc must be >= 1");
   if (p.CoutPad % conv_tc_pick_bn(p.Cout)) return fail("CoutPad must be a multiple of the channel tile");
   const int BN = pick_bn_for_launch(p, num_sms);

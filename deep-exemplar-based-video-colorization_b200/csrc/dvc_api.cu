@@ -62,7 +62,7 @@ struct dvc_ctx {
   std::unordered_map<std::string, std::vector<float>> host_bias[3];  // bias seen before its weight
   int num_sms = 148;
   int conv_math = DVC_MATH_FP32, corr_math = DVC_MATH_FP32;
-  int tc_kbytes = 64;     // tensor-core convolutions: K bytes per pipeline stage (64 or 128, see conv_tc.cu)
+  int tc_kbytes = 128;    // tensor-core convolutions: K bytes per pipeline stage (64 or 128, see conv_tc.cu)
   int tc_cluster = 1;     // tensor-core convolutions: 2 = 2-CTA clusters with multicast weight tiles
   int tc_kc = 1;          // tensor-core convolutions: k-blocks per TMEM chunk (see conv_tc.cu)
   bool two_level = true;  // fp32 convolutions: per-tap two-level accumulation (see conv_simt.cu)
@@ -838,7 +838,7 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!c || !name) return DVC_ERR_ARG;
   if (!strcmp(name, "two_level")) { c->two_level = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_kc")) { c->tc_kc = value < 1 ? 1 : value; return DVC_OK; }
-  if (!strcmp(name, "tc_kbytes")) { c->tc_kbytes = value == 128 ? 128 : 64; return DVC_OK; }
+  if (!strcmp(name, "tc_kbytes")) { c->tc_kbytes = value == 64 ? 64 : 128; return DVC_OK; }
   if (!strcmp(name, "tc_cluster")) { c->tc_cluster = value == 2 ? 2 : 1; return DVC_OK; }
   return fail(c, DVC_ERR_ARG, std::string("unknown debug flag ") + name);
 }
