@@ -87,6 +87,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   // by the epilogue warps (the tensor-core analogue of conv_simt.cu's two-level accumulation).
   const int kc = p.kc * (128 / KBY);  // p.kc counts 32-element k-blocks (12 MMA accumulations each)
   const int nchunks = (nk + kc - 1) / kc;
+  // Split-K against wave quantisation (e.g. 208 tiles on 148 SMs): a work item is (tile, split s of S); split s sums
+  // the chunks [nchunks*s/S, nchunks*(s+1)/S) on top of the register totals that split s-1 left in an fp32 workspace,
+  // so the accumulation order -- and every output bit -- is the same as without splitting.  Items are ordered
+  // split-major and every CTA walks its items in increasing order, so the chain of waits always ends at a split-0
+  // item that waits for nothing (all CTAs are resident: one per SM).
+  const int S = p.splits;
+  const int total_work = total_items * S;
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tmXh);
@@ -115,12 +122,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = item0; item < total_items; item += item_stride) {
+      for (int work = item0; work < total_work; work += item_stride) {
+        const int sp = work / total_items, item = work - sp * total_items;
         const int mg = item / n_tiles, nt = item - mg * n_tiles;
         const int m0 = (mg * CL + crank) * BM, n0 = nt * BN;
-        for (int tap = 0; tap < p.taps; ++tap) {
+        const int k_lo = (nchunks * sp / S) * kc, k_hi = min((nchunks * (sp + 1) / S) * kc, nk);
+        for (int k = k_lo; k < k_hi; ++k) {
+          const int tap = k / kbs, kb = k - tap * kbs;
           const int off = p.tap_off[tap];
-          for (int kb = 0; kb < kbs; ++kb) {
+          {
             tc::mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + stage * C::STAGE_BYTES;
             tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
@@ -146,8 +156,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk_id = 0;  // global chunk counter: TMEM buffer = chunk_id % NBUF
-      for (int item = item0; item < total_items; item += item_stride) {
-        for (int ch = 0; ch < nchunks; ++ch, ++chunk_id) {
+      for (int work = item0; work < total_work; work += item_stride) {
+        const int sp = work / total_items;
+        for (int ch = nchunks * sp / S; ch < nchunks * (sp + 1) / S; ++ch, ++chunk_id) {
           const int buf = chunk_id % C::NBUF;
           const uint32_t acc_phase = (chunk_id / C::NBUF) & 1;
           tc::mbar_wait(&tempty[buf], acc_phase ^ 1);
@@ -187,9 +198,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const int etid = threadIdx.x - 128;     // 0..255
     const int img = p.Hp * p.Wp;
     uint32_t chunk_id = 0;
-    for (int item = item0; item < total_items; item += item_stride) {
+    for (int work = item0; work < total_work; work += item_stride) {
+      const int sp = work / total_items, item = work - sp * total_items;
       const int mg = item / n_tiles, nt = item - mg * n_tiles;
       const int m0 = (mg * CL + crank) * BM, n0 = nt * BN;
+      const int tile_id = (mg * CL + crank) * n_tiles + nt;
       const int pp = m0 + q * 32 + lane;
       bool valid = pp < p.Mtot;
       int b = 0, yo = 0, xo = 0;
@@ -209,7 +222,22 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
       // ---- chunk sums: TMEM -> registers, fp32 round-to-nearest accumulation ----
       float tot[CPT];
-      for (int ch = 0; ch < nchunks; ++ch, ++chunk_id) {
+      // workspace layout [tile][channel][pixel row]: for a fixed channel the 32 lanes of a warp touch 128 contiguous bytes
+      float* wsp = p.ws + ((size_t)tile_id * BN + half * CPT) * BM + q * 32 + lane;
+      if (sp > 0) {
+        if (etid == 0) {
+          const int want = p.epoch * 16 + sp;
+          int got;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p.flags + tile_id) : "memory");
+          } while (got != want);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) tot[j] = __ldcg(wsp + (size_t)j * BM);
+      }
+      const int ch_lo = nchunks * sp / S, ch_hi = nchunks * (sp + 1) / S;
+      for (int ch = ch_lo; ch < ch_hi; ++ch, ++chunk_id) {
         const int buf = chunk_id % C::NBUF;
         const uint32_t acc_phase = (chunk_id / C::NBUF) & 1;
         tc::mbar_wait(&tfull[buf], acc_phase);
@@ -223,7 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             tc::tmem_ld_32x32(tsrc + c * 64, r0);
             tc::tmem_ld_32x32(tsrc + c * 64 + 32, r1);
             tc::tmem_ld_wait();
-            if (ch == 0) {
+            if (ch == 0) {  // first chunk of the tile (always in split 0)
 #pragma unroll
               for (int j = 0; j < 32; ++j) tot[c * 64 + j] = __uint_as_float(r0[j]), tot[c * 64 + 32 + j] = __uint_as_float(r1[j]);
             } else {
@@ -247,6 +275,18 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+      }
+
+      if (sp < S - 1) {  // hand the running totals to the next split of this tile
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) __stcg(wsp + (size_t)j * BM, tot[j]);
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (etid == 0) {
+          const int v = p.epoch * 16 + sp + 1;
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.flags + tile_id), "r"(v) : "memory");
+        }
+        continue;
       }
 
       // ---- bias, skip addend, activation, statistics, masked store ----
@@ -364,7 +404,7 @@ int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap&
     attr = true;
   }
   const int m_tiles = (p.Mtot + BM - 1) / BM;
-  const int items = ((m_tiles + CL - 1) / CL) * (p.CoutPad / BN);
+  const int items = ((m_tiles + CL - 1) / CL) * (p.CoutPad / BN) * p.splits;
   const int max_groups = num_sms / CL;
   const int grid = CL * (items < max_groups ? items : max_groups);
   cudaLaunchConfig_t cfg{};
@@ -403,6 +443,25 @@ int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, 
   if (variant) *variant = BN;
   // 2-CTA clusters when there are at least two pixel tiles per SM pair to go around
   const int CL = (p.cluster == 2 && (p.Mtot + BM - 1) / BM >= 2) ? 2 : 1;
+  ConvTcParams q = p;
+  {  // split-K factor: minimise rounds(S) / S over the persistent grid (2 % penalty per extra split for the hand-over)
+    const int m_tiles = (p.Mtot + BM - 1) / BM;
+    const int tiles = ((m_tiles + CL - 1) / CL) * CL * (p.CoutPad / BN);
+    const int kb128 = p.taps * (p.Cin / 32);               // 32-element k-blocks
+    const int nchunks = (kb128 + p.kc - 1) / p.kc;
+    int best = 1;
+    if (p.ws && p.flags && p.splits != 1) {
+      double best_cost = 1e30;
+      for (int S = 1; S <= 8; ++S) {
+        if (S > 1 && nchunks / S < 6) break;
+        const int rounds = (tiles * S + num_sms - 1) / num_sms;
+        const double cost = (double)rounds / S * (1.0 + 0.02 * (S - 1));
+        if (cost < best_cost - 1e-9) best_cost = cost, best = S;
+      }
+      if (p.splits > 1) best = p.splits < nchunks ? p.splits : nchunks;  // forced (tests)
+    }
+    q.splits = best;
+  }
   CUtensorMap mXh, mXl, mWh, mWl;
   if (encode_tmap_2d(&mXh, x_hi, (uint64_t)p.Mtot, p.Cin, BM, KBY / 4, 4, KBY) ||
       encode_tmap_2d(&mXl, x_lo, (uint64_t)p.Mtot, p.Cin, BM, KBY / 4, 4, KBY) ||
@@ -411,8 +470,8 @@ int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, 
     return fail("cuTensorMapEncodeTiled failed");
   int rc;
 #define DVC_LAUNCH(BNv, CLv)                                                              \
-  rc = (KBY == 128) ? launch_bn<BNv, CLv, 128>(mXh, mXl, mWh, mWl, p, num_sms, s)         \
-                    : launch_bn<BNv, CLv, 64>(mXh, mXl, mWh, mWl, p, num_sms, s)
+  rc = (KBY == 128) ? launch_bn<BNv, CLv, 128>(mXh, mXl, mWh, mWl, q, num_sms, s)         \
+                    : launch_bn<BNv, CLv, 64>(mXh, mXl, mWh, mWl, q, num_sms, s)
   if (CL == 2) {
     if (BN == 256) { DVC_LAUNCH(256, 2); } else if (BN == 128) { DVC_LAUNCH(128, 2); } else { DVC_LAUNCH(64, 2); }
   } else {

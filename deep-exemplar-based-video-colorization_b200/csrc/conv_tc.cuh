@@ -23,6 +23,10 @@ struct ConvTcParams {
   int act;
   float slope;
   double* stats;  // optional [B][Cout][2]
+  int splits;     // split-K factor S (1 = off); needs ws / flags below
+  float* ws;      // [tiles][BN][128] fp32 partial totals
+  int* flags;     // [tiles], value epoch*16 + (splits completed)
+  int epoch;      // unique per launch sharing `flags`
   int kbytes;     // bytes of K per pipeline stage: 64 (SWIZZLE_64B, twice the stages) or 128 (SWIZZLE_128B)
   int cluster;    // 2: run as 2-CTA clusters with TMA-multicast weight tiles; 1: single CTAs
   int kc;         // k-blocks (32 input channels each) summed in TMEM before promotion to fp32 registers

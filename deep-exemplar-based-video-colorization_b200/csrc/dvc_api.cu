@@ -70,6 +70,9 @@ struct dvc_ctx {
   // InstanceNorm statistics arena (doubles), bump-allocated per forward call
   double* stats = nullptr;
   size_t stats_cap = 0, stats_used = 0, stats_lo = 0, stats_hi = 0;
+  int cur_arena = 0;          // 0: frame-independent phase, 1: ColorVidNet (may run concurrently on two streams)
+  int tc_epoch[2] = {0, 0};   // split-K hand-over epochs, one flag buffer per arena
+  int tc_splits = 0;          // 0 = automatic split-K, 1 = off, >1 = forced
   // clip driver: frame t+1's VGG/WarpNet/correlation overlaps frame t's ColorVidNet on two internal streams
   cudaStream_t sA = nullptr, sC = nullptr;
   cudaEvent_t evA[4] = {nullptr, nullptr, nullptr, nullptr}, evC[4] = {nullptr, nullptr, nullptr, nullptr}, evFork = nullptr,
@@ -163,6 +166,7 @@ static int stats_begin(dvc_ctx* c, cudaStream_t s, int arena = 0) {
     CUDA_TRY(c, cudaMalloc((void**)&c->stats, need * sizeof(double)));
     c->stats_cap = need;
   }
+  c->cur_arena = arena ? 1 : 0;
   c->stats_lo = arena ? need / 2 : 0;
   c->stats_hi = arena ? need : need / 2;
   c->stats_used = c->stats_lo;
@@ -400,6 +404,17 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     t.y = y.d, t.y_lo = y.lo, t.yHp = p.yHp, t.yWp = p.yWp, t.yP = p.yP, t.yC = p.yC, t.yCoff = p.yCoff;
     t.add = p.add, t.add_lo = o.add ? o.add->lo : nullptr, t.aHp = p.aHp, t.aWp = p.aWp, t.aP = p.aP, t.aC = p.aC;
     t.act = o.act, t.slope = o.slope, t.stats = o.stats, t.kc = c->tc_kc, t.cluster = c->tc_cluster, t.kbytes = c->tc_kbytes;
+    t.splits = c->tc_splits, t.ws = nullptr, t.flags = nullptr, t.epoch = 0;
+    if (c->tc_splits != 1 && (c->tc_splits > 1 || t.Mtot <= 128 * 8 * c->num_sms)) {  // split-K hand-over workspace + flags of this phase's arena (L2-resident, reused by every layer)
+      const size_t mt = ((size_t)t.Mtot + 127) / 128 + 1;
+      void *wsb, *flb;
+      const int sigw[5] = {0, 0, 0, 0, 0};
+      DVC_TRY(get_buf(c, c->cur_arena ? "tc.ws1" : "tc.ws0", mt * 128 * (size_t)w->cout_pad_tc * sizeof(float), &wsb, sigw, false, s));
+      DVC_TRY(get_buf(c, c->cur_arena ? "tc.flags1" : "tc.flags0", (size_t)1 << 20, &flb, sigw, true, s));
+      if (mt * (size_t)(w->cout_pad_tc / 64) < ((size_t)1 << 18)) {
+        t.ws = (float*)wsb, t.flags = (int*)flb, t.epoch = ++c->tc_epoch[c->cur_arena];
+      }
+    }
     std::string err;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->prof_conv) {
@@ -838,6 +853,7 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!c || !name) return DVC_ERR_ARG;
   if (!strcmp(name, "two_level")) { c->two_level = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_kc")) { c->tc_kc = value < 1 ? 1 : value; return DVC_OK; }
+  if (!strcmp(name, "tc_splits")) { c->tc_splits = value < 0 ? 0 : (value > 8 ? 8 : value); return DVC_OK; }
   if (!strcmp(name, "tc_kbytes")) { c->tc_kbytes = value == 64 ? 64 : 128; return DVC_OK; }
   if (!strcmp(name, "tc_cluster")) { c->tc_cluster = value == 2 ? 2 : 1; return DVC_OK; }
   return fail(c, DVC_ERR_ARG, std::string("unknown debug flag ") + name);
