@@ -180,8 +180,8 @@ def main():
                     help="k-blocks summed in TMEM before promotion to fp32 registers (1 = parity mode)")
     ap.add_argument("--tc-kbytes", type=int, default=int(os.environ.get("DVC_TC_KBYTES", "128")), choices=[64, 128],
                     help="K bytes per pipeline stage of the conv engine (64 = twice the stages, measured slower)")
-    ap.add_argument("--tc-splits", type=int, default=int(os.environ.get("DVC_TC_SPLITS", "0")),
-                    help="split-K of the conv engine: 0 automatic, 1 off")
+    ap.add_argument("--tc-splits", type=int, default=int(os.environ.get("DVC_TC_SPLITS", "1")),
+                    help="split-K of the conv engine: 1 off (default), 0 automatic")
     ap.add_argument("--tc-cluster", type=int, default=int(os.environ.get("DVC_TC_CLUSTER", "1")), choices=[1, 2],
                     help="2 = 2-CTA clusters with TMA-multicast weight tiles in the conv engine")
     ap.add_argument("--cpu-sample", type=int, default=2, help="frames timed for cpu_baseline (0 = skip)")

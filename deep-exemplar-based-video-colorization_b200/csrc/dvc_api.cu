@@ -72,7 +72,7 @@ struct dvc_ctx {
   size_t stats_cap = 0, stats_used = 0, stats_lo = 0, stats_hi = 0;
   int cur_arena = 0;          // 0: frame-independent phase, 1: ColorVidNet (may run concurrently on two streams)
   int tc_epoch[2] = {0, 0};   // split-K hand-over epochs, one flag buffer per arena
-  int tc_splits = 0;          // 0 = automatic split-K, 1 = off, >1 = forced
+  int tc_splits = 1;          // split-K: 1 = off (default: measured no gain once two streams overlap), 0 = automatic, >1 = forced
   // clip driver: frame t+1's VGG/WarpNet/correlation overlaps frame t's ColorVidNet on two internal streams
   cudaStream_t sA = nullptr, sC = nullptr;
   cudaEvent_t evA[4] = {nullptr, nullptr, nullptr, nullptr}, evC[4] = {nullptr, nullptr, nullptr, nullptr}, evFork = nullptr,

@@ -42,13 +42,13 @@ def conv_math(request, ctx):
         ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
         ctx.debug_flag("tc_cluster", 2 if request.param.endswith("cluster2") else 1)
         ctx.debug_flag("tc_kbytes", 64 if request.param.endswith("k64") else 128)
-        ctx.debug_flag("tc_splits", 3 if request.param.endswith("split3") else 0)  # 0 = automatic split-K
+        ctx.debug_flag("tc_splits", 3 if request.param.endswith("split3") else 1)
     else:
         ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
     yield request.param
     ctx.debug_flag("tc_cluster", 1)
     ctx.debug_flag("tc_kbytes", 128)
-    ctx.debug_flag("tc_splits", 0)
+    ctx.debug_flag("tc_splits", 1)
     ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
 
 
