@@ -60,36 +60,47 @@ def synth_exemplar(seed=4321):
     return torch.nn.functional.pad(make_lab(seed, 1, H, W_RAW), (0, W - W_RAW, 0, 0), mode="replicate")
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / power / throttle reasons streamed DURING the timed region (B200_PROFILING.md recipe)."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self._halt = index, [], threading.Event()
+        self.index, self.proc, self.lines = index, None, []
 
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.05)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._pump, daemon=True)
+            self._t.start()
+        except Exception:
+            self.proc = None
 
-    def stop(self):
-        self._halt.set()
-        self.join(timeout=5)
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin=None, t_end=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        rows = [l.split(",") for t, l in self.lines if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.06)]
+        rows = [[x.strip() for x in r] for r in rows if len(r) >= 7]
+        sm = sorted(int(r[0]) for r in rows if r[0].isdigit())
+        mx = [int(r[1]) for r in rows if r[1].isdigit()]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "", 1).isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.strip().lower() == "active"})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None, "reasons": reasons,
+                "samples": len(rows)}
 
 
 def measured_peak():
@@ -247,14 +258,17 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.12)  # let the first samples arrive; they are filtered to the timed window below
+    t_begin = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     ctx.colorize_clip(dev_L[Wm:Wm + K], TEMPERATURE, out=dev_out)  # K frames, recurrence of test.py:96 on the device
     e1.record()
     barrier()
+    t_end = time.perf_counter()
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count(True)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
 
     # ---------------- leg 2: end to end through the clip API with host buffers ----------------
     host_out = torch.empty(K, 2, H, W).pin_memory()
