@@ -1233,6 +1233,23 @@ extern "C" int dvc_colorize_clip(dvc_ctx* c, const float* L_in, int F, int H, in
   return DVC_OK;
 }
 
+// ---- pre / post-processing around the nets -----------------------------------------
+extern "C" int dvc_resize_half(dvc_ctx* c, const float* dev_src, int planes, int H, int W, float* dev_dst, void* stream) {
+  if (!c || !dev_src || !dev_dst || planes < 1) return c ? fail(c, DVC_ERR_ARG, "resize_half: bad argument") : DVC_ERR_ARG;
+  if (H < 2 || W < 2 || (H & 1) || (W & 1)) return fail(c, DVC_ERR_SHAPE, "resize_half: H and W must be even");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  launch_resize_half(dev_src, dev_dst, planes, H, W, (cudaStream_t)stream);
+  return check_launch(c, "resize_half");
+}
+
+extern "C" int dvc_upsample2_scaled(dvc_ctx* c, const float* dev_src, int planes, int h, int w, float scale, float* dev_dst,
+                                    void* stream) {
+  if (!c || !dev_src || !dev_dst || planes < 1 || h < 1 || w < 1) return c ? fail(c, DVC_ERR_ARG, "upsample2: bad argument") : DVC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  launch_upsample2(dev_src, dev_dst, planes, h, w, scale, (cudaStream_t)stream);
+  return check_launch(c, "upsample2");
+}
+
 // ---- exemplar operands for the NCCL broadcast -----------------------------------------------------
 extern "C" int64_t dvc_exemplar_pack_size(const dvc_ctx*, int H, int W) {
   const int64_t N = (int64_t)(H / 4) * (W / 4);

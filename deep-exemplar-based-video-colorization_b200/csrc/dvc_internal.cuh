@@ -126,6 +126,10 @@ void launch_corr_simt(const CorrParams& p, cudaStream_t s);
 // [B][C][N] -> [B][N][C] and back (the C ABI of the stand-alone correlation entry is channel-major)
 void launch_transpose_cn(const float* src, float* dst, int B, int C, int N, cudaStream_t s);
 
+// pre / post-processing around the nets (test.py:58,71 and 100-102)
+void launch_resize_half(const float* src, float* dst, int planes, int H, int W, cudaStream_t s);
+void launch_upsample2(const float* src, float* dst, int planes, int h, int w, float scale, cudaStream_t s);
+
 int64_t launch_counter_add(int64_t n);  // global launch counter (introspection)
 
 }  // namespace dvc

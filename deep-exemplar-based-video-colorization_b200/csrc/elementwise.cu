@@ -425,6 +425,49 @@ __global__ void __launch_bounds__(256) transpose_cn_kernel(const float* __restri
     if (c0 + r < Cc && r0 + tx < R) dst[((size_t)b * Cc + c0 + r) * R + r0 + tx] = t[tx][r];
 }
 
+// F.interpolate(x, scale_factor=0.5, mode="bilinear") (test.py:58,71) for even sizes: the sample point of output
+// (i, j) is source (2i + 0.5, 2j + 0.5), i.e. the mean of a 2x2 block with weights 0.5 * 0.5.
+__global__ void __launch_bounds__(256) resize_half_kernel(const float* __restrict__ src, float* __restrict__ dst, int planes,
+                                                          int H, int W) {
+  const int h = H / 2, w = W / 2;
+  const long total = (long)planes * h * w;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % w);
+    const long t = idx / w;
+    const int i = (int)(t % h);
+    const long pl = t / h;
+    const float* sp = src + (pl * H + 2 * i) * W + 2 * j;
+    const float2 a = __ldg(reinterpret_cast<const float2*>(sp)), b = __ldg(reinterpret_cast<const float2*>(sp + W));
+    // torch: lambda = 0.5 on both axes: (a0*0.5 + a1*0.5) * 0.5 + (b0*0.5 + b1*0.5) * 0.5, rows first
+    dst[idx] = 0.5f * (0.5f * a.x + 0.5f * a.y) + 0.5f * (0.5f * b.x + 0.5f * b.y);
+  }
+}
+
+// F.interpolate(x, scale_factor=2, mode="bilinear") * scale (test.py:100-102, align_corners=False): output I samples
+// source I/2 - 0.25, clamped at the borders -> weights (0.25, 0.75) / (0.75, 0.25) on neighbouring source pixels.
+__global__ void __launch_bounds__(256) upsample2_kernel(const float* __restrict__ src, float* __restrict__ dst, int planes,
+                                                        int h, int w, float scale) {
+  const int H = 2 * h, W = 2 * w;
+  const long total = (long)planes * H * W;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int J = (int)(idx % W);
+    const long t = idx / W;
+    const int I = (int)(t % H);
+    const long pl = t / H;
+    // source index and weight like torch's area_pixel_compute_source_index (negative coordinates clamp to 0)
+    float sy = (I + 0.5f) * 0.5f - 0.5f, sx = (J + 0.5f) * 0.5f - 0.5f;
+    sy = sy < 0.f ? 0.f : sy, sx = sx < 0.f ? 0.f : sx;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = sy - y0, lx = sx - x0;
+    const float* sp = src + pl * h * w;
+    const float v00 = __ldg(sp + (long)y0 * w + x0), v01 = __ldg(sp + (long)y0 * w + x1);
+    const float v10 = __ldg(sp + (long)y1 * w + x0), v11 = __ldg(sp + (long)y1 * w + x1);
+    const float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    dst[idx] = v * scale;
+  }
+}
+
 inline int grid_for(long total, int threads, int cap = 148 * 16) {
   long g = (total + threads - 1) / threads;
   if (g > cap) g = cap;
@@ -506,6 +549,16 @@ void launch_final_ab(const float* x, int H, int W, int P, int C, const float* w,
 void launch_make_last(const float* IA_l, const float* ab, float* last, int B, int H, int W, cudaStream_t s) {
   dim3 grid(grid_for((long)H * W, 256), B);
   make_last_kernel<<<grid, 256, 0, s>>>(IA_l, ab, last, H * W);
+  launch_counter_add(1);
+}
+
+void launch_resize_half(const float* src, float* dst, int planes, int H, int W, cudaStream_t s) {
+  resize_half_kernel<<<grid_for((long)planes * (H / 2) * (W / 2), 256), 256, 0, s>>>(src, dst, planes, H, W);
+  launch_counter_add(1);
+}
+
+void launch_upsample2(const float* src, float* dst, int planes, int h, int w, float scale, cudaStream_t s) {
+  upsample2_kernel<<<grid_for((long)planes * 4 * h * w, 256), 256, 0, s>>>(src, dst, planes, h, w, scale);
   launch_counter_add(1);
 }
 
