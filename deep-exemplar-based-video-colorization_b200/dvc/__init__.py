@@ -22,6 +22,7 @@ EXPORTED = [
     "dvc_set_exemplar", "dvc_colorize_frames", "dvc_colorize_clip", "dvc_exemplar_pack_size",
     "dvc_exemplar_export", "dvc_exemplar_import", "dvc_launch_count", "dvc_profile_corr", "dvc_corr_mean_ms",
     "dvc_debug_set_flag", "dvc_debug_get_buffer", "dvc_profile_conv", "dvc_conv_profile",
+    "dvc_resize_half", "dvc_upsample2_scaled",
 ]
 
 _lib = None
@@ -72,6 +73,8 @@ def load_library():
         lib.dvc_profile_corr.argtypes = [c_void, c_int]
         lib.dvc_corr_mean_ms.argtypes = [c_void, c_int]
         lib.dvc_corr_mean_ms.restype = ctypes.c_double
+        lib.dvc_resize_half.argtypes = [c_void, c_void, c_int, c_int, c_int, c_void, c_void]
+        lib.dvc_upsample2_scaled.argtypes = [c_void, c_void, c_int, c_int, c_int, c_float, c_void, c_void]
         lib.dvc_profile_conv.argtypes = [c_void, c_int]
         lib.dvc_conv_profile.argtypes = [c_void, c_int, c_int, P(ctypes.c_double), P(ctypes.c_double)]
         lib.dvc_debug_set_flag.argtypes = [c_void, ctypes.c_char_p, c_int]
@@ -250,6 +253,24 @@ class Context:
         rc = self.lib.dvc_colorize_clip(self.h, _ptr(L), F_, H, W, float(temperature), _ptr(fl), _ptr(out),
                                         _stream(self.device))
         self._check(rc, "dvc_colorize_clip")
+        return out
+
+    # ---- pre / post-processing around the nets (test.py:58,71,100-102) ----------------------------------
+    def resize_half(self, x):
+        """F.interpolate(x, scale_factor=0.5, mode="bilinear") for a CUDA [B,C,H,W] tensor with even H, W."""
+        x = _dev_f32(x, "resize_half input")
+        B, C, H, W = x.shape
+        out = torch.empty(B, C, H // 2, W // 2, device=x.device, dtype=torch.float32)
+        self._check(self.lib.dvc_resize_half(self.h, _ptr(x), B * C, H, W, _ptr(out), _stream(x.device)), "dvc_resize_half")
+        return out
+
+    def upsample2_scaled(self, x, scale=1.25):
+        """F.interpolate(x, scale_factor=2, mode="bilinear") * scale for a CUDA [B,C,h,w] tensor."""
+        x = _dev_f32(x, "upsample2 input")
+        B, C, h, w = x.shape
+        out = torch.empty(B, C, 2 * h, 2 * w, device=x.device, dtype=torch.float32)
+        self._check(self.lib.dvc_upsample2_scaled(self.h, _ptr(x), B * C, h, w, float(scale), _ptr(out), _stream(x.device)),
+                    "dvc_upsample2_scaled")
         return out
 
     # ---- multi-GPU: exemplar operands as one flat buffer (broadcast with torch.distributed / NCCL) ----

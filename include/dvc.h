@@ -120,6 +120,16 @@ int dvc_colorize_frames(dvc_ctx* ctx, const float* dev_IA_l, const float* dev_IA
 int dvc_colorize_clip(dvc_ctx* ctx, const float* host_L, int F, int H, int W, float temperature,
                       const float* host_first_last_lab, float* host_ab, void* stream);
 
+/* ---- pre / post-processing around the nets ------------------------------ */
+
+/* F.interpolate(x, scale_factor=0.5, mode="bilinear") -- test.py:58,71.  dev_src [planes,H,W] (H, W even) ->
+ * dev_dst [planes,H/2,W/2]; planes = B*C of a contiguous NCHW tensor. */
+int dvc_resize_half(dvc_ctx* ctx, const float* dev_src, int planes, int H, int W, float* dev_dst, void* stream);
+/* F.interpolate(x, scale_factor=2, mode="bilinear") * scale -- test.py:100-102 (scale = 1.25 there).
+ * dev_src [planes,h,w] -> dev_dst [planes,2h,2w]. */
+int dvc_upsample2_scaled(dvc_ctx* ctx, const float* dev_src, int planes, int h, int w, float scale, float* dev_dst,
+                         void* stream);
+
 /* ---- multi-GPU: exemplar operands travel once per clip ----------------------- */
 
 /* Size in floats of the packed exemplar operands (phi_hat planes + pooled Lab) for an HxW exemplar. */

@@ -306,6 +306,16 @@ def colorize_clip(sds, frames_lab, IB_lab, temperature=1e-10, row_chunk=4096):
     return torch.cat(outs, 0)
 
 
+def resize_half(x):
+    """test.py:58,71: F.interpolate(x, scale_factor=0.5, mode="bilinear")."""
+    return F.interpolate(x, scale_factor=0.5, mode="bilinear")
+
+
+def upsample2_scaled(ab, scale=1.25):
+    """test.py:100-102: F.interpolate(ab, scale_factor=2, mode="bilinear") * 1.25."""
+    return F.interpolate(ab, scale_factor=2, mode="bilinear") * scale
+
+
 def legal_shape(H, W):
     """Shapes the reference's full path accepts: H % 8 == 0 and W % 16 == 0."""
     return H % 8 == 0 and W % 16 == 0 and H >= 16 and W >= 16
