@@ -43,9 +43,9 @@ typedef enum dvc_status {
 typedef enum dvc_net { DVC_NET_VGG = 0, DVC_NET_WARP = 1, DVC_NET_COLOR = 2 } dvc_net;
 
 /* Arithmetic used by the GEMM-shaped kernels (convolutions, correlation).
- *   DVC_MATH_FP32    CUDA-core fp32 FMA (exact fp32 products; the parity reference on the GPU)
- *   DVC_MATH_TF32X3  tcgen05 kind::tf32 on hi/lo split operands, 3 MMAs per product, fp32 TMEM
- *                    accumulation (fp32-class accuracy; the default once validated)
+ *   DVC_MATH_FP32    CUDA-core fp32 FMA (exact fp32 products, two-level accumulation; the on-GPU fp32 reference)
+ *   DVC_MATH_TF32X3  tcgen05 kind::tf32 on hi/lo split operands, 3 MMAs per product, TMEM chunk sums promoted
+ *                    to fp32 registers (fp32-class accuracy; THE DEFAULT for convolutions and correlation)
  *   DVC_MATH_BF16X3  tcgen05 kind::f16 (bf16) on hi/lo split operands (correlation only; fast mode)
  */
 typedef enum dvc_math { DVC_MATH_FP32 = 0, DVC_MATH_TF32X3 = 1, DVC_MATH_BF16X3 = 2 } dvc_math;
