@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    // The whole warp runs the loop convergently (so that addresses / coordinates are provably warp-uniform and live
+    // in uniform registers); one elected lane issues the instructions.
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int work = item0; work < total_work; work += item_stride) {
@@ -130,8 +132,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         for (int k = k_lo; k < k_hi; ++k) {
           const int tap = k / kbs, kb = k - tap * kbs;
           const int off = p.tap_off[tap];
-          {
-            tc::mbar_wait(&empty[stage], phase ^ 1);
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          if (tc::elect_one()) {
             uint8_t* st = smem + stage * C::STAGE_BYTES;
             tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
             tc::tma_load_2d(st, &tmXh, &full[stage], kb * KE, m0 + off);
@@ -145,14 +147,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
               tc::tma_load_2d_mc(st + 2 * A_BYTES + C::B_BYTES + hrow * KBY, &tmWl, &full[stage], kb * KE,
                                  tap * p.CoutPad + n0 + hrow, 3);
             }
-            if (++stage == C::STAGES) stage = 0, phase ^= 1;
           }
+          __syncwarp();
+          if (++stage == C::STAGES) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (warp-convergent loop, one elected lane issues) =================
+    {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk_id = 0;  // global chunk counter: TMEM buffer = chunk_id % NBUF
@@ -172,18 +175,21 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             auto mkdesc = [](uint32_t a) { return KBY == 128 ? tc::umma_desc_k128(a) : tc::umma_desc_k64(a); };
             const uint64_t dXh = mkdesc(sa), dXl = mkdesc(sa + A_BYTES);
             const uint64_t dWh = mkdesc(sa + 2 * A_BYTES), dWl = mkdesc(sa + 2 * A_BYTES + C::B_BYTES);
+            if (tc::elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < KBY / 32; ++kk) {
-              const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-              tc::umma_ss<true>(d, dXl + adv, dWh + adv, IDESC, (k > ch * kc || kk) ? 1u : 0u);
-              tc::umma_ss<true>(d, dXh + adv, dWl + adv, IDESC, 1u);
-              tc::umma_ss<true>(d, dXh + adv, dWh + adv, IDESC, 1u);
+              for (int kk = 0; kk < KBY / 32; ++kk) {
+                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                tc::umma_ss<true>(d, dXl + adv, dWh + adv, IDESC, (k > ch * kc || kk) ? 1u : 0u);
+                tc::umma_ss<true>(d, dXh + adv, dWl + adv, IDESC, 1u);
+                tc::umma_ss<true>(d, dXh + adv, dWh + adv, IDESC, 1u);
+              }
+              if (CL == 1)
+                tc::umma_commit(&empty[stage]);
+              else
+                tc::umma_commit_mc(&empty[stage], 3);
+              if (k == k_end - 1) tc::umma_commit(&tfull[buf]);
             }
-            if (CL == 1)
-              tc::umma_commit(&empty[stage]);
-            else
-              tc::umma_commit_mc(&empty[stage], 3);
-            if (k == k_end - 1) tc::umma_commit(&tfull[buf]);
+            __syncwarp();
             if (++stage == C::STAGES) stage = 0, phase ^= 1;
           }
         }

@@ -163,27 +163,30 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer (warp-convergent loop, one elected lane issues) =================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int col0 = bphi * p.NB + (t0 + t) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* st = smem + stage * STAGE_BYTES;
-          tc::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          tc::tma_load_2d(st, &tmAh, &full[stage], kb * KB, b * p.NA + m0);
-          tc::tma_load_2d(st + A_BYTES, &tmAl, &full[stage], kb * KB, b * p.NA + m0);
-          tc::tma_load_2d(st + 2 * A_BYTES, &tmBh, &full[stage], kb * KB, col0);
-          tc::tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmBl, &full[stage], kb * KB, col0);
+          if (tc::elect_one()) {
+            uint8_t* st = smem + stage * STAGE_BYTES;
+            tc::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+            tc::tma_load_2d(st, &tmAh, &full[stage], kb * KB, b * p.NA + m0);
+            tc::tma_load_2d(st + A_BYTES, &tmAl, &full[stage], kb * KB, b * p.NA + m0);
+            tc::tma_load_2d(st + 2 * A_BYTES, &tmBh, &full[stage], kb * KB, col0);
+            tc::tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmBl, &full[stage], kb * KB, col0);
+          }
+          __syncwarp();
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (warp-convergent loop, one elected lane issues) =================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
@@ -198,16 +201,19 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           const uint32_t sa = tc::smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t dAh = tc::umma_desc_k128(sa), dAl = tc::umma_desc_k128(sa + A_BYTES);
           const uint64_t dBh = tc::umma_desc_k128(sa + 2 * A_BYTES), dBl = tc::umma_desc_k128(sa + 2 * A_BYTES + B_BYTES);
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 128 / UMMA_K_BYTES; ++kk) {
-            const uint64_t adv = (uint64_t)((kk * UMMA_K_BYTES) >> 4);  // start-address field is in 16-byte units
-            // small cross terms first, the dominant hi.hi term last
-            tc::umma_ss<TF32>(d, dAl + adv, dBh + adv, IDESC, (kb | kk) ? 1u : 0u);
-            tc::umma_ss<TF32>(d, dAh + adv, dBl + adv, IDESC, 1u);
-            tc::umma_ss<TF32>(d, dAh + adv, dBh + adv, IDESC, 1u);
+            for (int kk = 0; kk < 128 / UMMA_K_BYTES; ++kk) {
+              const uint64_t adv = (uint64_t)((kk * UMMA_K_BYTES) >> 4);  // start-address field is in 16-byte units
+              // small cross terms first, the dominant hi.hi term last
+              tc::umma_ss<TF32>(d, dAl + adv, dBh + adv, IDESC, (kb | kk) ? 1u : 0u);
+              tc::umma_ss<TF32>(d, dAh + adv, dBl + adv, IDESC, 1u);
+              tc::umma_ss<TF32>(d, dAh + adv, dBh + adv, IDESC, 1u);
+            }
+            tc::umma_commit(&empty[stage]);  // smem stage reusable once these MMAs have read it
+            if (kb == nkb - 1) tc::umma_commit(&tfull[buf]);
           }
-          tc::umma_commit(&empty[stage]);  // smem stage reusable once these MMAs have read it
-          if (kb == nkb - 1) tc::umma_commit(&tfull[buf]);
+          __syncwarp();
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
