@@ -103,6 +103,15 @@ class ClockSampler:
                 "samples": len(rows)}
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes of one launch from the committed ncu --set full capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_r1_traffic.json")
+    try:
+        return json.load(open(path))[kernel]["bytes"]
+    except Exception:
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -341,7 +350,8 @@ def main():
         # dominant kernel by device time (profiles/launches_r1.md: conv_tc_kernel<256> ~ 50 % of a frame)
         "roofline": {"kernel": "conv_tc_kernel<256> (3xTF32 flat shifted GEMM, all launches of a frame)", "bound": "tensor",
                      "achieved": conv_ach, "peak": peak, "unit": "TFLOP/s", "frac": conv_ach / peak if peak else None,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": ncu_traffic("conv_tc_kernel<256>"), "peak_source": peak_src,
+                     "traffic_note": "DRAM bytes of ONE profiled launch (a 1/8-resolution 512->512 layer), profiles/ncu_r1_conv256.md",
                      "launches_per_frame": n256 / KP, "ms_per_frame": ms256 / KP,
                      "note": "sum of algorithmic FLOPs (2 x output pixels x 9 x Cin x Cout) / sum of CUDA-event launch times, "
                              "single-stream pass of %d frames inside this run; the 3 MMA passes of the operand split are not "
@@ -350,7 +360,7 @@ def main():
         # the north-star kernel (BASELINE metric: correlation tensor-pipe fraction)
         "roofline_corr": {"kernel": f"corr_tc_kernel ({args.corr_math}) incl. operand split + merge", "bound": "tensor",
                           "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                          "traffic": None, "peak_source": peak_src, "launch_ms": corr_ms,
+                          "traffic": ncu_traffic("corr_tc_kernel"), "peak_source": peak_src, "launch_ms": corr_ms,
                           "note": "algorithmic 2*N*N*(256+3) FLOP per launch; ceiling 1/6 (tf32x3) or 1/3 (bf16x3) of the bf16 peak"},
         "serial_ms_per_frame": ms_serial,
         "conv_tc_all": {"launches_per_frame": conv_all[0] / KP, "ms_per_frame": conv_all[1] / KP,
