@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--corr-math", default=os.environ.get("DVC_CORR_MATH", "tf32x3"), choices=["fp32", "tf32x3", "bf16x3"])
+    ap.add_argument("--corr-math", default=os.environ.get("DVC_CORR_MATH", "tf32x3"), choices=["fp32", "tf32x3", "bf16x3", "fp16x3"])
     ap.add_argument("--conv-math", default=os.environ.get("DVC_CONV_MATH", "tf32x3"), choices=["fp32", "tf32x3"])
     ap.add_argument("--tc-kc", type=int, default=int(os.environ.get("DVC_TC_KC", "1")),
                     help="k-blocks summed in TMEM before promotion to fp32 registers (1 = parity mode)")
@@ -230,7 +230,7 @@ def main():
     ctx = dvc.get_context(local)
     for net, key in ((dvc.NET_VGG, "vgg"), (dvc.NET_WARP, "warp"), (dvc.NET_COLOR, "color")):
         ctx.set_weights(net, make_state_dict(key, seed=0))
-    corr_mode = {"fp32": dvc.MATH_FP32, "tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3}[args.corr_math]
+    corr_mode = {"fp32": dvc.MATH_FP32, "tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3, "fp16x3": dvc.MATH_FP16X3}[args.corr_math]
     ctx.set_math(conv=dvc.MATH_TF32X3 if args.conv_math == "tf32x3" else dvc.MATH_FP32, corr=corr_mode)
     ctx.debug_flag("tc_kc", args.tc_kc)
     ctx.debug_flag("tc_cluster", args.tc_cluster)

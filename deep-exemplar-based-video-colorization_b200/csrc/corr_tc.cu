@@ -5,7 +5,10 @@
 // fp32-class accuracy from low-precision MMAs by operand splitting: x = hi + lo with hi, lo exactly
 // representable in the MMA input type (tf32: 2 x 11 significant bits; bf16: 2 x 8), and
 //   f ~= hi_a.hi_b + hi_a.lo_b + lo_a.hi_b           (lo.lo dropped: 2^-22 resp. 2^-16 relative)
-// all three accumulated into the same fp32 TMEM tile.  DVC_MATH_TF32X3 is the parity mode (|df| ~ 1e-7,
+// all three accumulated into the same fp32 TMEM tile.  A third format, FP16X3, splits x * 2^14 into two fp16 planes
+// (theta_hat / phi_hat are unit vectors, so the fixed power-of-two scale is exact and cannot overflow): the same
+// 2 x 11 significant bits as tf32 at twice the MMA rate and half the operand bytes; scores come out times 2^28.
+// DVC_MATH_TF32X3 is the parity mode (|df| ~ 1e-7,
 // fp32 class), DVC_MATH_BF16X3 the fast mode (|df| ~ 2e-6).
 //
 // Kernel structure (one CTA = 128 query rows x a range of 256-column tiles of reference positions):
@@ -21,6 +24,7 @@
 // kernel combines the per-split row statistics.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cudaTypedefs.h>
 #include <math.h>
 
@@ -76,6 +80,7 @@ struct TcParams {
   int NA, NB, B, Bphi, C;
   int tiles_per_split;
   float sc;  // log2(e) / T
+  float out_scale;  // scores in TMEM are true scores / out_scale (2^-28 for pre-scaled fp16 operands, else 1)
   const float4* V;
   SplitOut* part;  // [nsplit][B*NA]
 };
@@ -87,13 +92,27 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
-template <bool TF32>
+template <int FMT>
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ src, void* __restrict__ hi,
                                                            void* __restrict__ lo, size_t n4) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
     const float x[4] = {v.x, v.y, v.z, v.w};
-    if constexpr (TF32) {
+    if constexpr (FMT == 2) {
+      __half h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xs = x[j] * 16384.0f;
+        h[j] = __float2half_rn(xs);
+        l[j] = __float2half_rn(xs - __half2float(h[j]));
+      }
+      reinterpret_cast<uint2*>(hi)[i] = make_uint2(
+          (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+          (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+      reinterpret_cast<uint2*>(lo)[i] = make_uint2(
+          (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16),
+          (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16));
+    } else if constexpr (FMT == 0) {
       float h[4], l[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) h[j] = tf32_rna(x[j]), l[j] = tf32_rna(x[j] - h[j]);
@@ -117,13 +136,14 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 }
 
 // ---- main kernel ---------------------------------------------------------------------------------------
-template <bool TF32, bool SOFTMAX>
+template <int FMT, bool SOFTMAX>
 __global__ void __launch_bounds__(NTHREADS, 1)
     corr_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
+  constexpr bool TF32 = (FMT == 0);
   constexpr int KB = TF32 ? 32 : 64;       // K elements per 128-byte k-block
   constexpr int UMMA_K_BYTES = 32;         // one MMA consumes 32 bytes of K (8 tf32 / 16 bf16)
-  constexpr uint32_t IDESC = tc::umma_idesc(TF32 ? 2u : 1u, BM, BN);
+  constexpr uint32_t IDESC = tc::umma_idesc(FMT == 0 ? 2u : (FMT == 1 ? 1u : 0u), BM, BN);  // tf32 / bf16 / f16
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -223,6 +243,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row_local = q * 32 + lane;
     const int row = m0 + row_local;
+    const float sck = p.sc * p.out_scale;  // exponent scale in units of the (possibly pre-scaled) TMEM scores
     float run_m = -INFINITY, run_s = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
     int run_i = 0;
     const float4* __restrict__ Vg = p.V + (size_t)bphi * p.NB;
@@ -259,14 +280,14 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           }
         } else {
           if (cm > run_m) {
-            const float sc_old = (run_m == -INFINITY) ? 0.f : exp2f((run_m - cm) * p.sc);
+            const float sc_old = (run_m == -INFINITY) ? 0.f : exp2f((run_m - cm) * sck);
             run_s *= sc_old, a0 *= sc_old, a1 *= sc_old, a2 *= sc_old;
             run_m = cm;
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (i < nvalid) {
-              const float e = exp2f((__uint_as_float(r[i]) - run_m) * p.sc);
+              const float e = exp2f((__uint_as_float(r[i]) - run_m) * sck);
               const float4 v = __ldg(Vg + cb + i);  // same address across the warp: one broadcast load
               run_s += e;
               a0 = fmaf(e, v.x, a0), a1 = fmaf(e, v.y, a1), a2 = fmaf(e, v.z, a2);
@@ -280,7 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
     if (row < p.NA) {
       SplitOut o;
-      o.m = run_m, o.s = run_s, o.a0 = a0, o.a1 = a1, o.a2 = a2, o.idx = run_i, o.pad0 = o.pad1 = 0.f;
+      o.m = run_m * p.out_scale, o.s = run_s, o.a0 = a0, o.a1 = a1, o.a2 = a2, o.idx = run_i, o.pad0 = o.pad1 = 0.f;
       p.part[((size_t)blockIdx.z * p.B + b) * p.NA + row] = o;
     }
   }
@@ -348,17 +369,17 @@ int ws_get(int i, size_t bytes, void** out) {
   return 0;
 }
 
-template <bool TF32, bool SOFTMAX>
+template <int FMT, bool SOFTMAX>
 int launch_main(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl,
                 const TcParams& tp, dim3 grid, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(corr_tc_kernel<TF32, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+    if (cudaFuncSetAttribute(corr_tc_kernel<FMT, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
         cudaSuccess)
       return -1;
     attr = true;
   }
-  corr_tc_kernel<TF32, SOFTMAX><<<grid, NTHREADS, SMEM_BYTES, s>>>(mAh, mAl, mBh, mBl, tp);
+  corr_tc_kernel<FMT, SOFTMAX><<<grid, NTHREADS, SMEM_BYTES, s>>>(mAh, mAl, mBh, mBl, tp);
   return 0;
 }
 
@@ -370,6 +391,7 @@ int launch_corr_tc(const CorrParams& p, int math, cudaStream_t s, std::string* e
     return -1;
   };
   const bool tf32 = (math == 1);
+  const int fmt = math == 1 ? 0 : (math == 2 ? 1 : 2);  // DVC_MATH_TF32X3 / BF16X3 / FP16X3
   if (p.C != 256) return fail("C must be 256");
   const int eb = tf32 ? 4 : 2;
   const size_t ea = (size_t)p.B * p.NA * p.C, ephi = (size_t)p.Bphi * p.NB * p.C;
@@ -399,16 +421,17 @@ int launch_corr_tc(const CorrParams& p, int math, cudaStream_t s, std::string* e
   if (ws_get(4, (size_t)nsplit * p.B * p.NA * sizeof(SplitOut), &part)) return fail("workspace allocation failed");
 
   const int grid1 = 148 * 8;
-  if (tf32)
-    split_planes_kernel<true><<<grid1, 256, 0, s>>>(p.theta, Ah, Al, ea / 4);
-  else
-    split_planes_kernel<false><<<grid1, 256, 0, s>>>(p.theta, Ah, Al, ea / 4);
-  launch_counter_add(1);
-  if (tf32)
-    split_planes_kernel<true><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
-  else
-    split_planes_kernel<false><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
-  launch_counter_add(1);
+  if (fmt == 0) {
+    split_planes_kernel<0><<<grid1, 256, 0, s>>>(p.theta, Ah, Al, ea / 4);
+    split_planes_kernel<0><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
+  } else if (fmt == 1) {
+    split_planes_kernel<1><<<grid1, 256, 0, s>>>(p.theta, Ah, Al, ea / 4);
+    split_planes_kernel<1><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
+  } else {
+    split_planes_kernel<2><<<grid1, 256, 0, s>>>(p.theta, Ah, Al, ea / 4);
+    split_planes_kernel<2><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
+  }
+  launch_counter_add(2);
 
   CUtensorMap mAh, mAl, mBh, mBl;
   const uint32_t boxk = tf32 ? 32 : 64;
@@ -420,15 +443,18 @@ int launch_corr_tc(const CorrParams& p, int math, cudaStream_t s, std::string* e
   TcParams tp;
   tp.NA = p.NA, tp.NB = p.NB, tp.B = p.B, tp.Bphi = p.Bphi, tp.C = p.C, tp.tiles_per_split = tps;
   tp.sc = 1.4426950408889634f / p.temperature;
+  tp.out_scale = fmt == 2 ? 3.725290298461914e-09f /* 2^-28 */ : 1.0f;
   tp.V = reinterpret_cast<const float4*>(p.V);
   tp.part = reinterpret_cast<SplitOut*>(part);
   dim3 grid(row_blocks, p.B, nsplit);
   const bool softmax = !(p.temperature <= 2e-10f);
   int rc;
-  if (tf32)
-    rc = softmax ? launch_main<true, true>(mAh, mAl, mBh, mBl, tp, grid, s) : launch_main<true, false>(mAh, mAl, mBh, mBl, tp, grid, s);
+  if (fmt == 0)
+    rc = softmax ? launch_main<0, true>(mAh, mAl, mBh, mBl, tp, grid, s) : launch_main<0, false>(mAh, mAl, mBh, mBl, tp, grid, s);
+  else if (fmt == 1)
+    rc = softmax ? launch_main<1, true>(mAh, mAl, mBh, mBl, tp, grid, s) : launch_main<1, false>(mAh, mAl, mBh, mBl, tp, grid, s);
   else
-    rc = softmax ? launch_main<false, true>(mAh, mAl, mBh, mBl, tp, grid, s) : launch_main<false, false>(mAh, mAl, mBh, mBl, tp, grid, s);
+    rc = softmax ? launch_main<2, true>(mAh, mAl, mBh, mBl, tp, grid, s) : launch_main<2, false>(mAh, mAl, mBh, mBl, tp, grid, s);
   if (rc) return fail("cudaFuncSetAttribute(max dynamic smem) failed");
   launch_counter_add(1);
   const int rows = p.B * p.NA;

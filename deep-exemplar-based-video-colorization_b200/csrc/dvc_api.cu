@@ -844,7 +844,7 @@ extern "C" int dvc_set_math(dvc_ctx* c, int conv_math, int corr_math) {
   if (!c) return DVC_ERR_ARG;
   if (conv_math != DVC_MATH_FP32 && conv_math != DVC_MATH_TF32X3) return fail(c, DVC_ERR_ARG, "conv math must be DVC_MATH_FP32 or DVC_MATH_TF32X3");
   if (conv_math != c->conv_math) c->ex_valid = false, c->warp_cache_valid = false;
-  if (corr_math != DVC_MATH_FP32 && corr_math != DVC_MATH_TF32X3 && corr_math != DVC_MATH_BF16X3)
+  if (corr_math != DVC_MATH_FP32 && corr_math != DVC_MATH_TF32X3 && corr_math != DVC_MATH_BF16X3 && corr_math != DVC_MATH_FP16X3)
     return fail(c, DVC_ERR_ARG, "unknown corr math");
   c->conv_math = conv_math, c->corr_math = corr_math;
   return DVC_OK;

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdvc.so")
 
 NET_VGG, NET_WARP, NET_COLOR = 0, 1, 2
-MATH_FP32, MATH_TF32X3, MATH_BF16X3 = 0, 1, 2
+MATH_FP32, MATH_TF32X3, MATH_BF16X3, MATH_FP16X3 = 0, 1, 2, 3
 
 EXPORTED = [
     "dvc_create", "dvc_destroy", "dvc_last_error", "dvc_version", "dvc_set_math", "dvc_set_weight",

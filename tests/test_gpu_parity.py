@@ -78,12 +78,12 @@ def test_vgg19_all_keys_and_no_preprocess(ctx, conv_math, sds):
 
 
 # ------------------------------------------------------------------------------------------ K7
-@pytest.fixture(params=["fp32", "tf32x3", "bf16x3"])
+@pytest.fixture(params=["fp32", "tf32x3", "bf16x3", "fp16x3"])
 def corr_math(request, ctx):
     """Run the correlation tests on the CUDA-core kernel and on both tcgen05 operand-split modes."""
     import dvc
 
-    mode = {"fp32": dvc.MATH_FP32, "tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3}[request.param]
+    mode = {"fp32": dvc.MATH_FP32, "tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3, "fp16x3": dvc.MATH_FP16X3}[request.param]
     ctx.set_math(conv=dvc.MATH_TF32X3, corr=mode)
     yield request.param
     ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)

@@ -5,9 +5,9 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "deep-exemplar-b
 import torch
 import dvc
 ctx = dvc.get_context(0)
-names = {dvc.MATH_TF32X3: "tf32x3", dvc.MATH_BF16X3: "bf16x3"}
+names = {dvc.MATH_TF32X3: "tf32x3", dvc.MATH_BF16X3: "bf16x3", dvc.MATH_FP16X3: "fp16x3"}
 only = sys.argv[1:]
-for math in (dvc.MATH_TF32X3, dvc.MATH_BF16X3):
+for math in (dvc.MATH_TF32X3, dvc.MATH_BF16X3, dvc.MATH_FP16X3):
     if only and names[math] not in only: continue
     for (NA, NB) in ((128, 256), (300, 517), (1000, 130), (5184, 5184), (25920, 25920)):
         g = torch.Generator().manual_seed(NA + NB)
