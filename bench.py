@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--corr-math", default=os.environ.get("DVC_CORR_MATH", "tf32x3"), choices=["fp32", "tf32x3", "bf16x3", "fp16x3"])
+    ap.add_argument("--corr-math", default=os.environ.get("DVC_CORR_MATH", "fp16x3"), choices=["fp32", "tf32x3", "bf16x3", "fp16x3"])
     ap.add_argument("--conv-math", default=os.environ.get("DVC_CONV_MATH", "tf32x3"), choices=["fp32", "tf32x3"])
     ap.add_argument("--tc-kc", type=int, default=int(os.environ.get("DVC_TC_KC", "1")),
                     help="k-blocks summed in TMEM before promotion to fp32 registers (1 = parity mode)")
@@ -361,7 +361,8 @@ def main():
         "roofline_corr": {"kernel": f"corr_tc_kernel ({args.corr_math}) incl. operand split + merge", "bound": "tensor",
                           "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                           "traffic": ncu_traffic("corr_tc_kernel"), "peak_source": peak_src, "launch_ms": corr_ms,
-                          "note": "algorithmic 2*N*N*(256+3) FLOP per launch; ceiling 1/6 (tf32x3) or 1/3 (bf16x3) of the bf16 peak"},
+                          "note": "algorithmic 2*N*N*(256+3) FLOP per launch; 3 MMA passes per product are not counted, so the ceiling is "
+                                  "1/3 (fp16x3 / bf16x3) or 1/6 (tf32x3) of the dense 16-bit peak"},
         "serial_ms_per_frame": ms_serial,
         "conv_tc_all": {"launches_per_frame": conv_all[0] / KP, "ms_per_frame": conv_all[1] / KP,
                         "tflops": conv_all[2] / (conv_all[1] * 1e-3) / 1e12 if conv_all[1] > 0 else 0.0},

@@ -124,7 +124,7 @@ class Context:
             raise DvcError(f"{what} failed ({rc}): {self.lib.dvc_last_error(self.h).decode()}")
 
     # ---- configuration / weights -------------------------------------------------------------
-    def set_math(self, conv=MATH_TF32X3, corr=MATH_TF32X3):
+    def set_math(self, conv=MATH_TF32X3, corr=MATH_FP16X3):
         self._check(self.lib.dvc_set_math(self.h, conv, corr), "dvc_set_math")
 
     def set_weights(self, net, state_dict):

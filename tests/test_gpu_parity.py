@@ -39,7 +39,7 @@ def conv_math(request, ctx):
     import dvc
 
     if request.param.startswith("tf32x3"):
-        ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
+        ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
         ctx.debug_flag("tc_cluster", 2 if request.param.endswith("cluster2") else 1)
         ctx.debug_flag("tc_kbytes", 64 if request.param.endswith("k64") else 128)
         ctx.debug_flag("tc_splits", 3 if request.param.endswith("split3") else 1)
@@ -49,7 +49,7 @@ def conv_math(request, ctx):
     ctx.debug_flag("tc_cluster", 1)
     ctx.debug_flag("tc_kbytes", 128)
     ctx.debug_flag("tc_splits", 1)
-    ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
+    ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
 
 
 # ------------------------------------------------------------------------------------------ VGG19
@@ -86,7 +86,7 @@ def corr_math(request, ctx):
     mode = {"fp32": dvc.MATH_FP32, "tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3, "fp16x3": dvc.MATH_FP16X3}[request.param]
     ctx.set_math(conv=dvc.MATH_TF32X3, corr=mode)
     yield request.param
-    ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
+    ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
 
 
 @pytest.mark.parametrize("NA,NB,T", [(96, 96, 1e-10), (300, 517, 1e-10), (300, 517, 0.01), (1000, 130, 0.005),

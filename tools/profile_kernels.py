@@ -9,7 +9,7 @@ from dvc.synth import make_lab, make_state_dict
 ctx = dvc.get_context(0)
 for net, key in ((dvc.NET_VGG, "vgg"), (dvc.NET_WARP, "warp"), (dvc.NET_COLOR, "color")):
     ctx.set_weights(net, make_state_dict(key, seed=0))
-ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3 if os.environ.get("DVC_CORR", "tf32x3") == "tf32x3" else dvc.MATH_BF16X3)
+ctx.set_math(conv=dvc.MATH_TF32X3, corr={"tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3, "fp16x3": dvc.MATH_FP16X3}[os.environ.get("DVC_CORR", "fp16x3")])
 ctx.debug_flag("tc_kc", int(os.environ.get("DVC_KC", "1")))
 H, W = 480, 864
 ctx.set_exemplar(make_lab(60, 1, H, W))
