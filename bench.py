@@ -200,6 +200,8 @@ def main():
                     help="k-blocks summed in TMEM before promotion to fp32 registers (1 = parity mode)")
     ap.add_argument("--tc-kbytes", type=int, default=int(os.environ.get("DVC_TC_KBYTES", "128")), choices=[64, 128],
                     help="K bytes per pipeline stage of the conv engine (64 = twice the stages, measured slower)")
+    ap.add_argument("--tc-f16", type=int, default=int(os.environ.get("DVC_TC_F16", "1")),
+                    help="1: convolutions with bounded inputs run 3xFP16 on scaled planes; 0: 3xTF32 everywhere")
     ap.add_argument("--tc-splits", type=int, default=int(os.environ.get("DVC_TC_SPLITS", "1")),
                     help="split-K of the conv engine: 1 off (default), 0 automatic")
     ap.add_argument("--tc-cluster", type=int, default=int(os.environ.get("DVC_TC_CLUSTER", "1")), choices=[1, 2],
@@ -236,6 +238,7 @@ def main():
     ctx.debug_flag("tc_cluster", args.tc_cluster)
     ctx.debug_flag("tc_kbytes", args.tc_kbytes)
     ctx.debug_flag("tc_splits", args.tc_splits)
+    ctx.debug_flag("tc_f16", args.tc_f16)
 
     K, Wm = args.steps, args.warmup
     # every rank owns its own contiguous segment of synthetic frames (distinct content per rank and per step)

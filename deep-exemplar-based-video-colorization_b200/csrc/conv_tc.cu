@@ -53,14 +53,17 @@ __device__ __forceinline__ float tf32_rna(float x) {
 // CL = 2: the kernel runs as 2-CTA clusters on adjacent pixel tiles of the same channel tile; each CTA fetches half
 // of every weight tile and TMA-multicasts it to both, which cuts the L2 -> SM operand traffic by a third (BN = 256)
 // to a half (BN = 64).  MMAs stay per-CTA (cta_group::1); a stage is released to both producers by a multicast commit.
-template <int BN, int CL, int KBY>
+// F16: operands are fp16 hi/lo planes of x * 2^e (e static per tensor / layer, chosen from a proven bound so that
+// nothing overflows): the same 2 x 11 significant bits as the tf32 split at twice the MMA rate, half the operand
+// bytes and half as many truncating accumulations per unit of K; the epilogue multiplies by 2^-(e_x + e_w) (exact).
+template <int BN, int CL, int KBY, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                    const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const ConvTcParams p) {
   using C = Cfg<BN, KBY>;
   constexpr int A_BYTES = C::A_BYTES;
-  constexpr int KE = KBY / 4;  // K elements per stage
-  constexpr uint32_t IDESC = tc::umma_idesc(2u, BM, BN);
+  constexpr int KE = F16 ? KBY / 2 : KBY / 4;  // K elements per stage
+  constexpr uint32_t IDESC = tc::umma_idesc(F16 ? 0u : 2u, BM, BN);
   constexpr int CPT = BN / 2;  // output channels per epilogue thread (two warps share a TMEM lane quarter)
 
   extern __shared__ uint8_t smem_raw[];
@@ -179,9 +182,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
               for (int kk = 0; kk < KBY / 32; ++kk) {
                 const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-                tc::umma_ss<true>(d, dXl + adv, dWh + adv, IDESC, (k > ch * kc || kk) ? 1u : 0u);
-                tc::umma_ss<true>(d, dXh + adv, dWl + adv, IDESC, 1u);
-                tc::umma_ss<true>(d, dXh + adv, dWh + adv, IDESC, 1u);
+                tc::umma_ss<!F16>(d, dXl + adv, dWh + adv, IDESC, (k > ch * kc || kk) ? 1u : 0u);
+                tc::umma_ss<!F16>(d, dXh + adv, dWl + adv, IDESC, 1u);
+                tc::umma_ss<!F16>(d, dXh + adv, dWh + adv, IDESC, 1u);
               }
               if (CL == 1)
                 tc::umma_commit(&empty[stage]);
@@ -304,8 +307,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + j));
-            v[j] = tot[c * 32 + j] + bv.x, v[j + 1] = tot[c * 32 + j + 1] + bv.y;
-            v[j + 2] = tot[c * 32 + j + 2] + bv.z, v[j + 3] = tot[c * 32 + j + 3] + bv.w;
+            if constexpr (F16) {
+              v[j] = fmaf(tot[c * 32 + j], p.out_scale, bv.x), v[j + 1] = fmaf(tot[c * 32 + j + 1], p.out_scale, bv.y);
+              v[j + 2] = fmaf(tot[c * 32 + j + 2], p.out_scale, bv.z), v[j + 3] = fmaf(tot[c * 32 + j + 3], p.out_scale, bv.w);
+            } else {
+              v[j] = tot[c * 32 + j] + bv.x, v[j + 1] = tot[c * 32 + j + 1] + bv.y;
+              v[j + 2] = tot[c * 32 + j + 2] + bv.z, v[j + 3] = tot[c * 32 + j + 3] + bv.w;
+            }
           }
           if (p.add && valid) {
 #pragma unroll
@@ -399,12 +407,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
 }
 
-template <int BN, int CL, int KBY>
+template <int BN, int CL, int KBY, bool F16>
 int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap& mWh, const CUtensorMap& mWl,
               const ConvTcParams& p, int num_sms, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<BN, CL, KBY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, KBY>::SMEM_BYTES) !=
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, CL, KBY, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, KBY>::SMEM_BYTES) !=
         cudaSuccess)
       return -1;
     attr = true;
@@ -419,7 +427,7 @@ int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap&
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
   cfg.attrs = at, cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, KBY>, mXh, mXl, mWh, mWl, p) == cudaSuccess ? 0 : -2;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, KBY, F16>, mXh, mXl, mWh, mWl, p) == cudaSuccess ? 0 : -2;
 }
 
 }  // namespace
@@ -435,14 +443,17 @@ static int pick_bn_for_launch(const ConvTcParams& p, int num_sms) {
   return bn;
 }
 
-int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
-                   int num_sms, cudaStream_t s, std::string* err, int* variant) {
+int launch_conv_tc(const ConvTcParams& p, const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int num_sms,
+                   cudaStream_t s, std::string* err, int* variant) {
   auto fail = [&](const char* m) {
     if (err) *err = m;
     return -1;
   };
   if (p.Cin % 32) return fail("Cin must be a multiple of 32");
-  const int KBY = p.kbytes == 64 ? 64 : 128;
+  const bool f16 = p.f16 != 0;
+  const int eb = f16 ? 2 : 4;
+  // a 128-byte row holds 32 tf32 / 64 fp16 channels; 32-channel fp16 layers use the 64-byte (SWIZZLE_64B) rows
+  const int KBY = (p.kbytes == 64 || (f16 && p.Cin % 64)) ? 64 : 128;
   if (p.kc < 1) return fail("kc must be >= 1");
   if (p.CoutPad % conv_tc_pick_bn(p.Cout)) return fail("CoutPad must be a multiple of the channel tile");
   const int BN = pick_bn_for_launch(p, num_sms);
@@ -453,7 +464,7 @@ int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, 
   {  // split-K factor: minimise rounds(S) / S over the persistent grid (2 % penalty per extra split for the hand-over)
     const int m_tiles = (p.Mtot + BM - 1) / BM;
     const int tiles = ((m_tiles + CL - 1) / CL) * CL * (p.CoutPad / BN);
-    const int kb128 = p.taps * (p.Cin / 32);               // 32-element k-blocks
+    const int kb128 = p.taps * (p.Cin / (f16 ? 64 : 32));  // 128-byte k-blocks (12 MMA accumulations each)
     const int nchunks = (kb128 + p.kc - 1) / p.kc;
     int best = 1;
     if (p.ws && p.flags && p.splits != 1) {
@@ -469,15 +480,17 @@ int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, 
     q.splits = best;
   }
   CUtensorMap mXh, mXl, mWh, mWl;
-  if (encode_tmap_2d(&mXh, x_hi, (uint64_t)p.Mtot, p.Cin, BM, KBY / 4, 4, KBY) ||
-      encode_tmap_2d(&mXl, x_lo, (uint64_t)p.Mtot, p.Cin, BM, KBY / 4, 4, KBY) ||
-      encode_tmap_2d(&mWh, w_hi, (uint64_t)p.taps * p.CoutPad, p.Cin, BN / CL, KBY / 4, 4, KBY) ||
-      encode_tmap_2d(&mWl, w_lo, (uint64_t)p.taps * p.CoutPad, p.Cin, BN / CL, KBY / 4, 4, KBY))
+  if (encode_tmap_2d(&mXh, x_hi, (uint64_t)p.Mtot, p.Cin, BM, KBY / eb, eb, KBY) ||
+      encode_tmap_2d(&mXl, x_lo, (uint64_t)p.Mtot, p.Cin, BM, KBY / eb, eb, KBY) ||
+      encode_tmap_2d(&mWh, w_hi, (uint64_t)p.taps * p.CoutPad, p.Cin, BN / CL, KBY / eb, eb, KBY) ||
+      encode_tmap_2d(&mWl, w_lo, (uint64_t)p.taps * p.CoutPad, p.Cin, BN / CL, KBY / eb, eb, KBY))
     return fail("cuTensorMapEncodeTiled failed");
   int rc;
 #define DVC_LAUNCH(BNv, CLv)                                                              \
-  rc = (KBY == 128) ? launch_bn<BNv, CLv, 128>(mXh, mXl, mWh, mWl, q, num_sms, s)         \
-                    : launch_bn<BNv, CLv, 64>(mXh, mXl, mWh, mWl, q, num_sms, s)
+  rc = f16 ? ((KBY == 128) ? launch_bn<BNv, CLv, 128, true>(mXh, mXl, mWh, mWl, q, num_sms, s)   \
+                           : launch_bn<BNv, CLv, 64, true>(mXh, mXl, mWh, mWl, q, num_sms, s))   \
+           : ((KBY == 128) ? launch_bn<BNv, CLv, 128, false>(mXh, mXl, mWh, mWl, q, num_sms, s)  \
+                           : launch_bn<BNv, CLv, 64, false>(mXh, mXl, mWh, mWl, q, num_sms, s))
   if (CL == 2) {
     if (BN == 256) { DVC_LAUNCH(256, 2); } else if (BN == 128) { DVC_LAUNCH(128, 2); } else { DVC_LAUNCH(64, 2); }
   } else {

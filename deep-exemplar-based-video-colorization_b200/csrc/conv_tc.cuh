@@ -23,6 +23,8 @@ struct ConvTcParams {
   int act;
   float slope;
   double* stats;  // optional [B][Cout][2]
+  int f16;          // operands are fp16 hi/lo planes (else tf32 planes stored as fp32 words)
+  float out_scale;  // fp16 mode: 2^-(e_x + e_w), undoes the exact power-of-two operand scales
   int splits;     // split-K factor S (1 = off); needs ws / flags below
   float* ws;      // [tiles][BN][128] fp32 partial totals
   int* flags;     // [tiles], value epoch*16 + (splits completed)
@@ -35,7 +37,7 @@ struct ConvTcParams {
 int conv_tc_pick_bn(int cout);  // channel tile (64 / 128 / 256) used for `cout` output channels
 // x_hi/x_lo: activation planes [Mtot][Cin]; w_hi/w_lo: weight planes [taps][CoutPad][Cin] (tf32-rounded fp32 words)
 // *variant receives the channel tile chosen (64 / 128 / 256)
-int launch_conv_tc(const ConvTcParams& p, const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo,
-                   int num_sms, cudaStream_t s, std::string* err, int* variant = nullptr);
+int launch_conv_tc(const ConvTcParams& p, const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int num_sms,
+                   cudaStream_t s, std::string* err, int* variant = nullptr);
 
 }  // namespace dvc

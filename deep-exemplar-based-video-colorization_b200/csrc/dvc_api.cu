@@ -30,8 +30,66 @@ struct ConvW {
   float* b = nullptr;  // [cout_pad]
   float* wt_hi = nullptr;  // [taps][cout_pad_tc][cin_pad]  tf32 hi plane (tensor-core kernel: K contiguous)
   float* wt_lo = nullptr;  //                               tf32 lo plane
+  void* w16_hi = nullptr;  // [taps][cout_pad_tc][cin_pad]  fp16 hi plane of w * 2^e_w
+  void* w16_lo = nullptr;
+  int e_w = 0;
   int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, cout_pad_tc = 0, k = 0;
 };
+
+// exponent e such that |x| <= bound implies |x * 2^e| <= 2^15 (fp16 max 65504), clamped to a sane range
+static inline int e16_for(double bound) {
+  if (!(bound > 0)) return 14;
+  int e = (int)floor(log2(32768.0 / bound));
+  return e > 14 ? 14 : (e < -14 ? -14 : e);
+}
+static inline unsigned short host_f2h(float f) {  // fp32 -> fp16 bits, round to nearest even, subnormals kept
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  const int32_t exp = (int32_t)((x >> 23) & 0xff) - 127 + 15;
+  uint32_t man = x & 0x7fffffu;
+  if (((x >> 23) & 0xff) == 0xff) return (unsigned short)(sign | 0x7c00u | (man ? 0x200u : 0));
+  if (exp >= 31) return (unsigned short)(sign | 0x7bffu);  // saturate instead of inf
+  if (exp <= 0) {
+    if (exp < -10) return (unsigned short)sign;
+    man |= 0x800000u;
+    const int shift = 14 - exp;
+    uint32_t h = man >> shift;
+    const uint32_t rem = man & ((1u << shift) - 1), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1))) h++;
+    return (unsigned short)(sign | h);
+  }
+  uint32_t h = ((uint32_t)exp << 10) | (man >> 13);
+  const uint32_t rem = man & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) h++;
+  return (unsigned short)(sign | h);
+}
+static inline float host_h2f(unsigned short h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  const uint32_t exp = (h >> 10) & 0x1f, man = h & 0x3ffu;
+  float f;
+  if (exp == 0) {
+    f = ldexpf((float)man, -24);
+  } else if (exp == 31) {
+    f = man ? NAN : INFINITY;
+  } else {
+    f = ldexpf((float)(man | 0x400u), (int)exp - 25);
+  }
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u |= sign;
+  memcpy(&f, &u, 4);
+  return f;
+}
+// fp16 hi/lo planes of v * 2^e: returns device buffers
+static void host_split16(const std::vector<float>& v, int e, std::vector<unsigned short>& hi, std::vector<unsigned short>& lo) {
+  hi.resize(v.size()), lo.resize(v.size());
+  for (size_t i = 0; i < v.size(); ++i) {
+    const float x = ldexpf(v[i], e);
+    hi[i] = host_f2h(x);
+    lo[i] = host_f2h(x - host_h2f(hi[i]));
+  }
+}
 
 static inline float host_tf32_rna(float x) {  // cvt.rna.tf32.f32: nearest, ties away, 10 explicit mantissa bits
   uint32_t u;
@@ -64,6 +122,8 @@ struct dvc_ctx {
   // default: tensor cores with fp32-class accuracy (3xTF32); DVC_MATH_FP32 selects the exact CUDA-core engines
   int conv_math = DVC_MATH_TF32X3, corr_math = DVC_MATH_FP16X3;
   int tc_kbytes = 128;    // tensor-core convolutions: K bytes per pipeline stage (64 or 128, see conv_tc.cu)
+  int tc_f16 = 1;         // tensor-core convolutions: fp16 hi/lo planes for layers with provably bounded inputs
+  std::unordered_map<std::string, float> vec_absmax[3];  // max |scale| of the *_ss vectors
   int tc_cluster = 1;     // tensor-core convolutions: 2 = 2-CTA clusters with multicast weight tiles
   int tc_kc = 1;          // tensor-core convolutions: k-blocks per TMEM chunk (see conv_tc.cu)
   bool two_level = true;  // fp32 convolutions: per-tap two-level accumulation (see conv_simt.cu)
@@ -141,14 +201,21 @@ static int get_buf(dvc_ctx* c, const std::string& name, size_t bytes, void** out
 // padded NHWC activation; the zero border is established once per (name, shape) and never written by
 // the convolution epilogues, the gather kernels rewrite their own borders every call.
 // split: allocate tf32 hi/lo planes (input of a tensor-core convolution)
+// mode 0: one fp32 plane; 1: tf32 hi/lo planes (fp32 words); 2: fp16 hi/lo planes of value * 2^e16 only;
+// 3: an fp32 plane AND fp16 hi/lo planes (tensors that also feed a non-convolution consumer)
 static int get_act(dvc_ctx* c, const std::string& name, int B, int H, int W, int C, int P, Act* a, cudaStream_t s,
-                   bool split = false) {
+                   int mode = 0) {
+  *a = Act();
   a->B = B, a->H = H, a->W = W, a->C = C, a->P = P;
-  const int sig[5] = {B, H, W, C, split ? -1 - P : P};
+  const int sig[5] = {B, H, W, C, mode == 1 ? -1 - P : P + 1000 * mode};
+  const size_t n = a->elems();
+  const size_t bytes = mode == 0 ? n * 4 : (mode == 1 ? n * 8 : (mode == 2 ? n * 4 : n * 8));
   void* p = nullptr;
-  DVC_TRY(get_buf(c, name, a->elems() * sizeof(float) * (split ? 2 : 1), &p, sig, true, s));
-  a->d = (float*)p;
-  a->lo = split ? a->d + a->elems() : nullptr;
+  DVC_TRY(get_buf(c, name, bytes, &p, sig, true, s));
+  if (mode == 0 || mode == 1 || mode == 3) a->d = (float*)p;
+  if (mode == 1) a->lo = a->d + n;
+  if (mode == 2) a->h16 = p, a->l16 = (char*)p + n * 2;
+  if (mode == 3) a->h16 = (char*)p + n * 4, a->l16 = (char*)p + n * 6;
   return DVC_OK;
 }
 static bool tc_mode(const dvc_ctx* c) { return c->conv_math == DVC_MATH_TF32X3; }
@@ -196,6 +263,23 @@ static bool ends_with(const std::string& s, const char* suf) {
   return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
 }
 
+// fp16 hi/lo planes of a packed [tap][cout][cin] weight block, scaled by the largest exact power of two that fits
+static int upload_w16(dvc_ctx* c, const std::vector<float>& full, ConvW& w) {
+  float amax = 0.f;
+  for (float v : full) amax = fmaxf(amax, fabsf(v));
+  w.e_w = e16_for(amax);
+  std::vector<unsigned short> hi, lo;
+  host_split16(full, w.e_w, hi, lo);
+  if (w.w16_hi) cudaFree(w.w16_hi);
+  if (w.w16_lo) cudaFree(w.w16_lo);
+  w.w16_hi = w.w16_lo = nullptr;
+  CUDA_TRY(c, cudaMalloc(&w.w16_hi, hi.size() * 2));
+  CUDA_TRY(c, cudaMalloc(&w.w16_lo, lo.size() * 2));
+  CUDA_TRY(c, cudaMemcpy(w.w16_hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+  CUDA_TRY(c, cudaMemcpy(w.w16_lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+  return DVC_OK;
+}
+
 extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const float* data, const int64_t* shape,
                               int ndim) {
   if (!c || !key_c || !data || !shape || net < 0 || net > 2 || ndim < 1 || ndim > 4)
@@ -217,6 +301,9 @@ extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const floa
       if (d) cudaFree(d);
       CUDA_TRY(c, cudaMalloc((void**)&d, n * sizeof(float)));
       CUDA_TRY(c, cudaMemcpy(d, h.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+      float amax = 0.f;
+      for (float v : h) amax = fmaxf(amax, fabsf(v));
+      c->vec_absmax[net][base] = amax;
       return DVC_OK;
     }
     if (!((kh == 3 && kw == 3) || (kh == 1 && kw == 1))) return fail(c, DVC_ERR_SHAPE, "unsupported kernel size: " + key);
@@ -250,12 +337,13 @@ extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const floa
     if (cin_pad % 32 == 0 && co >= 32) {  // tensor-core operand: [tap][cout_pad_tc][cin] hi / lo planes
       const int bn = conv_tc_pick_bn(co);
       const int cpt = (co + bn - 1) / bn * bn;
-      std::vector<float> hi((size_t)taps * cpt * cin_pad, 0.f), lo(hi.size(), 0.f);
+      std::vector<float> hi((size_t)taps * cpt * cin_pad, 0.f), lo(hi.size(), 0.f), full(hi.size(), 0.f);
       for (int o = 0; o < co; ++o)
         for (int i = 0; i < ci; ++i)
           for (int t = 0; t < taps; ++t) {
             const float v = h[((size_t)o * ci + i) * taps + t];
             const float vh = host_tf32_rna(v);
+            full[((size_t)t * cpt + o) * cin_pad + i] = v;
             hi[((size_t)t * cpt + o) * cin_pad + i] = vh;
             lo[((size_t)t * cpt + o) * cin_pad + i] = host_tf32_rna(v - vh);
           }
@@ -264,13 +352,14 @@ extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const floa
       CUDA_TRY(c, cudaMemcpy(cw.wt_hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
       CUDA_TRY(c, cudaMemcpy(cw.wt_lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
       cw.cout_pad_tc = cpt;
+      DVC_TRY(upload_w16(c, full, cw));
       if (net == DVC_NET_COLOR && taps == 9 && (base == "conv8_1.1" || base == "conv9_1.1" || base == "conv10_1.1")) {
         // ColorVidNet.py:81-83: Upsample(2, nearest) + Conv2d(3x3, pad 1).  Phase (a, b) of the output sees a 2x2
         // low-resolution neighbourhood whose weights are sums of the 3x3 taps that land on the same source pixel.
         for (int ph = 0; ph < 4; ++ph) {
           const int a = ph >> 1, b2 = ph & 1;
           ConvW& pw = c->conv[net][base + "#p" + std::to_string(ph)];
-          std::vector<float> phi_((size_t)4 * cpt * cin_pad, 0.f), plo(phi_.size(), 0.f);
+          std::vector<float> phi_((size_t)4 * cpt * cin_pad, 0.f), plo(phi_.size(), 0.f), pfull(phi_.size(), 0.f);
           for (int o = 0; o < co; ++o)
             for (int i = 0; i < ci; ++i)
               for (int r = 0; r < 2; ++r)
@@ -285,6 +374,7 @@ extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const floa
                     }
                   }
                   const float vh = host_tf32_rna(v);
+                  pfull[((size_t)(r * 2 + cc) * cpt + o) * cin_pad + i] = v;
                   phi_[((size_t)(r * 2 + cc) * cpt + o) * cin_pad + i] = vh;
                   plo[((size_t)(r * 2 + cc) * cpt + o) * cin_pad + i] = host_tf32_rna(v - vh);
                 }
@@ -295,6 +385,7 @@ extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const floa
           CUDA_TRY(c, cudaMemcpy(pw.wt_hi, phi_.data(), phi_.size() * sizeof(float), cudaMemcpyHostToDevice));
           CUDA_TRY(c, cudaMemcpy(pw.wt_lo, plo.data(), plo.size() * sizeof(float), cudaMemcpyHostToDevice));
           pw.cin = ci, pw.cin_pad = cin_pad, pw.cout = co, pw.cout_pad = cout_pad, pw.cout_pad_tc = cpt, pw.k = 2;
+          DVC_TRY(upload_w16(c, pfull, pw));
           pw.b = nullptr;  // shares the bias of the 3x3 convolution (resolved at launch)
           pw.w = nullptr;
         }
@@ -365,7 +456,8 @@ struct ConvOpt {
 static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const ConvOpt& o, cudaStream_t s) {
   if (x.C != w->cin_pad) return fail(c, DVC_ERR_SHAPE, "conv: input channel mismatch");
   const int taps = o.phase >= 0 ? 4 : w->k * w->k;
-  if (o.phase >= 0 && !x.lo) return fail(c, DVC_ERR_STATE, "conv: phase convolution needs the tensor-core engine");
+  const bool f16 = x.h16 != nullptr;
+  if (o.phase >= 0 && !x.lo && !f16) return fail(c, DVC_ERR_STATE, "conv: phase convolution needs the tensor-core engine");
   if (taps == 9 && x.P < o.dil) return fail(c, DVC_ERR_STATE, "conv: input border narrower than the dilation");
   ConvParams p{};
   p.x = x.d, p.Hp = x.Hp(), p.Wp = x.Wp(), p.P = x.P, p.H = x.H, p.W = x.W, p.Cin = x.C;
@@ -383,9 +475,11 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
   p.nchw = nullptr;
   p.act = o.act, p.slope = o.slope, p.stats = o.stats;
   p.y_lo = y.lo;
-  if (x.lo) {  // hi/lo planes: tensor-core engine
-    if (!w->wt_hi) return fail(c, DVC_ERR_STATE, "conv: split input but no tensor-core weights");
+  if (x.lo || f16) {  // hi/lo planes: tensor-core engine (TF32 words, or fp16 halves of value * 2^e16)
+    if (!w->wt_hi || (f16 && !w->w16_hi)) return fail(c, DVC_ERR_STATE, "conv: split input but no tensor-core weights");
     ConvTcParams t{};
+    t.f16 = f16 ? 1 : 0;
+    t.out_scale = f16 ? ldexpf(1.0f, -(x.e16 + w->e_w)) : 1.0f;
     t.Hp = p.Hp, t.Wp = p.Wp, t.P = p.P, t.H = p.H, t.W = p.W, t.Cin = p.Cin, t.Mtot = x.B * p.Hp * p.Wp;
     t.taps = taps, t.stride = o.stride, t.Cout = w->cout, t.CoutPad = w->cout_pad_tc, t.bias = w->b;
     t.oscale = 1, t.oa = 0, t.ob = 0;
@@ -424,7 +518,9 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
       CUDA_TRY(c, cudaEventRecord(e0, s));
     }
     int variant = 0;
-    if (launch_conv_tc(t, x.d, x.lo, w->wt_hi, w->wt_lo, c->num_sms, s, &err, &variant) != 0) return fail(c, DVC_ERR_CUDA, "conv_tc: " + err);
+    const int lrc = f16 ? launch_conv_tc(t, x.h16, x.l16, w->w16_hi, w->w16_lo, c->num_sms, s, &err, &variant)
+                        : launch_conv_tc(t, x.d, x.lo, w->wt_hi, w->wt_lo, c->num_sms, s, &err, &variant);
+    if (lrc != 0) return fail(c, DVC_ERR_CUDA, "conv_tc: " + err);
     if (c->prof_conv) {
       CUDA_TRY(c, cudaEventRecord(e1, s));
       // algorithmic FLOPs: 2 x output pixels x taps x Cin x Cout (padding channels and masked border pixels excluded)
@@ -460,6 +556,7 @@ static int run_xform(dvc_ctx* c, const Act& src, Act& dst, const XfOpt& o, cudaS
   XformParams p{};
   p.src = src.d, p.src_lo = src.lo, p.sH = src.H, p.sW = src.W, p.sP = src.P, p.sC = src.C, p.sCoff = 0;
   p.dst_lo = dst.lo;
+  p.dst_h16 = dst.h16, p.dst_l16 = dst.l16, p.dscale16 = ldexpf(1.0f, dst.e16);
   p.dst = dst.d, p.dH = dst.H, p.dW = dst.W, p.dP = dst.P, p.dC = dst.C, p.dCoff = o.dCoff;
   p.C = C, p.pad_mode = o.pad_mode, p.up = o.up, p.sub = o.sub, p.rowpad = o.rowpad;
   p.stats = o.stats, p.count = o.count, p.eps = 1e-5f, p.scale = o.scale;
@@ -473,11 +570,12 @@ static int run_xform(dvc_ctx* c, const Act& src, Act& dst, const XfOpt& o, cudaS
 }
 
 static int run_pixnorm(dvc_ctx* c, const Act& src, float* dst, float* dst_lo, int dP, int pad_mode, const double* stats,
-                       double count, cudaStream_t s) {
+                       double count, cudaStream_t s, void* h16 = nullptr, void* l16 = nullptr, int e16 = 0) {
   if (src.C != 128 && src.C != 256 && src.C != 512) return fail(c, DVC_ERR_SHAPE, "pixnorm: channel count");
   PixNormParams p{};
   p.src = src.d, p.src_lo = src.lo, p.sH = src.H, p.sW = src.W, p.sP = src.P, p.sC = src.C;
   p.dst = dst, p.dst_lo = dst_lo, p.dP = dP, p.dC = src.C, p.C = src.C, p.pad_mode = pad_mode;
+  p.dst_h16 = h16, p.dst_l16 = l16, p.dscale16 = ldexpf(1.0f, e16);
   p.stats = stats, p.count = count, p.eps = 2.220446049250313e-16f;  // sys.float_info.epsilon
   launch_pixnorm(p, src.B, s);
   return check_launch(c, "pixnorm");
@@ -535,8 +633,11 @@ static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const c
   const int net = DVC_NET_WARP;
   const int B = n[0].B;
   Act cat;
-  const bool sp = tc_mode(c);
-  DVC_TRY(get_act(c, tag + ".cat", B, h, w, 256, 1, &cat, s, sp));
+  // tensor-core mode: every tensor below is an InstanceNorm output (|z| <= sqrt(count)) through a PReLU, so its fp16
+  // hi/lo planes get a static exact power-of-two scale; cat and the residual chain also keep an fp32 plane (mode 3)
+  const bool h16 = tc_mode(c) && c->tc_f16;
+  const int sp = h16 ? 2 : (tc_mode(c) ? 1 : 0), sp_res = h16 ? 3 : sp;
+  DVC_TRY(get_act(c, tag + ".cat", B, h, w, 256, 1, &cat, s, sp_res));
 
   struct Head {
     const char* c1;
@@ -549,6 +650,13 @@ static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const c
                          {"layer3_1.1", "layer3_1.3", "layer3_1.5", "layer3_1.7", 1, 1, 1},
                          {"layer4_1.1", "layer4_1.3", "layer4_1.5", "layer4_1.7", 1, 1, 2},
                          {"layer5_1.1", "layer5_1.3", "layer5_1.6", "layer5_1.8", 1, 2, 2}};
+  double cat_bound = 0;  // every head's last InstanceNorm runs over at most h*w positions
+  for (int k = 0; k < 4; ++k) {
+    float s2;
+    DVC_TRY(need_slope(c, net, heads[k].s2, &s2));
+    cat_bound = fmax(cat_bound, sqrt((double)h * w) * fmax(1.0, fabs(s2)));
+  }
+  cat.e16 = e16_for(cat_bound);
   for (int k = 0; k < 4; ++k) {
     const Head& hd = heads[k];
     const ConvW *w1, *w2;
@@ -567,10 +675,12 @@ static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const c
     o1.stats = st1;
     DVC_TRY(run_conv(c, w1, x, raw1, o1, s));
     DVC_TRY(get_act(c, t + ".mid", B, x.H * hd.up_mid, x.W * hd.up_mid, w1->cout, 1, &mid, s, sp));
+    mid.e16 = e16_for(sqrt((double)x.H * x.W) * fmax(1.0, fabs(s1)));
     XfOpt x1;
     x1.pad_mode = PAD_REFLECT, x1.up = hd.up_mid, x1.stats = st1, x1.count = (double)x.H * x.W, x1.act = 2, x1.slope = s1;
     DVC_TRY(run_xform(c, raw1, mid, x1, s));
     const int h2 = (mid.H + hd.stride2 - 1) / hd.stride2, w2o = (mid.W + hd.stride2 - 1) / hd.stride2;
+
     DVC_TRY(get_act(c, t + ".raw2", B, h2, w2o, 64, 0, &raw2, s));
     DVC_TRY(stats_alloc(c, B, 64, &st2, s));
     ConvOpt o2;
@@ -591,9 +701,10 @@ static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const c
 
   // three residual blocks (NonlocalNet.py:341-352), ping-pong between two padded buffers
   Act xa = cat, xb, raw, mid;
-  DVC_TRY(get_act(c, tag + ".res_b", B, h, w, 256, 1, &xb, s, sp));
+  DVC_TRY(get_act(c, tag + ".res_b", B, h, w, 256, 1, &xb, s, sp_res));
   DVC_TRY(get_act(c, tag + ".res_raw", B, h, w, 256, 0, &raw, s));
   DVC_TRY(get_act(c, tag + ".res_mid", B, h, w, 256, 1, &mid, s, sp));
+  double chain_bound = cat_bound;
   for (int i = 0; i < 3; ++i) {
     const std::string base = "layer." + std::to_string(i);
     const ConvW *w1, *w2;
@@ -609,12 +720,16 @@ static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const c
     DVC_TRY(run_conv(c, w1, xa, raw, o1, s));
     XfOpt x1;
     x1.pad_mode = PAD_REFLECT, x1.stats = st1, x1.count = (double)h * w, x1.act = 2, x1.slope = sl;
+    const double in_bound = sqrt((double)h * w) * fmax(1.0, fabs(sl));
+    mid.e16 = e16_for(in_bound);
     DVC_TRY(run_xform(c, raw, mid, x1, s));
     ConvOpt o2;
     o2.stats = st2;
     DVC_TRY(run_conv(c, w2, mid, raw, o2, s));
     XfOpt x2;
     x2.pad_mode = PAD_REFLECT, x2.stats = st2, x2.count = (double)h * w, x2.act = 2, x2.slope = sl, x2.res = &xa;
+    chain_bound += in_bound;  // out = PReLU(IN(..)) + residual (NonlocalNet.py:44-51)
+    xb.e16 = e16_for(chain_bound);
     DVC_TRY(run_xform(c, raw, xb, x2, s));
     std::swap(xa, xb);
   }
@@ -677,10 +792,12 @@ static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* o
     }
     return run_conv(c, w, x, *y, o, s);
   };
+  // InstanceNorm outputs are bounded by sqrt(count) (x |scale|): fp16 hi/lo planes with a static power-of-two scale
   auto norm = [&](const char* name, const Act& raw, const double* st, Act* y, int outP, int up, int sub,
-                  const float* scale) -> int {
+                  const float* scale, float scale_abs = 1.f) -> int {
     DVC_TRY(get_act(c, tag + "." + name + "#" + std::to_string(uid++), B, ((raw.H + sub - 1) / sub) * up,
-                    ((raw.W + sub - 1) / sub) * up, raw.C, outP, y, s, tc_mode(c)));
+                    ((raw.W + sub - 1) / sub) * up, raw.C, outP, y, s, tc_mode(c) ? (c->tc_f16 ? 2 : 1) : 0));
+    y->e16 = e16_for(sqrt((double)raw.H * raw.W) * fmax(1e-3, (double)scale_abs));
     XfOpt o;
     o.pad_mode = PAD_ZERO, o.up = up, o.sub = sub, o.stats = st, o.count = (double)raw.H * raw.W, o.scale = scale;
     return run_xform(c, raw, *y, o, s);
@@ -697,7 +814,7 @@ static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* o
       DVC_TRY(norm((std::string(name) + ".in").c_str(), raw, st, &nl, 1, 1, 1, nullptr));
       for (int ph = 0; ph < 4; ++ph) {
         auto it = c->conv[net].find(std::string(name) + "#p" + std::to_string(ph));
-        if (it == c->conv[net].end() || !it->second.wt_hi) return fail(c, DVC_ERR_STATE, std::string("phase weights missing: ") + name);
+        if (it == c->conv[net].end() || !it->second.wt_hi || !it->second.w16_hi) return fail(c, DVC_ERR_STATE, std::string("phase weights missing: ") + name);
         ConvW pw = it->second;
         pw.b = w->b;
         ConvOpt o;
@@ -725,16 +842,16 @@ static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* o
   DVC_TRY(conv("conv1_1.2", a, &b, 1, ACT_RELU, 1, nullptr, nullptr, 0));
   DVC_TRY(conv("conv1_2", b, &raw1, 0, ACT_RELU, 1, nullptr, &st1, 0));
   DVC_TRY(norm("n1", raw1, st1, &n1, 1, 1, 1, nullptr));
-  DVC_TRY(norm("d1", raw1, st1, &d1, 1, 1, 2, ss1));
+  DVC_TRY(norm("d1", raw1, st1, &d1, 1, 1, 2, ss1, c->vec_absmax[net]["conv1_2norm_ss"]));
   DVC_TRY(conv("conv2_1", d1, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
   DVC_TRY(conv("conv2_2", a, &raw2, 0, ACT_RELU, 1, nullptr, &st2, 0));
   DVC_TRY(norm("n2", raw2, st2, &n2, 1, 1, 1, nullptr));
-  DVC_TRY(norm("d2", raw2, st2, &d2, 1, 1, 2, ss2));
+  DVC_TRY(norm("d2", raw2, st2, &d2, 1, 1, 2, ss2, c->vec_absmax[net]["conv2_2norm_ss"]));
   DVC_TRY(conv("conv3_1", d2, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
   DVC_TRY(conv("conv3_2", a, &b, 1, ACT_RELU, 1, nullptr, nullptr, 0));
   DVC_TRY(conv("conv3_3", b, &raw3, 0, ACT_RELU, 1, nullptr, &st3, 0));
   DVC_TRY(norm("n3", raw3, st3, &n3, 1, 1, 1, nullptr));
-  DVC_TRY(norm("d3", raw3, st3, &d3, 1, 1, 2, ss3));
+  DVC_TRY(norm("d3", raw3, st3, &d3, 1, 1, 2, ss3, c->vec_absmax[net]["conv3_3norm_ss"]));
   DVC_TRY(conv("conv4_1", d3, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
   DVC_TRY(conv("conv4_2", a, &b, 1, ACT_RELU, 1, nullptr, nullptr, 0));
   DVC_TRY(conv("conv4_3", b, &raw4, 0, ACT_RELU, 1, nullptr, &st4, 0));
@@ -815,6 +932,8 @@ extern "C" int dvc_destroy(dvc_ctx* c) {
       if (kv.second.w) cudaFree(kv.second.w);
       if (kv.second.b) cudaFree(kv.second.b);
       if (kv.second.wt_hi) cudaFree(kv.second.wt_hi);
+      if (kv.second.w16_hi) cudaFree(kv.second.w16_hi);
+      if (kv.second.w16_lo) cudaFree(kv.second.w16_lo);
       if (kv.second.wt_lo) cudaFree(kv.second.wt_lo);
     }
     for (auto& kv : c->vec[n])
@@ -854,6 +973,7 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!c || !name) return DVC_ERR_ARG;
   if (!strcmp(name, "two_level")) { c->two_level = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_kc")) { c->tc_kc = value < 1 ? 1 : value; return DVC_OK; }
+  if (!strcmp(name, "tc_f16")) { c->tc_f16 = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_splits")) { c->tc_splits = value < 0 ? 0 : (value > 8 ? 8 : value); return DVC_OK; }
   if (!strcmp(name, "tc_kbytes")) { c->tc_kbytes = value == 64 ? 64 : 128; return DVC_OK; }
   if (!strcmp(name, "tc_cluster")) { c->tc_cluster = value == 2 ? 2 : 1; return DVC_OK; }
@@ -1072,8 +1192,10 @@ static int normalised_features(dvc_ctx* c, const std::string& tag, VggMaps& maps
   const char* keys[4] = {"r22", "r32", "r42", "r52"};
   for (int k = 0; k < 4; ++k) {
     const Act& r = maps.m[keys[k]];
-    DVC_TRY(get_act(c, tag + ".n" + std::to_string(k), r.B, r.H, r.W, r.C, 1, &n[k], s, tc_mode(c)));
-    DVC_TRY(run_pixnorm(c, r, n[k].d, n[k].lo, 1, PAD_REFLECT, nullptr, 1.0, s));  // feature_normalize, util.py:155-158
+    // unit-L2 pixels: |x| <= 1, fp16 planes of x * 2^14
+    DVC_TRY(get_act(c, tag + ".n" + std::to_string(k), r.B, r.H, r.W, r.C, 1, &n[k], s, tc_mode(c) ? (c->tc_f16 ? 2 : 1) : 0));
+    n[k].e16 = 14;
+    DVC_TRY(run_pixnorm(c, r, n[k].d, n[k].lo, 1, PAD_REFLECT, nullptr, 1.0, s, n[k].h16, n[k].l16, n[k].e16));  // feature_normalize, util.py:155-158
   }
   return DVC_OK;
 }

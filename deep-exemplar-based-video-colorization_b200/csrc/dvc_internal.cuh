@@ -17,6 +17,10 @@ namespace dvc {
 struct Act {
   float* d = nullptr;   // pixel (b=0, yp=0, xp=0), channel 0; the hi plane when lo != nullptr
   float* lo = nullptr;  // lo plane of a tf32 hi/lo split activation (value = hi + lo), same geometry
+  // fp16 hi/lo planes of value * 2^e16 (same geometry, 2-byte elements); the fp32 plane `d` may coexist (d != nullptr)
+  void* h16 = nullptr;
+  void* l16 = nullptr;
+  int e16 = 0;
   int B = 0, H = 0, W = 0, C = 0, P = 0;
   int Hp() const { return H + 2 * P; }
   int Wp() const { return W + 2 * P; }
@@ -57,6 +61,9 @@ struct XformParams {
   int sH, sW, sP, sC, sCoff;
   float* dst;
   float* dst_lo;  // optional: store as hi/lo planes
+  void* dst_h16;  // optional fp16 hi/lo planes of value * dscale16 (dst may be nullptr then)
+  void* dst_l16;
+  float dscale16;
   const float* res_lo;
   int dH, dW, dP, dC, dCoff;
   int C;
@@ -79,6 +86,9 @@ struct PixNormParams {
   int sH, sW, sP, sC;
   float* dst;
   float* dst_lo;
+  void* dst_h16;  // optional fp16 hi/lo planes of value * dscale16
+  void* dst_l16;
+  float dscale16;
   int dP, dC;  // destination has the same logical HxW
   int C, pad_mode;
   const double* stats;  // optional channel sums [B][C][2] -> subtract mean over positions

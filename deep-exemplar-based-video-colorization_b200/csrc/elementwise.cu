@@ -2,6 +2,7 @@
 // nearest up-sampling / stride-2 pick / residual add (one gather kernel), per-pixel channel
 // normalisation, max-pool, layout conversion at the NCHW boundary, colour-space prologue.
 // All are coalesced over the channel (innermost) dimension with 128-bit accesses.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "dvc_internal.cuh"
@@ -34,6 +35,22 @@ __device__ __forceinline__ void st4(float* __restrict__ p, float* __restrict__ l
   } else {
     *reinterpret_cast<float4*>(p + off) = v;
   }
+}
+
+// fp16 hi/lo planes of v * scale (scale = 2^e from a proven bound on |v|, so the clamp never triggers in range):
+// hi + lo carries 2 x 11 significant bits like the tf32 split, at half the bytes
+__device__ __forceinline__ void st4h(__half* __restrict__ hp, __half* __restrict__ lp, size_t off, float4 v, float scale) {
+  const float x[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+  unsigned short h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float xc = fminf(fmaxf(x[j], -65504.f), 65504.f);
+    const __half hh = __float2half_rn(xc);
+    h[j] = __half_as_ushort(hh);
+    l[j] = __half_as_ushort(__float2half_rn(xc - __half2float(hh)));
+  }
+  *reinterpret_cast<uint2*>(hp + off) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+  *reinterpret_cast<uint2*>(lp + off) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
 }
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
@@ -106,7 +123,9 @@ __global__ void __launch_bounds__(256) xform_kernel(const XformParams p) {
         v.w = v.w > 0.f ? v.w : v.w * p.slope;
       }
     }
-    st4(p.dst, p.dst_lo, (((size_t)b * dHp + yp) * dWp + xp) * p.dC + p.dCoff + c, v);
+    const size_t doff = (((size_t)b * dHp + yp) * dWp + xp) * p.dC + p.dCoff + c;
+    if (p.dst) st4(p.dst, p.dst_lo, doff, v);
+    if (p.dst_h16) st4h(reinterpret_cast<__half*>(p.dst_h16), reinterpret_cast<__half*>(p.dst_l16), doff, v, p.dscale16);
   }
 }
 
@@ -159,7 +178,10 @@ __global__ void __launch_bounds__(256) pixnorm_kernel(const PixNormParams p) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       // true division like torch.div(x, norm) (util.py:157, NonlocalNet.py:471)
-      st4(p.dst, p.dst_lo, dof + (i * 32 + lane) * 4, make_float4(v[i].x / n, v[i].y / n, v[i].z / n, v[i].w / n));
+      const float4 o4 = make_float4(v[i].x / n, v[i].y / n, v[i].z / n, v[i].w / n);
+      if (p.dst) st4(p.dst, p.dst_lo, dof + (i * 32 + lane) * 4, o4);
+      if (p.dst_h16)
+        st4h(reinterpret_cast<__half*>(p.dst_h16), reinterpret_cast<__half*>(p.dst_l16), dof + (i * 32 + lane) * 4, o4, p.dscale16);
     }
   }
 }

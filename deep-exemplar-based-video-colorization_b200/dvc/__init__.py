@@ -305,8 +305,14 @@ class Context:
         split = P < 0  # hi/lo planes of a tensor-core activation are stored back to back
         if split:
             P = -1 - P
+        mode16, P = divmod(P, 1000)  # 2: fp16 hi/lo planes of value * 2^e only; 3: an fp32 plane followed by them
         n = B * (H + 2 * P) * (W + 2 * P) * C
-        t = flat[:n] + flat[n:2 * n] if split else flat[:n]
+        if mode16 == 2:
+            # the static exponent lives in the layer program; return hi + lo in scaled units
+            halves = flat.view(torch.float16)
+            t = halves[:n].float() + halves[n:2 * n].float()
+        else:
+            t = flat[:n] + flat[n:2 * n] if split else flat[:n]
         t = t.view(B, H + 2 * P, W + 2 * P, C)
         return t[:, P:P + H, P:P + W, :].permute(0, 3, 1, 2).contiguous()
 

@@ -32,10 +32,11 @@ def ab_gate(ours, g):
     return err, max(1e-3, 2.0 * floor)
 
 
-@pytest.fixture(params=["fp32", "tf32x3", "tf32x3-cluster2", "tf32x3-k64", "tf32x3-split3"])
+@pytest.fixture(params=["fp32", "tf32x3", "tf32x3-nof16", "tf32x3-cluster2", "tf32x3-k64", "tf32x3-split3"])
 def conv_math(request, ctx):
     """Convolutions on CUDA cores (exact fp32, two-level accumulation) and on tcgen05 (3xTF32 operand split),
-    the latter as single CTAs (64-byte and 128-byte K stages) and as 2-CTA clusters with TMA-multicast weights."""
+    the latter as single CTAs (64-byte and 128-byte K stages) and as 2-CTA clusters with TMA-multicast weights.
+    Layers with provably bounded inputs run 3xFP16 on scaled planes unless "-nof16" turns that off."""
     import dvc
 
     if request.param.startswith("tf32x3"):
@@ -43,12 +44,14 @@ def conv_math(request, ctx):
         ctx.debug_flag("tc_cluster", 2 if request.param.endswith("cluster2") else 1)
         ctx.debug_flag("tc_kbytes", 64 if request.param.endswith("k64") else 128)
         ctx.debug_flag("tc_splits", 3 if request.param.endswith("split3") else 1)
+        ctx.debug_flag("tc_f16", 0 if request.param.endswith("nof16") else 1)
     else:
         ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
     yield request.param
     ctx.debug_flag("tc_cluster", 1)
     ctx.debug_flag("tc_kbytes", 128)
     ctx.debug_flag("tc_splits", 1)
+    ctx.debug_flag("tc_f16", 1)
     ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
 
 
