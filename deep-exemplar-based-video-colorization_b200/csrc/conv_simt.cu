@@ -6,6 +6,8 @@
 //
 // Tile: 128 padded pixels x BN output channels x 8 input channels per step, 256 threads, 8 x (BN/16)
 // accumulators per thread, register-prefetch double buffering (one __syncthreads per k-step).
+#include <cuda_fp16.h>
+
 #include "dvc_internal.cuh"
 
 namespace dvc {
@@ -238,8 +240,17 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const ConvParams p, int
   __syncthreads();
   const int b = blockIdx.y;
   const int pix = blockIdx.x * 128 + threadIdx.x;
-  if (pix >= p.H * p.W) return;
-  const int y = pix / p.W, x = pix - y * p.W;
+  // fp16 output planes with a device-derived scale (tensor-core mode: the next layer is a 3xFP16 convolution)
+  float yscale = 1.f, amax = 0.f;
+  if (p.dyn.h16) {
+    const int e_out = dyn_out_exponent(p.dyn);
+    yscale = exp2_int(e_out);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dyn.cell_out->e = e_out;
+  }
+  const bool live = pix < p.H * p.W;  // dead lanes recompute pixel 0 and store nothing (the warp stays converged)
+  if (!live && !p.dyn.cell_out) return;
+  const int pc = live ? pix : 0;
+  const int y = pc / p.W, x = pc - y * p.W;
   float acc[COUT];
 #pragma unroll
   for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
@@ -274,7 +285,22 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const ConvParams p, int
       if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
       if (p.act == ACT_LRELU) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
     }
-    if (p.y_lo) {
+    if (!live) continue;
+    if (p.dyn.cell_out) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
+    if (p.dyn.h16) {
+      unsigned short h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xc = fminf(fmaxf(v[j] * yscale, -65504.f), 65504.f);
+        const __half hh = __float2half_rn(xc);
+        h[j] = __half_as_ushort(hh);
+        l[j] = __half_as_ushort(__float2half_rn(xc - __half2float(hh)));
+      }
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.dyn.h16) + o + c4 * 4) =
+          make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.dyn.l16) + o + c4 * 4) =
+          make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    } else if (p.y_lo) {
       float h[4], l[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -290,6 +316,7 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const ConvParams p, int
       *reinterpret_cast<float4*>(p.y + o + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
     }
   }
+  if (p.dyn.cell_out) warp_amax_commit(amax, p.dyn.cell_out);
 }
 
 }  // namespace

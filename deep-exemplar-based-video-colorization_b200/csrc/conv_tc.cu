@@ -17,6 +17,7 @@
 //               fp32 or as hi/lo planes for the next tensor-core layer.
 // Replaces nn.Conv2d (+ReLU/LeakyReLU/skip add) at NonlocalNet.py:235-255,364-423 and ColorVidNet.py:96-143.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "conv_tc.cuh"
@@ -207,6 +208,16 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const int etid = threadIdx.x - 128;     // 0..255
     const int img = p.Hp * p.Wp;
     uint32_t chunk_id = 0;
+    // device-side scales (conv -> ReLU -> conv chains on fp16 planes, dvc_internal.cuh: DynOut)
+    float oscale = p.out_scale, yscale = 1.f, amax = 0.f;
+    if constexpr (F16) {
+      if (p.dyn.cell_in) oscale *= exp2_int(-p.dyn.cell_in->e);
+      if (p.dyn.h16) {
+        const int e_out = dyn_out_exponent(p.dyn);
+        yscale = exp2_int(e_out);
+        if (etid == 0 && blockIdx.x == 0) p.dyn.cell_out->e = e_out;
+      }
+    }
     for (int work = item0; work < total_work; work += item_stride) {
       const int sp = work / total_items, item = work - sp * total_items;
       const int mg = item / n_tiles, nt = item - mg * n_tiles;
@@ -308,8 +319,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           for (int j = 0; j < 32; j += 4) {
             const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + j));
             if constexpr (F16) {
-              v[j] = fmaf(tot[c * 32 + j], p.out_scale, bv.x), v[j + 1] = fmaf(tot[c * 32 + j + 1], p.out_scale, bv.y);
-              v[j + 2] = fmaf(tot[c * 32 + j + 2], p.out_scale, bv.z), v[j + 3] = fmaf(tot[c * 32 + j + 3], p.out_scale, bv.w);
+              v[j] = fmaf(tot[c * 32 + j], oscale, bv.x), v[j + 1] = fmaf(tot[c * 32 + j + 1], oscale, bv.y);
+              v[j + 2] = fmaf(tot[c * 32 + j + 2], oscale, bv.z), v[j + 3] = fmaf(tot[c * 32 + j + 3], oscale, bv.w);
             } else {
               v[j] = tot[c * 32 + j] + bv.x, v[j + 1] = tot[c * 32 + j + 1] + bv.y;
               v[j + 2] = tot[c * 32 + j + 2] + bv.z, v[j + 3] = tot[c * 32 + j + 3] + bv.w;
@@ -331,8 +342,30 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
             if (p.act == ACT_LRELU) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
           }
+          if (F16 && p.dyn.cell_out && valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(v[j]));
+          }
           if (valid) {
-            if (p.y_lo) {
+            if (F16 && p.dyn.h16) {
+              __half* hp = reinterpret_cast<__half*>(p.dyn.h16) + yoff + ch0;
+              __half* lp = reinterpret_cast<__half*>(p.dyn.l16) + yoff + ch0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float x0 = fminf(fmaxf(v[j + 2 * t] * yscale, -65504.f), 65504.f);
+                  const float x1 = fminf(fmaxf(v[j + 2 * t + 1] * yscale, -65504.f), 65504.f);
+                  const __half2 h2 = __floats2half2_rn(x0, x1);
+                  const float2 hf = __half22float2(h2);
+                  const __half2 l2 = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                  hw[t] = *reinterpret_cast<const uint32_t*>(&h2), lw[t] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                *reinterpret_cast<uint4*>(hp + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(lp + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              }
+            } else if (p.y_lo) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 float h[4], l[4];
@@ -396,6 +429,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
+    if (F16 && p.dyn.cell_out) warp_amax_commit(amax, p.dyn.cell_out);
   }
 
   tc::tc_fence_before();
@@ -464,8 +498,9 @@ int launch_conv_tc(const ConvTcParams& p, const void* x_hi, const void* x_lo, co
   {  // split-K factor: minimise rounds(S) / S over the persistent grid (2 % penalty per extra split for the hand-over)
     const int m_tiles = (p.Mtot + BM - 1) / BM;
     const int tiles = ((m_tiles + CL - 1) / CL) * CL * (p.CoutPad / BN);
-    const int kb128 = p.taps * (p.Cin / (f16 ? 64 : 32));  // 128-byte k-blocks (12 MMA accumulations each)
-    const int nchunks = (kb128 + p.kc - 1) / p.kc;
+    // k-blocks of KBY bytes and the chunks the kernel sums them in (p.kc counts 128-byte k-blocks)
+    const int nk = p.taps * (p.Cin / (KBY / eb)), kcs = p.kc * (128 / KBY);
+    const int nchunks = (nk + kcs - 1) / kcs;
     int best = 1;
     if (p.ws && p.flags && p.splits != 1) {
       double best_cost = 1e30;
@@ -476,6 +511,7 @@ int launch_conv_tc(const ConvTcParams& p, const void* x_hi, const void* x_lo, co
         if (cost < best_cost - 1e-9) best_cost = cost, best = S;
       }
       if (p.splits > 1) best = p.splits < nchunks ? p.splits : nchunks;  // forced (tests)
+      if (best < 1) best = 1;
     }
     q.splits = best;
   }

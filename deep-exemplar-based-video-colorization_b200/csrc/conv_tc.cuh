@@ -25,6 +25,8 @@ struct ConvTcParams {
   double* stats;  // optional [B][Cout][2]
   int f16;          // operands are fp16 hi/lo planes (else tf32 planes stored as fp32 words)
   float out_scale;  // fp16 mode: 2^-(e_x + e_w), undoes the exact power-of-two operand scales
+  DynOut dyn;       // fp16 mode: device-side scales (dyn.cell_in: the input exponent is added to out_scale's on the
+                    // device; dyn.h16: store fp16 planes with a derived exponent; dyn.cell_out: record max |output|)
   int splits;     // split-K factor S (1 = off); needs ws / flags below
   float* ws;      // [tiles][BN][128] fp32 partial totals
   int* flags;     // [tiles], value epoch*16 + (splits completed)

@@ -33,6 +33,8 @@ struct ConvW {
   void* w16_hi = nullptr;  // [taps][cout_pad_tc][cin_pad]  fp16 hi plane of w * 2^e_w
   void* w16_lo = nullptr;
   int e_w = 0;
+  float l1max = 0.f;  // max over output channels of sum |w| (bounds |conv output| by l1max * max|input| + bmax)
+  float bmax = 0.f;   // max |bias|
   int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, cout_pad_tc = 0, k = 0;
 };
 
@@ -122,6 +124,8 @@ struct dvc_ctx {
   // default: tensor cores with fp32-class accuracy (3xTF32); DVC_MATH_FP32 selects the exact CUDA-core engines
   int conv_math = DVC_MATH_TF32X3, corr_math = DVC_MATH_FP16X3;
   int tc_kbytes = 128;    // tensor-core convolutions: K bytes per pipeline stage (64 or 128, see conv_tc.cu)
+  ScaleCell* cell_next = nullptr;
+  int cell_left = 0;
   int tc_f16 = 1;         // tensor-core convolutions: fp16 hi/lo planes for layers with provably bounded inputs
   std::unordered_map<std::string, float> vec_absmax[3];  // max |scale| of the *_ss vectors
   int tc_cluster = 1;     // tensor-core convolutions: 2 = 2-CTA clusters with multicast weight tiles
@@ -238,6 +242,7 @@ static int stats_begin(dvc_ctx* c, cudaStream_t s, int arena = 0) {
   c->stats_lo = arena ? need / 2 : 0;
   c->stats_hi = arena ? need : need / 2;
   c->stats_used = c->stats_lo;
+  c->cell_left = 0;
   return DVC_OK;
 }
 static int stats_alloc(dvc_ctx* c, int B, int C, double** out, cudaStream_t s) {
@@ -246,6 +251,18 @@ static int stats_alloc(dvc_ctx* c, int B, int C, double** out, cudaStream_t s) {
   *out = c->stats + c->stats_used;
   c->stats_used += n;
   CUDA_TRY(c, cudaMemsetAsync(*out, 0, n * sizeof(double), s));
+  return DVC_OK;
+}
+
+// device scale cells (dvc_internal.cuh: ScaleCell) come out of the statistics arena in chunks of 128, one memset each
+static int cell_alloc(dvc_ctx* c, ScaleCell** out, cudaStream_t s) {
+  if (c->cell_left == 0) {
+    double* blk;
+    DVC_TRY(stats_alloc(c, 1, 64, &blk, s));  // 128 doubles = 128 cells of 8 bytes
+    c->cell_next = (ScaleCell*)blk, c->cell_left = 128;
+  }
+  *out = c->cell_next++;
+  c->cell_left--;
   return DVC_OK;
 }
 
@@ -268,6 +285,20 @@ static int upload_w16(dvc_ctx* c, const std::vector<float>& full, ConvW& w) {
   float amax = 0.f;
   for (float v : full) amax = fmaxf(amax, fabsf(v));
   w.e_w = e16_for(amax);
+  {  // rows of `full` are [tap][cout][cin]: L1 norm per output channel
+    const size_t cin = (size_t)w.cin_pad, cpt = (size_t)w.cout_pad_tc, taps = full.size() / (cin * cpt);
+    std::vector<double> l1(cpt, 0.0);
+    for (size_t t = 0; t < taps; ++t)
+      for (size_t o = 0; o < cpt; ++o) {
+        const float* r = &full[(t * cpt + o) * cin];
+        double sacc = 0;
+        for (size_t i = 0; i < cin; ++i) sacc += fabs((double)r[i]);
+        l1[o] += sacc;
+      }
+    double m = 0;
+    for (double v : l1) m = fmax(m, v);
+    w.l1max = (float)(m * (1.0 + 1e-6));
+  }
   std::vector<unsigned short> hi, lo;
   host_split16(full, w.e_w, hi, lo);
   if (w.w16_hi) cudaFree(w.w16_hi);
@@ -331,6 +362,15 @@ extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const floa
       CUDA_TRY(c, cudaMemset(cw.b, 0, cout_pad * sizeof(float)));
     }
     cw.cin = ci, cw.cin_pad = cin_pad, cw.cout = co, cw.cout_pad = cout_pad, cw.k = kh;
+    {
+      double m = 0;
+      for (int o = 0; o < co; ++o) {
+        double sacc = 0;
+        for (size_t i = 0; i < (size_t)ci * taps; ++i) sacc += fabs((double)h[(size_t)o * ci * taps + i]);
+        m = fmax(m, sacc);
+      }
+      cw.l1max = (float)(m * (1.0 + 1e-6));
+    }
     if (cw.wt_hi) cudaFree(cw.wt_hi);
     if (cw.wt_lo) cudaFree(cw.wt_lo);
     cw.wt_hi = cw.wt_lo = nullptr;
@@ -385,6 +425,7 @@ extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const floa
           CUDA_TRY(c, cudaMemcpy(pw.wt_hi, phi_.data(), phi_.size() * sizeof(float), cudaMemcpyHostToDevice));
           CUDA_TRY(c, cudaMemcpy(pw.wt_lo, plo.data(), plo.size() * sizeof(float), cudaMemcpyHostToDevice));
           pw.cin = ci, pw.cin_pad = cin_pad, pw.cout = co, pw.cout_pad = cout_pad, pw.cout_pad_tc = cpt, pw.k = 2;
+          pw.cin_pad = cin_pad, pw.cout_pad_tc = cpt;
           DVC_TRY(upload_w16(c, pfull, pw));
           pw.b = nullptr;  // shares the bias of the 3x3 convolution (resolved at launch)
           pw.w = nullptr;
@@ -392,8 +433,11 @@ extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const floa
       }
     }
     auto hb = c->host_bias[net].find(base);
-    if (hb != c->host_bias[net].end())
+    cw.bmax = 0.f;
+    if (hb != c->host_bias[net].end()) {
       CUDA_TRY(c, cudaMemcpy(cw.b, hb->second.data(), hb->second.size() * sizeof(float), cudaMemcpyHostToDevice));
+      for (float v : hb->second) cw.bmax = fmaxf(cw.bmax, fabsf(v));
+    }
     return DVC_OK;
   }
   if (ndim == 1 && ends_with(key, ".bias")) {
@@ -403,6 +447,8 @@ extern "C" int dvc_set_weight(dvc_ctx* c, int net, const char* key_c, const floa
     if (it != c->conv[net].end() && it->second.b) {
       if ((int)n > it->second.cout_pad) return fail(c, DVC_ERR_SHAPE, "bias longer than its weight: " + key);
       CUDA_TRY(c, cudaMemcpy(it->second.b, h.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+      it->second.bmax = 0.f;
+      for (float v : h) it->second.bmax = fmaxf(it->second.bmax, fabsf(v));
     }
     if (base == "conv10_ab") {
       float*& d = c->vec[net]["conv10_ab.bias"];
@@ -451,7 +497,29 @@ struct ConvOpt {
   const Act* add = nullptr;
   double* stats = nullptr;
   int yCoff = 0;
+  float l1_override = 0.f;  // > 0: weight L1 bound shared by the four phase launches of one up-convolution
 };
+
+// scale bookkeeping of a convolution whose output records max |y| (y.cell) and possibly stores fp16 planes (y.h16)
+static int fill_dyn(dvc_ctx* c, const ConvW* w, const Act& x, const Act& y, const ConvOpt& o, DynOut* d) {
+  *d = DynOut();
+  if (x.cell) d->cell_in = x.cell;
+  if (!y.cell) return DVC_OK;
+  d->cell_out = y.cell;
+  if (!y.h16) return DVC_OK;
+  if (y.d) return fail(c, DVC_ERR_STATE, "conv: device-scaled output with an fp32 plane");
+  d->h16 = y.h16, d->l16 = y.l16;
+  if (!x.cell) d->in_bound = x.h16 ? ldexpf(32768.0f, -x.e16) : 0.f;
+  if (!x.cell && !x.h16) return fail(c, DVC_ERR_STATE, "conv: device-scaled output needs a bounded input");
+  if (o.add) {
+    if (!o.add->cell) return fail(c, DVC_ERR_STATE, "conv: device-scaled output needs the addend's max");
+    d->cell_add = o.add->cell;
+  }
+  d->w_l1 = o.l1_override > 0.f ? o.l1_override : w->l1max;
+  d->b_max = w->bmax;
+  d->gain = o.act == ACT_LRELU ? fmaxf(1.f, fabsf(o.slope)) : 1.f;
+  return DVC_OK;
+}
 
 static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const ConvOpt& o, cudaStream_t s) {
   if (x.C != w->cin_pad) return fail(c, DVC_ERR_SHAPE, "conv: input channel mismatch");
@@ -479,7 +547,9 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     if (!w->wt_hi || (f16 && !w->w16_hi)) return fail(c, DVC_ERR_STATE, "conv: split input but no tensor-core weights");
     ConvTcParams t{};
     t.f16 = f16 ? 1 : 0;
-    t.out_scale = f16 ? ldexpf(1.0f, -(x.e16 + w->e_w)) : 1.0f;
+    t.out_scale = f16 ? ldexpf(1.0f, -((x.cell ? 0 : x.e16) + w->e_w)) : 1.0f;
+    if ((y.h16 || y.cell) && !f16) return fail(c, DVC_ERR_STATE, "conv: device-scaled outputs need the fp16 engine");
+    DVC_TRY(fill_dyn(c, w, x, y, o, &t.dyn));
     t.Hp = p.Hp, t.Wp = p.Wp, t.P = p.P, t.H = p.H, t.W = p.W, t.Cin = p.Cin, t.Mtot = x.B * p.Hp * p.Wp;
     t.taps = taps, t.stride = o.stride, t.Cout = w->cout, t.CoutPad = w->cout_pad_tc, t.bias = w->b;
     t.oscale = 1, t.oa = 0, t.ob = 0;
@@ -531,6 +601,12 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
   if (o.add && o.add->lo) return fail(c, DVC_ERR_STATE, "conv: CUDA-core kernel cannot read a split addend");
   // tensor-core mode: the two K = 27 / 63 first layers use the per-pixel kernel (the fp32 parity mode keeps the
   // two-level GEMM kernel for every layer)
+  if (y.h16 || y.cell) {
+    if (!x.cell) return fail(c, DVC_ERR_STATE, "conv: first layer needs the input's max");
+    DVC_TRY(fill_dyn(c, w, x, y, o, &p.dyn));
+    if (!launch_conv_first(p, x.B, w->cin, s)) return fail(c, DVC_ERR_STATE, "conv: device-scaled outputs need the first-layer kernel");
+    return check_launch(c, "conv_first");
+  }
   if (tc_mode(c) && launch_conv_first(p, x.B, w->cin, s)) return check_launch(c, "conv_first");
   launch_conv_simt(p, x.B, c->two_level, s);
   return check_launch(c, "conv");
@@ -574,6 +650,10 @@ static int run_pixnorm(dvc_ctx* c, const Act& src, float* dst, float* dst_lo, in
   if (src.C != 128 && src.C != 256 && src.C != 512) return fail(c, DVC_ERR_SHAPE, "pixnorm: channel count");
   PixNormParams p{};
   p.src = src.d, p.src_lo = src.lo, p.sH = src.H, p.sW = src.W, p.sP = src.P, p.sC = src.C;
+  if (src.h16 && !src.d) {
+    if (!src.cell) return fail(c, DVC_ERR_STATE, "pixnorm: fp16 source without a scale cell");
+    p.src_h16 = src.h16, p.src_l16 = src.l16, p.src_cell = src.cell;
+  }
   p.dst = dst, p.dst_lo = dst_lo, p.dP = dP, p.dC = src.C, p.C = src.C, p.pad_mode = pad_mode;
   p.dst_h16 = h16, p.dst_l16 = l16, p.dscale16 = ldexpf(1.0f, e16);
   p.stats = stats, p.count = count, p.eps = 2.220446049250313e-16f;  // sys.float_info.epsilon
@@ -596,21 +676,36 @@ static const char* kVggSeq[] = {"conv1_1", "conv1_2", "P", "conv2_1", "conv2_2",
 static int vgg_trunk(dvc_ctx* c, const std::string& tag, const Act& x0, const std::string& last_key, VggMaps* out,
                      cudaStream_t s) {
   Act cur = x0;
+  // tensor-core mode: the whole conv -> ReLU -> conv trunk lives on fp16 hi/lo planes whose exact power-of-two scale
+  // each layer derives on the device from the measured max |input| and its weights' L1 norm (DynOut)
+  const bool dyn = tc_mode(c) && c->tc_f16;
+  const int mode = dyn ? 2 : (tc_mode(c) ? 1 : 0);
+  if (dyn) {
+    DVC_TRY(cell_alloc(c, &cur.cell, s));
+    launch_amax(cur.d, cur.elems(), cur.cell, s);
+    DVC_TRY(check_launch(c, "amax"));
+  }
   int block = 1, idx = 1;
   for (const char* name : kVggSeq) {
     std::string key;
     Act nxt;
     if (name[0] == 'P') {
       key = "p" + std::to_string(block);
-      DVC_TRY(get_act(c, tag + "." + key, cur.B, cur.H / 2, cur.W / 2, cur.C, 1, &nxt, s, tc_mode(c)));
-      launch_maxpool2(cur.d, cur.lo, cur.H, cur.W, cur.P, cur.C, nxt.d, nxt.lo, 1, cur.B, s);
+      DVC_TRY(get_act(c, tag + "." + key, cur.B, cur.H / 2, cur.W / 2, cur.C, 1, &nxt, s, mode));
+      if (dyn) {
+        DVC_TRY(cell_alloc(c, &nxt.cell, s));
+        launch_maxpool2_h16(cur.h16, cur.l16, cur.cell, cur.H, cur.W, cur.P, cur.C, nxt.h16, nxt.l16, nxt.cell, 1, cur.B, s);
+      } else {
+        launch_maxpool2(cur.d, cur.lo, cur.H, cur.W, cur.P, cur.C, nxt.d, nxt.lo, 1, cur.B, s);
+      }
       DVC_TRY(check_launch(c, "maxpool"));
       block++, idx = 1;
     } else {
       key = "r" + std::to_string(block) + std::to_string(idx);
       const ConvW* w;
       DVC_TRY(need_conv(c, DVC_NET_VGG, name, &w));
-      DVC_TRY(get_act(c, tag + "." + key, cur.B, cur.H, cur.W, w->cout, 1, &nxt, s, tc_mode(c)));
+      DVC_TRY(get_act(c, tag + "." + key, cur.B, cur.H, cur.W, w->cout, 1, &nxt, s, mode));
+      if (dyn) DVC_TRY(cell_alloc(c, &nxt.cell, s));
       ConvOpt o;
       o.act = ACT_RELU;
       DVC_TRY(run_conv(c, w, cur, nxt, o, s));
@@ -777,13 +872,17 @@ static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* o
   const int net = DVC_NET_COLOR;
   const int B = in0.B, H = in0.H, W = in0.W;
   int uid = 0;
+  const bool dyn = tc_mode(c) && c->tc_f16;
   auto conv = [&](const char* name, const Act& x, Act* y, int outP, int act, int dil, const Act* add, double** st,
                   float slope) -> int {
     const ConvW* w;
     DVC_TRY(need_conv(c, net, name, &w));
     // outputs with a border (outP > 0) feed another convolution: hi/lo planes in tensor-core mode
+    // ... fp16 planes with a device-derived scale when the fp16 engine is on (conv -> ReLU -> conv chains)
+    const bool tcx = x.lo || x.h16;  // this launch runs on the tensor-core engine
     DVC_TRY(get_act(c, tag + "." + name + "#" + std::to_string(uid++), x.B, x.H, x.W, w->cout, outP, y, s,
-                    tc_mode(c) && outP > 0));
+                    (tc_mode(c) && outP > 0) ? (dyn ? 2 : 1) : 0));
+    if (dyn && (tcx || outP > 0)) DVC_TRY(cell_alloc(c, &y->cell, s));
     ConvOpt o;
     o.act = act, o.dil = dil, o.add = add, o.slope = slope;
     if (st) {
@@ -808,17 +907,26 @@ static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* o
   auto upconv = [&](const char* name, const Act& raw, const double* st, const Act* add, Act* y) -> int {
     const ConvW* w;
     DVC_TRY(need_conv(c, net, name, &w));
-    DVC_TRY(get_act(c, tag + "." + name + "#" + std::to_string(uid++), B, raw.H * 2, raw.W * 2, w->cout, 1, y, s, tc_mode(c)));
+    DVC_TRY(get_act(c, tag + "." + name + "#" + std::to_string(uid++), B, raw.H * 2, raw.W * 2, w->cout, 1, y, s,
+                    tc_mode(c) ? (dyn ? 2 : 1) : 0));
     if (tc_mode(c)) {
       Act nl;
       DVC_TRY(norm((std::string(name) + ".in").c_str(), raw, st, &nl, 1, 1, 1, nullptr));
+      float l1 = 0.f;  // one exponent for the four phases that fill the same tensor
+      if (dyn) {
+        DVC_TRY(cell_alloc(c, &y->cell, s));
+        for (int ph = 0; ph < 4; ++ph) {
+          auto it = c->conv[net].find(std::string(name) + "#p" + std::to_string(ph));
+          if (it != c->conv[net].end()) l1 = fmaxf(l1, it->second.l1max);
+        }
+      }
       for (int ph = 0; ph < 4; ++ph) {
         auto it = c->conv[net].find(std::string(name) + "#p" + std::to_string(ph));
         if (it == c->conv[net].end() || !it->second.wt_hi || !it->second.w16_hi) return fail(c, DVC_ERR_STATE, std::string("phase weights missing: ") + name);
         ConvW pw = it->second;
-        pw.b = w->b;
+        pw.b = w->b, pw.bmax = w->bmax;
         ConvOpt o;
-        o.act = ACT_RELU, o.add = add, o.phase = ph;
+        o.act = ACT_RELU, o.add = add, o.phase = ph, o.l1_override = l1;
         DVC_TRY(run_conv(c, &pw, nl, *y, o, s));
       }
       return DVC_OK;
@@ -838,7 +946,13 @@ static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* o
 
   Act a, b, raw1, n1, d1, raw2, n2, d2, raw3, n3, d3, raw4, n4, raw5, n5, raw6, n6, raw7, t, u;
   double *st1, *st2, *st3, *st4, *st5, *st6, *st7, *st8, *st9;
-  DVC_TRY(conv("conv1_1.0", in0, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
+  Act xin = in0;
+  if (dyn) {
+    DVC_TRY(cell_alloc(c, &xin.cell, s));
+    launch_amax(xin.d, xin.elems(), xin.cell, s);
+    DVC_TRY(check_launch(c, "amax"));
+  }
+  DVC_TRY(conv("conv1_1.0", xin, &a, 1, ACT_RELU, 1, nullptr, nullptr, 0));
   DVC_TRY(conv("conv1_1.2", a, &b, 1, ACT_RELU, 1, nullptr, nullptr, 0));
   DVC_TRY(conv("conv1_2", b, &raw1, 0, ACT_RELU, 1, nullptr, &st1, 0));
   DVC_TRY(norm("n1", raw1, st1, &n1, 1, 1, 1, nullptr));
@@ -1079,6 +1193,7 @@ extern "C" int dvc_vgg19_forward(dvc_ctx* c, const float* x, int B, int H, int W
   }
   if (deepest < 0) return fail(c, DVC_ERR_ARG, "vgg19_forward: unknown out_key");
   Act x0;
+  DVC_TRY(stats_begin(c, s));
   DVC_TRY(get_act(c, "mvgg.x0", B, H, W, 8, 1, &x0, s));
   launch_nchw_to_act(x, 3, x0.d, nullptr, B, H, W, 8, 1, PAD_ZERO, preprocess ? 1 : 0, s);
   DVC_TRY(check_launch(c, "nchw_to_act"));
@@ -1088,7 +1203,10 @@ extern "C" int dvc_vgg19_forward(dvc_ctx* c, const float* x, int B, int H, int W
     auto it = maps.m.find(keys[i] ? keys[i] : "");
     if (it == maps.m.end()) return fail(c, DVC_ERR_ARG, std::string("vgg19_forward: unknown out_key ") + (keys[i] ? keys[i] : "(null)"));
     const Act& a = it->second;
-    launch_act_to_nchw(a.d, a.lo, a.H, a.W, a.P, a.C, 0, a.C, outs[i], B, s);
+    if (a.h16)
+      launch_act_to_nchw_h16(a.h16, a.l16, a.cell, a.H, a.W, a.P, a.C, a.C, outs[i], B, s);
+    else
+      launch_act_to_nchw(a.d, a.lo, a.H, a.W, a.P, a.C, 0, a.C, outs[i], B, s);
     DVC_TRY(check_launch(c, "act_to_nchw"));
   }
   return DVC_OK;

@@ -14,6 +14,49 @@
 
 namespace dvc {
 
+// Device-side scale record of an fp16-plane activation whose range is only known at run time (conv -> ReLU -> conv
+// chains).  The producer derives a rigorous bound of its outputs from the measured max |input| and the L1 norm of its
+// weights, stores planes of value * 2^e, and leaves the measured max |output| for the next layer.
+struct ScaleCell {
+  unsigned int amax_bits;  // float bits of max |value| (non-negative floats order like unsigned ints), atomicMax
+  int e;                   // exponent the planes were written with
+};
+
+struct DynOut {
+  void* h16 = nullptr;                 // fp16 hi / lo output planes (same geometry as the fp32 destination) or nullptr
+  void* l16 = nullptr;
+  ScaleCell* cell_out = nullptr;       // max |output| (always, when set) and the exponent used (when h16 is set)
+  const ScaleCell* cell_in = nullptr;  // dynamic input: exponent of its planes and its max |value| ...
+  float in_bound = 0.f;                // ... or a static bound of |input|
+  const ScaleCell* cell_add = nullptr;
+  float add_bound = 0.f;
+  float w_l1 = 0.f, b_max = 0.f, gain = 1.f;  // max_o sum |w[o]|, max |bias|, max(1, |activation slope|)
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float exp2_int(int e) { return __int_as_float((127 + e) << 23); }  // e in [-126, 127]
+// largest e with bound * 2^e <= 2^15 (fp16 max is 65504: one binade of slack), clamped
+__device__ __forceinline__ int e16_from_bound(float bound) {
+  if (!(bound > 0.f)) return 24;
+  if (!(bound < 3.0e38f)) return -100;
+  int ex;
+  (void)frexpf(bound, &ex);  // bound = m * 2^ex, m in [0.5, 1)  ->  bound <= 2^ex
+  const int e = 15 - ex;
+  return e > 24 ? 24 : (e < -100 ? -100 : e);
+}
+__device__ __forceinline__ int dyn_out_exponent(const DynOut& d) {
+  const float ain = d.cell_in ? __uint_as_float(d.cell_in->amax_bits) : d.in_bound;
+  const float aadd = d.cell_add ? __uint_as_float(d.cell_add->amax_bits) : d.add_bound;
+  const float bound = (fmaf(ain, d.w_l1, d.b_max) + aadd) * d.gain * 1.0001f;
+  return e16_from_bound(bound);
+}
+__device__ __forceinline__ void warp_amax_commit(float amax, ScaleCell* cell) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+  if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(&cell->amax_bits, __float_as_uint(amax));
+}
+#endif
+
 struct Act {
   float* d = nullptr;   // pixel (b=0, yp=0, xp=0), channel 0; the hi plane when lo != nullptr
   float* lo = nullptr;  // lo plane of a tf32 hi/lo split activation (value = hi + lo), same geometry
@@ -21,6 +64,7 @@ struct Act {
   void* h16 = nullptr;
   void* l16 = nullptr;
   int e16 = 0;
+  ScaleCell* cell = nullptr;  // set: e16 is unused, the exponent (and max |value|) live on the device
   int B = 0, H = 0, W = 0, C = 0, P = 0;
   int Hp() const { return H + 2 * P; }
   int Wp() const { return W + 2 * P; }
@@ -48,6 +92,7 @@ struct ConvParams {
   int act;
   float slope;
   double* stats;  // optional [B][Cout][2] (sum, sum of squares) of the stored values
+  DynOut dyn;     // fp16 output planes with a device-derived scale (first layers in tensor-core mode)
 };
 
 void launch_conv_simt(const ConvParams& p, int B, bool two_level, cudaStream_t s);
@@ -83,6 +128,9 @@ void launch_xform(const XformParams& p, int B, cudaStream_t s);
 struct PixNormParams {
   const float* src;
   const float* src_lo;
+  const void* src_h16;  // fp16 hi/lo source planes of value * 2^(src_cell->e) (src may be nullptr then)
+  const void* src_l16;
+  const ScaleCell* src_cell;
   int sH, sW, sP, sC;
   float* dst;
   float* dst_lo;
@@ -107,6 +155,14 @@ void launch_act_to_nchw(const float* src, const float* src_lo, int H, int W, int
                         int B, cudaStream_t s);
 void launch_maxpool2(const float* src, const float* src_lo, int sH, int sW, int sP, int C, float* dst, float* dst_lo,
                      int dP, int B, cudaStream_t s);
+// the same two on fp16 hi/lo planes with a device-side exponent (cell_out := cell_in for the pool: max-pooling
+// non-negative values keeps both the scale and the max)
+void launch_act_to_nchw_h16(const void* h16, const void* l16, const ScaleCell* cell, int H, int W, int P, int sC, int C,
+                            float* dst, int B, cudaStream_t s);
+void launch_maxpool2_h16(const void* h16, const void* l16, const ScaleCell* cell_in, int sH, int sW, int sP, int C,
+                         void* dh16, void* dl16, ScaleCell* cell_out, int dP, int B, cudaStream_t s);
+// max |x| over n floats -> cell->amax_bits (cell zeroed by the caller's arena)
+void launch_amax(const float* x, size_t n, ScaleCell* cell, cudaStream_t s);
 // NCHW [B][3][H][W] -> V [B][H/4*W/4][4] (4th lane zero): F.avg_pool2d(.,4), NonlocalNet.py:491-493
 void launch_avgpool4_lab(const float* src, float* V, int B, int H, int W, cudaStream_t s);
 // y rows [B][N][4], sim rows [B][N] at h x w -> nearest x4 NCHW (NonlocalNet.py:499-500)

@@ -53,6 +53,14 @@ __device__ __forceinline__ void st4h(__half* __restrict__ hp, __half* __restrict
   *reinterpret_cast<uint2*>(lp + off) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
 }
 
+// 4 channels of an fp16 hi/lo activation, in scaled units (hi + lo is exact in fp32: 2 x 11 significant bits)
+__device__ __forceinline__ float4 ld4h(const __half* __restrict__ hp, const __half* __restrict__ lp, size_t off) {
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(hp + off)), l = __ldg(reinterpret_cast<const uint2*>(lp + off));
+  const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+  const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+  return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+}
+
 __device__ __forceinline__ int reflect_idx(int i, int n) {
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;
@@ -138,6 +146,7 @@ __global__ void __launch_bounds__(256) pixnorm_kernel(const PixNormParams p) {
   const int dHp = p.sH + 2 * p.dP, dWp = p.sW + 2 * p.dP;
   const int sHp = p.sH + 2 * p.sP, sWp = p.sW + 2 * p.sP;
   const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+  const float descale = p.src_h16 ? exp2_int(-p.src_cell->e) : 1.f;
   float4 mean[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
@@ -164,7 +173,12 @@ __global__ void __launch_bounds__(256) pixnorm_kernel(const PixNormParams p) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       if (inside) {
-        v[i] = ld4(p.src, p.src_lo, so + (i * 32 + lane) * 4);
+        if (p.src_h16) {
+          v[i] = ld4h(reinterpret_cast<const __half*>(p.src_h16), reinterpret_cast<const __half*>(p.src_l16), so + (i * 32 + lane) * 4);
+          v[i].x *= descale, v[i].y *= descale, v[i].z *= descale, v[i].w *= descale;
+        } else {
+          v[i] = ld4(p.src, p.src_lo, so + (i * 32 + lane) * 4);
+        }
         v[i].x -= mean[i].x, v[i].y -= mean[i].y, v[i].z -= mean[i].z, v[i].w -= mean[i].w;
       } else {
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -321,6 +335,73 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__
     }
     st4(dst, dst_lo, ((size_t)b * dHp * dWp + pix) * C + c, v);
   }
+}
+
+// the two kernels above for fp16 hi/lo planes with a device-side exponent
+__global__ void __launch_bounds__(256) act_to_nchw_h16_kernel(const __half* __restrict__ hp, const __half* __restrict__ lp,
+                                                              const ScaleCell* __restrict__ cell, int H, int W, int P, int sC,
+                                                              int C, float* __restrict__ dst) {
+  __shared__ float t[32][33];
+  const float descale = exp2_int(-cell->e);
+  const int b = blockIdx.z;
+  const int Hp = H + 2 * P, Wp = W + 2 * P;
+  const int pix0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int pix = pix0 + r;
+    float v = 0.f;
+    if (pix < H * W && c0 + tx < C) {
+      const int y = pix / W, x = pix - y * W;
+      const size_t o = (((size_t)b * Hp + y + P) * Wp + x + P) * sC + c0 + tx;
+      v = (__half2float(hp[o]) + __half2float(lp[o])) * descale;
+    }
+    t[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, pix = pix0 + tx;
+    if (c < C && pix < H * W) dst[((size_t)b * C + c) * H * W + pix] = t[tx][r];
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool2_h16_kernel(const __half* __restrict__ hp, const __half* __restrict__ lp,
+                                                           const ScaleCell* __restrict__ cell_in, int sH, int sW, int sP, int C,
+                                                           __half* __restrict__ dh, __half* __restrict__ dl,
+                                                           ScaleCell* __restrict__ cell_out, int dP) {
+  const int b = blockIdx.y;
+  if (b == 0 && blockIdx.x == 0 && threadIdx.x == 0) *cell_out = *cell_in;  // same scale, same max (values are >= 0)
+  const int dH = sH / 2, dW = sW / 2;
+  const int dHp = dH + 2 * dP, dWp = dW + 2 * dP, sHp = sH + 2 * sP, sWp = sW + 2 * sP;
+  const int c4n = C >> 2;
+  const long total = (long)dHp * dWp * c4n;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c4n) * 4;
+    const int pix = (int)(idx / c4n);
+    const int yp = pix / dWp, xp = pix - yp * dWp;
+    const int y = yp - dP, x = xp - dP;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y >= 0 && y < dH && x >= 0 && x < dW) {
+      const size_t so = (((size_t)b * sHp + 2 * y + sP) * sWp + 2 * x + sP) * C + c;
+      const float4 a = ld4h(hp, lp, so);
+      const float4 b4 = ld4h(hp, lp, so + C);
+      const float4 c4 = ld4h(hp, lp, so + (size_t)sWp * C);
+      const float4 d = ld4h(hp, lp, so + (size_t)sWp * C + C);
+      v.x = fmaxf(fmaxf(a.x, b4.x), fmaxf(c4.x, d.x));
+      v.y = fmaxf(fmaxf(a.y, b4.y), fmaxf(c4.y, d.y));
+      v.z = fmaxf(fmaxf(a.z, b4.z), fmaxf(c4.z, d.z));
+      v.w = fmaxf(fmaxf(a.w, b4.w), fmaxf(c4.w, d.w));
+    }
+    st4h(dh, dl, ((size_t)b * dHp * dWp + pix) * C + c, v, 1.f);  // re-splitting hi + lo is exact
+  }
+}
+
+__global__ void __launch_bounds__(256) amax_kernel(const float4* __restrict__ x, size_t n4, ScaleCell* __restrict__ cell) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  warp_amax_commit(m, cell);
 }
 
 __global__ void __launch_bounds__(256) avgpool4_lab_kernel(const float* __restrict__ src, float* __restrict__ V, int H,
@@ -538,6 +619,28 @@ void launch_maxpool2(const float* src, const float* src_lo, int sH, int sW, int 
   const long total = (long)(sH / 2 + 2 * dP) * (sW / 2 + 2 * dP) * (C / 4);
   dim3 grid(grid_for(total, 256), B);
   maxpool2_kernel<<<grid, 256, 0, s>>>(src, src_lo, sH, sW, sP, C, dst, dst_lo, dP);
+  launch_counter_add(1);
+}
+
+void launch_act_to_nchw_h16(const void* h16, const void* l16, const ScaleCell* cell, int H, int W, int P, int sC, int C,
+                            float* dst, int B, cudaStream_t s) {
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
+  act_to_nchw_h16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(h16), reinterpret_cast<const __half*>(l16), cell, H, W,
+                                              P, sC, C, dst);
+  launch_counter_add(1);
+}
+
+void launch_maxpool2_h16(const void* h16, const void* l16, const ScaleCell* cell_in, int sH, int sW, int sP, int C, void* dh16,
+                         void* dl16, ScaleCell* cell_out, int dP, int B, cudaStream_t s) {
+  const long total = (long)(sH / 2 + 2 * dP) * (sW / 2 + 2 * dP) * (C / 4);
+  dim3 grid(grid_for(total, 256), B);
+  maxpool2_h16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(h16), reinterpret_cast<const __half*>(l16), cell_in, sH, sW,
+                                           sP, C, reinterpret_cast<__half*>(dh16), reinterpret_cast<__half*>(dl16), cell_out, dP);
+  launch_counter_add(1);
+}
+
+void launch_amax(const float* x, size_t n, ScaleCell* cell, cudaStream_t s) {
+  amax_kernel<<<(unsigned)grid_for((long)(n / 4), 256), 256, 0, s>>>(reinterpret_cast<const float4*>(x), n / 4, cell);
   launch_counter_add(1);
 }
 
