@@ -204,8 +204,8 @@ def main():
                     help="1: convolutions with bounded inputs run 3xFP16 on scaled planes; 0: 3xTF32 everywhere")
     ap.add_argument("--tc-splits", type=int, default=int(os.environ.get("DVC_TC_SPLITS", "1")),
                     help="split-K of the conv engine: 1 off (default), 0 automatic")
-    ap.add_argument("--tc-cluster", type=int, default=int(os.environ.get("DVC_TC_CLUSTER", "1")), choices=[1, 2],
-                    help="2 = 2-CTA clusters with TMA-multicast weight tiles in the conv engine")
+    ap.add_argument("--tc-cluster", type=int, default=int(os.environ.get("DVC_TC_CLUSTER", "2")), choices=[1, 2],
+                    help="2 = CTA pairs (tcgen05.mma.cta_group::2) in the conv engine, 1 = single CTAs")
     ap.add_argument("--cpu-sample", type=int, default=2, help="frames timed for cpu_baseline (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup

@@ -35,11 +35,12 @@ constexpr int NTHREADS = 384;  // warpgroup 0: warp 0 TMA, warp 1 MMA (2, 3 idle
 // A stage can be refilled only after its MMAs retire, so with S stages only S-1 refills are in flight while one
 // stage computes: at ~2.5 us TMA latency two 96 KB stages keep the tensor pipe ~60 % busy; the same shared memory
 // as four 48 KB stages hides the latency.
-template <int BN, int KBY>
+// CL = 2 (CTA pair): each CTA stages only its half of the channel rows, so the same shared memory holds more stages.
+template <int BN, int KBY, int CL>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) * (128 / KBY);
+  static constexpr int STAGES = (CL == 2 ? (BN == 256 ? 3 : 4) : (BN == 256 ? 2 : (BN == 128 ? 3 : 4))) * (128 / KBY);
   static constexpr int A_BYTES = BM * KBY;
-  static constexpr int B_BYTES = BN * KBY;
+  static constexpr int B_BYTES = (BN / CL) * KBY;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int NBUF = 512 / BN;  // TMEM accumulators (2 / 4 / 8): deeper ring hides the flush round trip
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + 8 * BN * 4;  // + barriers + statistics [4][2][BN]
@@ -51,9 +52,12 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
-// CL = 2: the kernel runs as 2-CTA clusters on adjacent pixel tiles of the same channel tile; each CTA fetches half
-// of every weight tile and TMA-multicasts it to both, which cuts the L2 -> SM operand traffic by a third (BN = 256)
-// to a half (BN = 64).  MMAs stay per-CTA (cta_group::1); a stage is released to both producers by a multicast commit.
+// CL = 2: the kernel runs as CTA pairs (cta_group::2) on adjacent pixel tiles of the same channel tile.  The 3 MMAs
+// per k-step of the operand split re-read both operands from shared memory, which makes a single CTA shared-memory
+// bound (BN = 256: 96 KB of TMA writes + 144 KB of MMA reads per 1536 tensor cycles = 156 B/clk against 128 B/clk;
+// BN = 128: 208 B/clk).  In a pair each CTA stages its own 128 pixel rows and only HALF of the channel rows; the
+// leader's tcgen05.mma.cta_group::2 computes the 256 x BN tile from both shared memories (104 / 156 B/clk).  Both
+// producers' TMA bytes are counted on the leader's full barrier; the leader's commits multicast to both CTAs.
 // F16: operands are fp16 hi/lo planes of x * 2^e (e static per tensor / layer, chosen from a proven bound so that
 // nothing overflows): the same 2 x 11 significant bits as the tf32 split at twice the MMA rate, half the operand
 // bytes and half as many truncating accumulations per unit of K; the epilogue multiplies by 2^-(e_x + e_w) (exact).
@@ -61,10 +65,10 @@ template <int BN, int CL, int KBY, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                    const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const ConvTcParams p) {
-  using C = Cfg<BN, KBY>;
+  using C = Cfg<BN, KBY, CL>;
   constexpr int A_BYTES = C::A_BYTES;
   constexpr int KE = F16 ? KBY / 2 : KBY / 4;  // K elements per stage
-  constexpr uint32_t IDESC = tc::umma_idesc(F16 ? 0u : 2u, BM, BN);
+  constexpr uint32_t IDESC = tc::umma_idesc(F16 ? 0u : 2u, BM * CL, BN);
   constexpr int CPT = BN / 2;  // output channels per epilogue thread (two warps share a TMEM lane quarter)
 
   extern __shared__ uint8_t smem_raw[];
@@ -104,17 +108,23 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc::tma_prefetch_desc(&tmXl);
     tc::tma_prefetch_desc(&tmWh);
     tc::tma_prefetch_desc(&tmWl);
-    for (int i = 0; i < C::STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], CL);
-    for (int i = 0; i < C::NBUF; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 8);
+    for (int i = 0; i < C::STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
+    for (int i = 0; i < C::NBUF; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 8 * CL);  // pair: both epilogues
     tc::fence_barrier_init();
   }
+  if (CL == 2) tc::cluster_sync_all();  // both CTAs are resident before the pair allocation
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, 512);
-    tc::tmem_relinquish();
+    if (CL == 2) {
+      tc::tmem_alloc_pair(tmem_slot, 512);
+      tc::tmem_relinquish_pair();
+    } else {
+      tc::tmem_alloc(tmem_slot, 512);
+      tc::tmem_relinquish();
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (CL == 2) tc::cluster_sync_all();  // the peer's barriers must be initialised before any multicast reaches them
+  if (CL == 2) tc::cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive reaches them
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -139,17 +149,19 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           tc::mbar_wait(&empty[stage], phase ^ 1);
           if (tc::elect_one()) {
             uint8_t* st = smem + stage * C::STAGE_BYTES;
-            tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-            tc::tma_load_2d(st, &tmXh, &full[stage], kb * KE, m0 + off);
-            tc::tma_load_2d(st + A_BYTES, &tmXl, &full[stage], kb * KE, m0 + off);
             if (CL == 1) {
+              tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+              tc::tma_load_2d(st, &tmXh, &full[stage], kb * KE, m0 + off);
+              tc::tma_load_2d(st + A_BYTES, &tmXl, &full[stage], kb * KE, m0 + off);
               tc::tma_load_2d(st + 2 * A_BYTES, &tmWh, &full[stage], kb * KE, tap * p.CoutPad + n0);
               tc::tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tmWl, &full[stage], kb * KE, tap * p.CoutPad + n0);
-            } else {  // my half of the channel rows, delivered to both CTAs
+            } else {  // my pixel rows and my half of the channel rows; all bytes are counted by the leader's barrier
+              if (crank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
               const int hrow = crank * (BN / 2);
-              tc::tma_load_2d_mc(st + 2 * A_BYTES + hrow * KBY, &tmWh, &full[stage], kb * KE, tap * p.CoutPad + n0 + hrow, 3);
-              tc::tma_load_2d_mc(st + 2 * A_BYTES + C::B_BYTES + hrow * KBY, &tmWl, &full[stage], kb * KE,
-                                 tap * p.CoutPad + n0 + hrow, 3);
+              tc::tma_load_2d_pair(st, &tmXh, &full[stage], kb * KE, m0 + off);
+              tc::tma_load_2d_pair(st + A_BYTES, &tmXl, &full[stage], kb * KE, m0 + off);
+              tc::tma_load_2d_pair(st + 2 * A_BYTES, &tmWh, &full[stage], kb * KE, tap * p.CoutPad + n0 + hrow);
+              tc::tma_load_2d_pair(st + 2 * A_BYTES + C::B_BYTES, &tmWl, &full[stage], kb * KE, tap * p.CoutPad + n0 + hrow);
             }
           }
           __syncwarp();
@@ -157,8 +169,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer (warp-convergent loop, one elected lane issues) =================
+  } else if (warp == 1 && (CL == 1 || crank == 0)) {
+    // ================= MMA issuer (warp-convergent loop, one elected lane issues; pair: the leader CTA only) ====
     {
       int stage = 0;
       uint32_t phase = 0;
@@ -183,15 +195,23 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
               for (int kk = 0; kk < KBY / 32; ++kk) {
                 const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-                tc::umma_ss<!F16>(d, dXl + adv, dWh + adv, IDESC, (k > ch * kc || kk) ? 1u : 0u);
-                tc::umma_ss<!F16>(d, dXh + adv, dWl + adv, IDESC, 1u);
-                tc::umma_ss<!F16>(d, dXh + adv, dWh + adv, IDESC, 1u);
+                if (CL == 1) {
+                  tc::umma_ss<!F16>(d, dXl + adv, dWh + adv, IDESC, (k > ch * kc || kk) ? 1u : 0u);
+                  tc::umma_ss<!F16>(d, dXh + adv, dWl + adv, IDESC, 1u);
+                  tc::umma_ss<!F16>(d, dXh + adv, dWh + adv, IDESC, 1u);
+                } else {
+                  tc::umma_ss_pair<!F16>(d, dXl + adv, dWh + adv, IDESC, (k > ch * kc || kk) ? 1u : 0u);
+                  tc::umma_ss_pair<!F16>(d, dXh + adv, dWl + adv, IDESC, 1u);
+                  tc::umma_ss_pair<!F16>(d, dXh + adv, dWh + adv, IDESC, 1u);
+                }
               }
-              if (CL == 1)
+              if (CL == 1) {
                 tc::umma_commit(&empty[stage]);
-              else
-                tc::umma_commit_mc(&empty[stage], 3);
-              if (k == k_end - 1) tc::umma_commit(&tfull[buf]);
+                if (k == k_end - 1) tc::umma_commit(&tfull[buf]);
+              } else {  // release the stage to both producers, hand the accumulator to both epilogues
+                tc::umma_commit_pair_mc(&empty[stage], 3);
+                if (k == k_end - 1) tc::umma_commit_pair_mc(&tfull[buf], 3);
+              }
             }
             __syncwarp();
             if (++stage == C::STAGES) stage = 0, phase ^= 1;
@@ -294,7 +314,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         }
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+        if (lane == 0) {
+          if (CL == 1)
+            tc::mbar_arrive(&tempty[buf]);
+          else
+            tc::mbar_arrive_leader(&tempty[buf]);
+        }
       }
 
       if (sp < S - 1) {  // hand the running totals to the next split of this tile
@@ -437,7 +462,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   if (CL == 2) tc::cluster_sync_all();  // no CTA may exit while the peer can still multicast into its shared memory
   if (warp == 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 512);
+    if (CL == 2)
+      tc::tmem_dealloc_pair(tmem_base, 512);
+    else
+      tc::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -446,7 +474,7 @@ int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap&
               const ConvTcParams& p, int num_sms, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<BN, CL, KBY, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, KBY>::SMEM_BYTES) !=
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, CL, KBY, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, KBY, CL>::SMEM_BYTES) !=
         cudaSuccess)
       return -1;
     attr = true;
@@ -456,7 +484,7 @@ int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap&
   const int max_groups = num_sms / CL;
   const int grid = CL * (items < max_groups ? items : max_groups);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<BN, KBY>::SMEM_BYTES, cfg.stream = s;
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<BN, KBY, CL>::SMEM_BYTES, cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;

@@ -128,7 +128,7 @@ struct dvc_ctx {
   int cell_left = 0;
   int tc_f16 = 1;         // tensor-core convolutions: fp16 hi/lo planes for layers with provably bounded inputs
   std::unordered_map<std::string, float> vec_absmax[3];  // max |scale| of the *_ss vectors
-  int tc_cluster = 1;     // tensor-core convolutions: 2 = 2-CTA clusters with multicast weight tiles
+  int tc_cluster = 2;     // tensor-core convolutions: 2 = CTA pairs (tcgen05.mma.cta_group::2), 1 = single CTAs
   int tc_kc = 1;          // tensor-core convolutions: k-blocks per TMEM chunk (see conv_tc.cu)
   bool two_level = true;  // fp32 convolutions: per-tap two-level accumulation (see conv_simt.cu)
   std::map<std::string, Buf> bufs;

@@ -36,6 +36,8 @@ def ctx(sds):
     c.set_weights(dvc.NET_VGG, sds["vgg"])
     c.set_weights(dvc.NET_WARP, sds["warp"])
     c.set_weights(dvc.NET_COLOR, sds["color"])
+    if os.environ.get("DVC_TEST_KC"):  # parity of a coarser TMEM promotion chunk (precision findings)
+        c.debug_flag("tc_kc", int(os.environ["DVC_TEST_KC"]))
     return c
 
 

@@ -32,23 +32,24 @@ def ab_gate(ours, g):
     return err, max(1e-3, 2.0 * floor)
 
 
-@pytest.fixture(params=["fp32", "tf32x3", "tf32x3-nof16", "tf32x3-cluster2", "tf32x3-k64", "tf32x3-split3"])
+@pytest.fixture(params=["fp32", "tf32x3", "tf32x3-nof16", "tf32x3-cluster1", "tf32x3-cluster1-nof16", "tf32x3-cluster1-k64",
+                        "tf32x3-k64", "tf32x3-split3"])
 def conv_math(request, ctx):
     """Convolutions on CUDA cores (exact fp32, two-level accumulation) and on tcgen05 (3xTF32 operand split),
-    the latter as single CTAs (64-byte and 128-byte K stages) and as 2-CTA clusters with TMA-multicast weights.
+    the latter as single CTAs (64-byte and 128-byte K stages) and as CTA pairs (tcgen05.mma.cta_group::2).
     Layers with provably bounded inputs run 3xFP16 on scaled planes unless "-nof16" turns that off."""
     import dvc
 
     if request.param.startswith("tf32x3"):
         ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
-        ctx.debug_flag("tc_cluster", 2 if request.param.endswith("cluster2") else 1)
+        ctx.debug_flag("tc_cluster", 1 if "cluster1" in request.param else 2)
         ctx.debug_flag("tc_kbytes", 64 if request.param.endswith("k64") else 128)
         ctx.debug_flag("tc_splits", 3 if request.param.endswith("split3") else 1)
         ctx.debug_flag("tc_f16", 0 if request.param.endswith("nof16") else 1)
     else:
         ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
     yield request.param
-    ctx.debug_flag("tc_cluster", 1)
+    ctx.debug_flag("tc_cluster", 2)
     ctx.debug_flag("tc_kbytes", 128)
     ctx.debug_flag("tc_splits", 1)
     ctx.debug_flag("tc_f16", 1)
