@@ -339,7 +339,9 @@ def main():
             "workload": "480x854 frame padded to 480x864 + 1 exemplar, full forward path (FrameColor.py:41-67), T=1e-10, "
                         "batch 1 with the frame recurrence of test.py:96; one contiguous K-frame segment per GPU",
             "N_positions": N_POS,
-            "conv_math": (f"tcgen05 3xTF32 operand split, TMEM chunk = {args.tc_kc} k-block(s) promoted to fp32 registers"
+            "conv_math": ((f"tcgen05 {'3xFP16 on exactly scaled hi/lo planes' if args.tc_f16 else '3xTF32 operand split'}, "
+                           f"{'CTA pairs (cta_group::2)' if args.tc_cluster == 2 else 'single CTAs'}, TMEM chunk = "
+                           f"{args.tc_kc} k-block(s) promoted to fp32 registers")
                           if args.conv_math == "tf32x3" else "fp32 CUDA-core (two-level accumulation)"),
             "corr_math": args.corr_math,
             "weights": "seeded random (dvc/synth.py), no checkpoint available",
@@ -351,14 +353,16 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         # dominant kernel by device time (profiles/launches_r1.md: conv_tc_kernel<256> ~ 50 % of a frame)
-        "roofline": {"kernel": "conv_tc_kernel<256> (3xTF32 flat shifted GEMM, all launches of a frame)", "bound": "tensor",
+        "roofline": {"kernel": "conv_tc_kernel<BN=256> (flat shifted GEMM, 3 MMA passes per product, all launches of a frame)",
+                     "bound": "tensor",
                      "achieved": conv_ach, "peak": peak, "unit": "TFLOP/s", "frac": conv_ach / peak if peak else None,
                      "traffic": ncu_traffic("conv_tc_kernel<256>"), "peak_source": peak_src,
-                     "traffic_note": "DRAM bytes of ONE profiled launch (a 1/8-resolution 512->512 layer), profiles/ncu_r1_conv256.md",
+                     "traffic_note": "DRAM bytes of ONE profiled launch (a 1/8-resolution 512->512 layer), profiles/ncu_r1_conv256.md; "
+                                     "algorithmic bytes of that launch: 2 x 6820 x 512 x 4 B activations in/out + 9.4 MB weights = 37 MB",
                      "launches_per_frame": n256 / KP, "ms_per_frame": ms256 / KP,
                      "note": "sum of algorithmic FLOPs (2 x output pixels x 9 x Cin x Cout) / sum of CUDA-event launch times, "
                              "single-stream pass of %d frames inside this run; the 3 MMA passes of the operand split are not "
-                             "counted, so frac is bounded by 1/6 of the dense-bf16 peak" % KP,
+                             "counted, so frac is bounded by 1/3 (3xFP16) or 1/6 (3xTF32) of the dense 16-bit peak" % KP,
                      "other_variants": conv_detail},
         # the north-star kernel (BASELINE metric: correlation tensor-pipe fraction)
         "roofline_corr": {"kernel": f"corr_tc_kernel ({args.corr_math}) incl. operand split + merge", "bound": "tensor",

@@ -228,15 +228,16 @@ void launch_conv_simt(const ConvParams& p, int B, bool two_level, cudaStream_t s
 namespace dvc {
 namespace {
 
-// First layers (Cin <= 8 real channels, 3x3): one thread = 4 adjacent pixels of a row x COUT/4 channels; the four
-// lanes of a quad cover one pixel's COUT channels, so a warp stores whole 128-byte lines, and every weight vector
-// read from shared memory feeds 4 pixels (16 FMA per LDS.128).  Accumulation order per output: taps outer, input
-// channels inner, one fma chain -- identical to a scalar loop.
-template <int COUT>
+// First layers (Cin <= 8 real channels, 3x3): one thread = 8 adjacent pixels of a row x COUT/8 channels; the eight
+// lanes of an octet cover one pixel's COUT channels, so every store request writes whole 32-byte sectors, and every
+// weight vector read from shared memory feeds 8 pixels (32 FMA per LDS.128).  NCI = input channels fetched (4 or 8).
+// Accumulation order per output: taps outer, input channels inner, one fma chain -- identical to a scalar loop.
+template <int COUT, int NCI>
 __global__ void __launch_bounds__(128) conv_first_kernel(const ConvParams p, int cin_real) {
-  constexpr int CG = COUT / 4;
+  constexpr int CG = COUT / 8;
   __shared__ __align__(16) float ws[9 * 8 * COUT];
   __shared__ float bs[COUT];
+  __shared__ float s_amax[4];
   for (int i = threadIdx.x; i < 9 * 8 * COUT; i += 128) {
     const int co = i % COUT, k = i / COUT;  // k = tap * 8 + ci
     ws[i] = __ldg(p.w + (size_t)k * p.CoutPad + co);
@@ -251,43 +252,44 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const ConvParams p, int
     yscale = exp2_int(e_out);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dyn.cell_out->e = e_out;
   }
-  const int g = threadIdx.x & 3;
-  const int quad = (blockIdx.x * 128 + threadIdx.x) >> 2;
-  const int qpr = (p.W + 3) >> 2;
-  const bool live = quad < p.H * qpr;  // dead lanes recompute quad 0 and store nothing (the warp stays converged)
-  const int qc = live ? quad : 0;
-  const int y = qc / qpr, x0 = (qc - y * qpr) * 4;
-  float acc[4][CG];
+  const int g = threadIdx.x & 7;
+  const int oct = (blockIdx.x * 128 + threadIdx.x) >> 3;
+  const int opr = (p.W + 7) >> 3;
+  const bool live = oct < p.H * opr;  // dead lanes recompute octet 0 and store nothing (the block stays converged)
+  const int oc = live ? oct : 0;
+  const int y = oc / opr, x0 = (oc - y * opr) * 8;
+  float acc[8][CG];
 #pragma unroll
-  for (int px = 0; px < 4; ++px)
+  for (int px = 0; px < 8; ++px)
 #pragma unroll
     for (int j = 0; j < CG; ++j) acc[px][j] = 0.f;
   const float* xb = p.x + (size_t)b * p.Hp * p.Wp * 8;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    float in[6][8];
+    float in[10][NCI];
 #pragma unroll
-    for (int col = 0; col < 6; ++col) {
+    for (int col = 0; col < 10; ++col) {
       const int xx = x0 + p.P - 1 + col;
       float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
       if (xx < p.Wp) {
         const float* px = xb + ((size_t)(y + p.P + r - 1) * p.Wp + xx) * 8;
-        v0 = __ldg(reinterpret_cast<const float4*>(px)), v1 = __ldg(reinterpret_cast<const float4*>(px + 4));
+        v0 = __ldg(reinterpret_cast<const float4*>(px));
+        if (NCI == 8) v1 = __ldg(reinterpret_cast<const float4*>(px + 4));
       }
       in[col][0] = v0.x, in[col][1] = v0.y, in[col][2] = v0.z, in[col][3] = v0.w;
-      in[col][4] = v1.x, in[col][5] = v1.y, in[col][6] = v1.z, in[col][7] = v1.w;
+      if (NCI == 8) in[col][4] = v1.x, in[col][5] = v1.y, in[col][6] = v1.z, in[col][7] = v1.w;
     }
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-      for (int ci = 0; ci < 8; ++ci) {
+      for (int ci = 0; ci < NCI; ++ci) {
         if (ci < cin_real) {
           const float4* wr = reinterpret_cast<const float4*>(ws + ((r * 3 + kx) * 8 + ci) * COUT + g * CG);
 #pragma unroll
           for (int c4 = 0; c4 < CG / 4; ++c4) {
             const float4 w4 = wr[c4];
 #pragma unroll
-            for (int px = 0; px < 4; ++px) {
+            for (int px = 0; px < 8; ++px) {
               const float a = in[px + kx][ci];
               acc[px][c4 * 4 + 0] = fmaf(a, w4.x, acc[px][c4 * 4 + 0]);
               acc[px][c4 * 4 + 1] = fmaf(a, w4.y, acc[px][c4 * 4 + 1]);
@@ -299,62 +301,78 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const ConvParams p, int
       }
     }
   }
+  float bias[CG];
 #pragma unroll
-  for (int px = 0; px < 4; ++px) {
+  for (int j = 0; j < CG; ++j) bias[j] = bs[g * CG + j];
+#pragma unroll
+  for (int px = 0; px < 8; ++px) {
     if (!live || x0 + px >= p.W) continue;
     const size_t o = (((size_t)b * p.yHp + y + p.yP) * p.yWp + x0 + px + p.yP) * p.yC + p.yCoff + g * CG;
+    float v[CG];
 #pragma unroll
-    for (int c4 = 0; c4 < CG / 4; ++c4) {
-      float v[4];
+    for (int j = 0; j < CG; ++j) {
+      v[j] = acc[px][j] + bias[j];
+      if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+      if (p.act == ACT_LRELU) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+      amax = fmaxf(amax, fabsf(v[j]));
+    }
+    if (p.dyn.h16) {
+      // |v * yscale| <= 2^15 by construction of the exponent (dvc_internal.cuh: dyn_out_exponent): no clamp needed
+      uint32_t hw[CG / 2], lw[CG / 2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[j] = acc[px][c4 * 4 + j] + bs[g * CG + c4 * 4 + j];
-        if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
-        if (p.act == ACT_LRELU) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+      for (int j = 0; j < CG; j += 2) {
+        const float a0 = v[j] * yscale, a1 = v[j + 1] * yscale;
+        const __half2 h2 = __floats2half2_rn(a0, a1);
+        const float2 hf = __half22float2(h2);
+        const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+        hw[j / 2] = *reinterpret_cast<const uint32_t*>(&h2), lw[j / 2] = *reinterpret_cast<const uint32_t*>(&l2);
       }
-      if (p.dyn.cell_out) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
-      if (p.dyn.h16) {
-        unsigned short h[4], l[4];
+      __half* hp = reinterpret_cast<__half*>(p.dyn.h16) + o;
+      __half* lp = reinterpret_cast<__half*>(p.dyn.l16) + o;
+      if constexpr (CG == 8) {
+        *reinterpret_cast<uint4*>(hp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(lp) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      } else {
+        *reinterpret_cast<uint2*>(hp) = make_uint2(hw[0], hw[1]);
+        *reinterpret_cast<uint2*>(lp) = make_uint2(lw[0], lw[1]);
+      }
+    } else if (p.y_lo) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float xc = fminf(fmaxf(v[j] * yscale, -65504.f), 65504.f);
-          const __half hh = __float2half_rn(xc);
-          h[j] = __half_as_ushort(hh);
-          l[j] = __half_as_ushort(__float2half_rn(xc - __half2float(hh)));
-        }
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.dyn.h16) + o + c4 * 4) =
-            make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
-        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.dyn.l16) + o + c4 * 4) =
-            make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
-      } else if (p.y_lo) {
+      for (int c4 = 0; c4 < CG / 4; ++c4) {
         float h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t u;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[j]));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[c4 * 4 + j]));
           h[j] = __uint_as_float(u);
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[j] - h[j]));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[c4 * 4 + j] - h[j]));
           l[j] = __uint_as_float(u);
         }
         *reinterpret_cast<float4*>(p.y + o + c4 * 4) = make_float4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<float4*>(p.y_lo + o + c4 * 4) = make_float4(l[0], l[1], l[2], l[3]);
-      } else {
-        *reinterpret_cast<float4*>(p.y + o + c4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
       }
+    } else {
+#pragma unroll
+      for (int c4 = 0; c4 < CG / 4; ++c4)
+        *reinterpret_cast<float4*>(p.y + o + c4 * 4) = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
     }
   }
-  if (p.dyn.cell_out) warp_amax_commit(amax, p.dyn.cell_out);
+  if (p.dyn.cell_out) block_amax_commit(amax, p.dyn.cell_out, s_amax);
 }
 
 }  // namespace
 
 bool launch_conv_first(const ConvParams& p, int B, int cin_real, cudaStream_t s) {
   if (p.Cin != 8 || p.taps != 9 || p.dil != 1 || p.stride != 1 || p.add || p.stats || p.P < 1) return false;
-  dim3 grid((p.H * ((p.W + 3) / 4) * 4 + 127) / 128, B);
-  if (p.Cout == 64)
-    conv_first_kernel<64><<<grid, 128, 0, s>>>(p, cin_real);
+  dim3 grid((p.H * ((p.W + 7) / 8) * 8 + 127) / 128, B);
+  if (p.Cout == 64 && cin_real <= 4)
+    conv_first_kernel<64, 4><<<grid, 128, 0, s>>>(p, cin_real);
+  else if (p.Cout == 64)
+    conv_first_kernel<64, 8><<<grid, 128, 0, s>>>(p, cin_real);
+  else if (p.Cout == 32 && cin_real <= 4)
+    conv_first_kernel<32, 4><<<grid, 128, 0, s>>>(p, cin_real);
   else if (p.Cout == 32)
-    conv_first_kernel<32><<<grid, 128, 0, s>>>(p, cin_real);
+    conv_first_kernel<32, 8><<<grid, 128, 0, s>>>(p, cin_real);
   else
     return false;
   launch_counter_add(1);

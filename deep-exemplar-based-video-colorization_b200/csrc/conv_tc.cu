@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       }
 
       // ---- bias, skip addend, activation, statistics, masked store ----
+      float fs0 = 0.f, fs1 = 0.f;  // fused 1x1 tail: partial dot products over this thread's channels
 #pragma unroll
       for (int c = 0; c < CPT / 32; ++c) {
         const int ch0 = n0 + half * CPT + c * 32;
@@ -366,6 +367,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           for (int j = 0; j < 32; ++j) {
             if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
             if (p.act == ACT_LRELU) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+          }
+          if (BN == 128 && p.fin_out) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.fin_w + ch0 + j));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.fin_w + p.Cout + ch0 + j));
+              fs0 += v[j] * w0.x + v[j + 1] * w0.y + v[j + 2] * w0.z + v[j + 3] * w0.w;
+              fs1 += v[j] * w1.x + v[j + 1] * w1.y + v[j + 2] * w1.z + v[j + 3] * w1.w;
+            }
           }
           if (F16 && p.dyn.cell_out && valid) {
 #pragma unroll
@@ -399,7 +409,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                 *reinterpret_cast<float4*>(p.y + yoff + ch0 + j) = make_float4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<float4*>(p.y_lo + yoff + ch0 + j) = make_float4(l[0], l[1], l[2], l[3]);
               }
-            } else {
+            } else if (p.y) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<float4*>(p.y + yoff + ch0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -435,6 +445,18 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             }
           }
         }
+      }
+      if (BN == 128 && p.fin_out) {  // the two channel halves of a pixel meet in shared memory
+        float2* s_fin = reinterpret_cast<float2*>(s_stat);
+        if (half == 1) s_fin[q * 32 + lane] = make_float2(fs0, fs1);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0 && valid) {
+          const float2 o2 = s_fin[q * 32 + lane];
+          const size_t hw = (size_t)p.H * p.W, po = (size_t)yo * p.W + xo;
+          p.fin_out[((size_t)b * 2 + 0) * hw + po] = tanhf(fs0 + o2.x + __ldg(p.fin_b + 0)) * 128.f;
+          p.fin_out[((size_t)b * 2 + 1) * hw + po] = tanhf(fs1 + o2.y + __ldg(p.fin_b + 1)) * 128.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       if (p.stats) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -518,7 +540,8 @@ int launch_conv_tc(const ConvTcParams& p, const void* x_hi, const void* x_lo, co
   const int KBY = (p.kbytes == 64 || (f16 && p.Cin % 64)) ? 64 : 128;
   if (p.kc < 1) return fail("kc must be >= 1");
   if (p.CoutPad % conv_tc_pick_bn(p.Cout)) return fail("CoutPad must be a multiple of the channel tile");
-  const int BN = pick_bn_for_launch(p, num_sms);
+  if (p.fin_out && (p.Cout != 128 || p.stride != 1 || p.oscale != 1 || p.stats)) return fail("fused 1x1 tail needs a plain 128-channel layer");
+  const int BN = p.fin_out ? 128 : pick_bn_for_launch(p, num_sms);
   if (variant) *variant = BN;
   // 2-CTA clusters when there are at least two pixel tiles per SM pair to go around
   const int CL = (p.cluster == 2 && (p.Mtot + BM - 1) / BM >= 2) ? 2 : 1;

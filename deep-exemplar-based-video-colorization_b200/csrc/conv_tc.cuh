@@ -27,6 +27,11 @@ struct ConvTcParams {
   float out_scale;  // fp16 mode: 2^-(e_x + e_w), undoes the exact power-of-two operand scales
   DynOut dyn;       // fp16 mode: device-side scales (dyn.cell_in: the input exponent is added to out_scale's on the
                     // device; dyn.h16: store fp16 planes with a derived exponent; dyn.cell_out: record max |output|)
+  // fused tail of ColorVidNet (ColorVidNet.py:143-144): out[b][c][y][x] = 128 * tanh(sum_ch v[ch] * fin_w[c][ch] + fin_b[c]),
+  // c = 0, 1, computed from the activated outputs instead of storing them (needs Cout == 128 == the channel tile)
+  const float* fin_w;
+  const float* fin_b;
+  float* fin_out;
   int splits;     // split-K factor S (1 = off); needs ws / flags below
   float* ws;      // [tiles][BN][128] fp32 partial totals
   int* flags;     // [tiles], value epoch*16 + (splits completed)

@@ -497,6 +497,9 @@ struct ConvOpt {
   const Act* add = nullptr;
   double* stats = nullptr;
   int yCoff = 0;
+  const float* fin_w = nullptr;  // fused conv10_ab + tanh tail (tensor-core engine only): weights [2][Cout], bias [2],
+  const float* fin_b = nullptr;  // NCHW destination [B][2][H][W]; the activated outputs themselves are not stored
+  float* fin_out = nullptr;
   float l1_override = 0.f;  // > 0: weight L1 bound shared by the four phase launches of one up-convolution
 };
 
@@ -553,6 +556,7 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     t.Hp = p.Hp, t.Wp = p.Wp, t.P = p.P, t.H = p.H, t.W = p.W, t.Cin = p.Cin, t.Mtot = x.B * p.Hp * p.Wp;
     t.taps = taps, t.stride = o.stride, t.Cout = w->cout, t.CoutPad = w->cout_pad_tc, t.bias = w->b;
     t.oscale = 1, t.oa = 0, t.ob = 0;
+    t.fin_w = o.fin_w, t.fin_b = o.fin_b, t.fin_out = o.fin_out;
     if (o.phase >= 0) {
       // nearest-x2 then 3x3 (zero pad 1) == four 2x2 convolutions on the low-resolution map, one per output parity
       // (a, b): rows {-1, 0} for a = 0 and {0, +1} for a = 1, same for columns (weights pre-summed at load time)
@@ -626,7 +630,7 @@ struct XfOpt {
 static int run_xform(dvc_ctx* c, const Act& src, Act& dst, const XfOpt& o, cudaStream_t s) {
   const int C = o.C ? o.C : src.C;
   const int eh = ((src.H + o.sub - 1) / o.sub) * o.up + 2 * o.rowpad, ew = ((src.W + o.sub - 1) / o.sub) * o.up;
-  if (dst.H != eh || dst.W != ew || dst.B != src.B || o.dCoff + C > dst.C || (C & 3))
+  if (dst.H != eh || dst.W != ew || dst.B != src.B || o.dCoff + C > dst.C || (C & 7) || (o.dCoff & 7) || (dst.C & 7) || (src.C & 7))
     return fail(c, DVC_ERR_SHAPE, "xform: shape mismatch");
   if (o.pad_mode == PAD_REFLECT && (dst.P >= dst.H || dst.P >= dst.W)) return fail(c, DVC_ERR_SHAPE, "xform: reflect pad too wide");
   XformParams p{};
@@ -991,6 +995,19 @@ static int colorvid(dvc_ctx* c, const std::string& tag, const Act& in0, float* o
   DVC_TRY(conv("conv9_2", u, &raw2, 0, ACT_RELU, 1, nullptr, &st9, 0));
   DVC_TRY(conv("conv1_2_short", n1, &t, 0, ACT_NONE, 1, nullptr, nullptr, 0));
   DVC_TRY(upconv("conv10_1.1", raw2, st9, &t, &u));
+  if (u.H != H || u.W != W) return fail(c, DVC_ERR_SHAPE, "ColorVidNet: decoder shape mismatch");
+  if (tc_mode(c) && (u.lo || u.h16)) {
+    // conv10_2 + LeakyReLU(0.2) + conv10_ab (1x1, 128 -> 2) + tanh * 128 in one launch: the 128-channel full-resolution
+    // activation (213 MB at 480p) is consumed in the epilogue instead of being written and re-read
+    const ConvW* w;
+    DVC_TRY(need_conv(c, net, "conv10_2", &w));
+    if (w->cout != 128) return fail(c, DVC_ERR_SHAPE, "ColorVidNet: conv10_2 must have 128 output channels");
+    Act none;
+    none.B = B, none.H = H, none.W = W, none.C = w->cout, none.P = 0;
+    ConvOpt o;
+    o.act = ACT_LRELU, o.slope = 0.2f, o.fin_w = wab, o.fin_b = bab, o.fin_out = out_nchw;
+    return run_conv(c, w, u, none, o, s);
+  }
   DVC_TRY(conv("conv10_2", u, &a, 0, ACT_LRELU, 1, nullptr, nullptr, 0.2f));
   if (a.H != H || a.W != W || a.C != 128) return fail(c, DVC_ERR_SHAPE, "ColorVidNet: decoder shape mismatch");
   launch_final_ab(a.d, H, W, a.P, a.C, wab, bab, out_nchw, B, s);

@@ -55,6 +55,20 @@ __device__ __forceinline__ void warp_amax_commit(float amax, ScaleCell* cell) {
   for (int off = 16; off >= 1; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
   if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(&cell->amax_bits, __float_as_uint(amax));
 }
+// block-wide variant (blockDim.x <= 1024, every thread calls it): one atomic per block; `red` holds >= 32 floats
+// (or as many as the block has warps)
+__device__ __forceinline__ void block_amax_commit(float amax, ScaleCell* cell, float* red) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if ((threadIdx.x & 31) == 0) red[w] = amax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+    if (m > 0.f) atomicMax(&cell->amax_bits, __float_as_uint(m));
+  }
+}
 #endif
 
 struct Act {

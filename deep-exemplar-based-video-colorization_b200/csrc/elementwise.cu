@@ -88,14 +88,17 @@ __global__ void __launch_bounds__(256) xform_kernel(const XformParams p) {
   }
   const int dHp = p.dH + 2 * p.dP, dWp = p.dW + 2 * p.dP;
   const int sWp = p.sW + 2 * p.sP, sHp = p.sH + 2 * p.sP;
-  const int c4n = p.C >> 2;
-  const long total = (long)dHp * dWp * c4n;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % c4n) * 4;
-    const int pix = (int)(idx / c4n);
+  // one thread = 8 channels of one destination pixel; 32-bit index math (dHp * dWp * C / 8 < 2^31 by far)
+  const int c8n = p.C >> 3;
+  const int total = dHp * dWp * c8n;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int pix = idx / c8n;
+    const int c = (idx - pix * c8n) * 8;
     const int yp = pix / dWp, xp = pix - yp * dWp;
     int y = yp - p.dP, x = xp - p.dP;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
     bool inside = (y >= 0 && y < p.dH && x >= 0 && x < p.dW);
     if (!inside && p.pad_mode == PAD_REFLECT) {
       y = reflect_idx(y, p.dH);
@@ -106,34 +109,50 @@ __global__ void __launch_bounds__(256) xform_kernel(const XformParams p) {
       int y1 = y;
       if (p.rowpad) y1 = min(max(y - 1, 0), p.dH - 3);
       const int ys = (y1 / p.up) * p.sub, xs = (x / p.up) * p.sub;
-      v = ld4(p.src, p.src_lo, (((size_t)b * sHp + ys + p.sP) * sWp + xs + p.sP) * p.sC + p.sCoff + c);
+      const size_t so = (((size_t)b * sHp + ys + p.sP) * sWp + xs + p.sP) * p.sC + p.sCoff + c;
+      const float4 v0 = ld4(p.src, p.src_lo, so), v1 = ld4(p.src, p.src_lo, so + 4);
+      v[0] = v0.x, v[1] = v0.y, v[2] = v0.z, v[3] = v0.w, v[4] = v1.x, v[5] = v1.y, v[6] = v1.z, v[7] = v1.w;
       if (p.stats) {
-        v.x = (v.x - s_mean[c + 0]) * s_rstd[c + 0];
-        v.y = (v.y - s_mean[c + 1]) * s_rstd[c + 1];
-        v.z = (v.z - s_mean[c + 2]) * s_rstd[c + 2];
-        v.w = (v.w - s_mean[c + 3]) * s_rstd[c + 3];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (v[j] - s_mean[c + j]) * s_rstd[c + j];
       }
       if (p.scale) {
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c));
-        v.x *= sc.x, v.y *= sc.y, v.z *= sc.z, v.w *= sc.w;
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c + 4));
+        v[0] *= s0.x, v[1] *= s0.y, v[2] *= s0.z, v[3] *= s0.w, v[4] *= s1.x, v[5] *= s1.y, v[6] *= s1.z, v[7] *= s1.w;
       }
       if (p.res) {
         const int rHp = p.dH + 2 * p.rP, rWp = p.dW + 2 * p.rP;
-        const float4 r = ld4(p.res, p.res_lo, (((size_t)b * rHp + y + p.rP) * rWp + x + p.rP) * p.rC + c);
-        v.x += r.x, v.y += r.y, v.z += r.z, v.w += r.w;
+        const size_t ro = (((size_t)b * rHp + y + p.rP) * rWp + x + p.rP) * p.rC + c;
+        const float4 r0 = ld4(p.res, p.res_lo, ro), r1 = ld4(p.res, p.res_lo, ro + 4);
+        v[0] += r0.x, v[1] += r0.y, v[2] += r0.z, v[3] += r0.w, v[4] += r1.x, v[5] += r1.y, v[6] += r1.z, v[7] += r1.w;
       }
       if (p.act == 1) {
-        v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
       } else if (p.act == 2) {
-        v.x = v.x > 0.f ? v.x : v.x * p.slope;
-        v.y = v.y > 0.f ? v.y : v.y * p.slope;
-        v.z = v.z > 0.f ? v.z : v.z * p.slope;
-        v.w = v.w > 0.f ? v.w : v.w * p.slope;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
       }
     }
     const size_t doff = (((size_t)b * dHp + yp) * dWp + xp) * p.dC + p.dCoff + c;
-    if (p.dst) st4(p.dst, p.dst_lo, doff, v);
-    if (p.dst_h16) st4h(reinterpret_cast<__half*>(p.dst_h16), reinterpret_cast<__half*>(p.dst_l16), doff, v, p.dscale16);
+    if (p.dst) {
+      st4(p.dst, p.dst_lo, doff, make_float4(v[0], v[1], v[2], v[3]));
+      st4(p.dst, p.dst_lo, doff + 4, make_float4(v[4], v[5], v[6], v[7]));
+    }
+    if (p.dst_h16) {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a0 = fminf(fmaxf(v[2 * j] * p.dscale16, -65504.f), 65504.f);
+        const float a1 = fminf(fmaxf(v[2 * j + 1] * p.dscale16, -65504.f), 65504.f);
+        const __half2 h2 = __floats2half2_rn(a0, a1);
+        const float2 hf = __half22float2(h2);
+        const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+        hw[j] = *reinterpret_cast<const uint32_t*>(&h2), lw[j] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.dst_h16) + doff) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.dst_l16) + doff) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
   }
 }
 
@@ -396,12 +415,13 @@ __global__ void __launch_bounds__(256) maxpool2_h16_kernel(const __half* __restr
 }
 
 __global__ void __launch_bounds__(256) amax_kernel(const float4* __restrict__ x, size_t n4, ScaleCell* __restrict__ cell) {
+  __shared__ float red[8];
   float m = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = __ldg(x + i);
     m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
   }
-  warp_amax_commit(m, cell);
+  block_amax_commit(m, cell, red);
 }
 
 __global__ void __launch_bounds__(256) avgpool4_lab_kernel(const float* __restrict__ src, float* __restrict__ V, int H,
@@ -581,7 +601,7 @@ inline int grid_for(long total, int threads, int cap = 148 * 16) {
 }  // namespace
 
 void launch_xform(const XformParams& p, int B, cudaStream_t s) {
-  const long total = (long)(p.dH + 2 * p.dP) * (p.dW + 2 * p.dP) * (p.C / 4);
+  const long total = (long)(p.dH + 2 * p.dP) * (p.dW + 2 * p.dP) * (p.C / 8);
   dim3 grid(grid_for(total, 256), B);
   const size_t sm = p.stats ? 2 * p.C * sizeof(float) : 0;
   xform_kernel<<<grid, 256, sm, s>>>(p);
@@ -640,7 +660,7 @@ void launch_maxpool2_h16(const void* h16, const void* l16, const ScaleCell* cell
 }
 
 void launch_amax(const float* x, size_t n, ScaleCell* cell, cudaStream_t s) {
-  amax_kernel<<<(unsigned)grid_for((long)(n / 4), 256), 256, 0, s>>>(reinterpret_cast<const float4*>(x), n / 4, cell);
+  amax_kernel<<<(unsigned)grid_for((long)(n / 4), 256, 148 * 4), 256, 0, s>>>(reinterpret_cast<const float4*>(x), n / 4, cell);
   launch_counter_add(1);
 }
 

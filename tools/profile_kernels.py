@@ -11,6 +11,7 @@ for net, key in ((dvc.NET_VGG, "vgg"), (dvc.NET_WARP, "warp"), (dvc.NET_COLOR, "
     ctx.set_weights(net, make_state_dict(key, seed=0))
 ctx.set_math(conv=dvc.MATH_TF32X3, corr={"tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3, "fp16x3": dvc.MATH_FP16X3}[os.environ.get("DVC_CORR", "fp16x3")])
 ctx.debug_flag("tc_kc", int(os.environ.get("DVC_KC", "1")))
+ctx.debug_flag("tc_splits", int(os.environ.get("DVC_SPLITS", "1")))
 H, W = 480, 864
 ctx.set_exemplar(make_lab(60, 1, H, W))
 L = make_lab(61, 2, H, W)[:, 0:1].cuda()
