@@ -357,8 +357,9 @@ def main():
                      "bound": "tensor",
                      "achieved": conv_ach, "peak": peak, "unit": "TFLOP/s", "frac": conv_ach / peak if peak else None,
                      "traffic": ncu_traffic("conv_tc_kernel<256>"), "peak_source": peak_src,
-                     "traffic_note": "DRAM bytes of ONE profiled launch (a 1/8-resolution 512->512 layer), profiles/ncu_r1_conv256.md; "
-                                     "algorithmic bytes of that launch: 2 x 6820 x 512 x 4 B activations in/out + 9.4 MB weights = 37 MB",
+                     "traffic_note": "DRAM bytes of ONE profiled launch (a quarter-resolution 256->256 layer), profiles/ncu_r1_conv256.md; "
+                                     "algorithmic bytes of that launch: 27.2 MB fp16 hi/lo input planes + 2.4 MB weights + 27.2 MB "
+                                     "fp32 output = 56.8 MB (the output stays in L2 for the next layer)",
                      "launches_per_frame": n256 / KP, "ms_per_frame": ms256 / KP,
                      "note": "sum of algorithmic FLOPs (2 x output pixels x 9 x Cin x Cout) / sum of CUDA-event launch times, "
                              "single-stream pass of %d frames inside this run; the 3 MMA passes of the operand split are not "

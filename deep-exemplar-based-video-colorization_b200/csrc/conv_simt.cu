@@ -230,11 +230,15 @@ namespace {
 
 // First layers (Cin <= 8 real channels, 3x3): one thread = 8 adjacent pixels of a row x COUT/8 channels; the eight
 // lanes of an octet cover one pixel's COUT channels, so every store request writes whole 32-byte sectors, and every
-// weight vector read from shared memory feeds 8 pixels (32 FMA per LDS.128).  NCI = input channels fetched (4 or 8).
+// weight vector read from shared memory feeds 8 pixels (32 FMA per LDS.128).  CIN = real input channels (compile time;
+// 0 = run-time `cin_real`, all 8 fetched); the row loop stays rolled so that the body fits the instruction cache (the
+// fully unrolled 27 x 8-channel body was ~240 KB of SASS and stalled on instruction fetch).
 // Accumulation order per output: taps outer, input channels inner, one fma chain -- identical to a scalar loop.
-template <int COUT, int NCI>
+template <int COUT, int CIN>
 __global__ void __launch_bounds__(128) conv_first_kernel(const ConvParams p, int cin_real) {
   constexpr int CG = COUT / 8;
+  constexpr int NCI = (CIN > 0 && CIN <= 4) ? 4 : 8;  // input channels fetched per pixel
+  constexpr int NCL = CIN > 0 ? CIN : 8;              // input channels in the unrolled body
   __shared__ __align__(16) float ws[9 * 8 * COUT];
   __shared__ float bs[COUT];
   __shared__ float s_amax[4];
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const ConvParams p, int
 #pragma unroll
     for (int j = 0; j < CG; ++j) acc[px][j] = 0.f;
   const float* xb = p.x + (size_t)b * p.Hp * p.Wp * 8;
-#pragma unroll
+#pragma unroll 1
   for (int r = 0; r < 3; ++r) {
     float in[10][NCI];
 #pragma unroll
@@ -282,8 +286,8 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const ConvParams p, int
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-      for (int ci = 0; ci < NCI; ++ci) {
-        if (ci < cin_real) {
+      for (int ci = 0; ci < NCL; ++ci) {
+        if (CIN > 0 || ci < cin_real) {
           const float4* wr = reinterpret_cast<const float4*>(ws + ((r * 3 + kx) * 8 + ci) * COUT + g * CG);
 #pragma unroll
           for (int c4 = 0; c4 < CG / 4; ++c4) {
@@ -365,14 +369,14 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const ConvParams p, int
 bool launch_conv_first(const ConvParams& p, int B, int cin_real, cudaStream_t s) {
   if (p.Cin != 8 || p.taps != 9 || p.dil != 1 || p.stride != 1 || p.add || p.stats || p.P < 1) return false;
   dim3 grid((p.H * ((p.W + 7) / 8) * 8 + 127) / 128, B);
-  if (p.Cout == 64 && cin_real <= 4)
-    conv_first_kernel<64, 4><<<grid, 128, 0, s>>>(p, cin_real);
+  if (p.Cout == 64 && cin_real == 3)  // VGG19 conv1_1
+    conv_first_kernel<64, 3><<<grid, 128, 0, s>>>(p, cin_real);
   else if (p.Cout == 64)
-    conv_first_kernel<64, 8><<<grid, 128, 0, s>>>(p, cin_real);
-  else if (p.Cout == 32 && cin_real <= 4)
-    conv_first_kernel<32, 4><<<grid, 128, 0, s>>>(p, cin_real);
+    conv_first_kernel<64, 0><<<grid, 128, 0, s>>>(p, cin_real);
+  else if (p.Cout == 32 && cin_real == 7)  // ColorVidNet conv1_1.0
+    conv_first_kernel<32, 7><<<grid, 128, 0, s>>>(p, cin_real);
   else if (p.Cout == 32)
-    conv_first_kernel<32, 8><<<grid, 128, 0, s>>>(p, cin_real);
+    conv_first_kernel<32, 0><<<grid, 128, 0, s>>>(p, cin_real);
   else
     return false;
   launch_counter_add(1);
