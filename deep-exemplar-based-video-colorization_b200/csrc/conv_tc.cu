@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   float* s_stat = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 512);  // [4 lane quarters][2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (p.Mtot + BM - 1) / BM;
+  const int m_tiles = p.mtn ? p.mtn : (p.Mtot + BM - 1) / BM;
   const int n_tiles = p.CoutPad / BN;
   const int crank = (CL == 2) ? (int)tc::cluster_ctarank() : 0;
   const int m_groups = (m_tiles + CL - 1) / CL;          // CL adjacent pixel tiles per work item
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       for (int work = item0; work < total_work; work += item_stride) {
         const int sp = work / total_items, item = work - sp * total_items;
         const int mg = item / n_tiles, nt = item - mg * n_tiles;
-        const int m0 = (mg * CL + crank) * BM, n0 = nt * BN;
+        const int m0 = (p.mt0 + mg * CL + crank) * BM, n0 = nt * BN;
         const int k_lo = (nchunks * sp / S) * kc, k_hi = min((nchunks * (sp + 1) / S) * kc, nk);
         for (int k = k_lo; k < k_hi; ++k) {
           const int tap = k / kbs, kb = k - tap * kbs;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     for (int work = item0; work < total_work; work += item_stride) {
       const int sp = work / total_items, item = work - sp * total_items;
       const int mg = item / n_tiles, nt = item - mg * n_tiles;
-      const int m0 = (mg * CL + crank) * BM, n0 = nt * BN;
+      const int m0 = (p.mt0 + mg * CL + crank) * BM, n0 = nt * BN;
       const int tile_id = (mg * CL + crank) * n_tiles + nt;
       const int pp = m0 + q * 32 + lane;
       bool valid = pp < p.Mtot;
@@ -501,7 +501,7 @@ int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap&
       return -1;
     attr = true;
   }
-  const int m_tiles = (p.Mtot + BM - 1) / BM;
+  const int m_tiles = p.mtn ? p.mtn : (p.Mtot + BM - 1) / BM;
   const int items = ((m_tiles + CL - 1) / CL) * (p.CoutPad / BN) * p.splits;
   const int max_groups = num_sms / CL;
   const int grid = CL * (items < max_groups ? items : max_groups);
@@ -541,13 +541,28 @@ int launch_conv_tc(const ConvTcParams& p, const void* x_hi, const void* x_lo, co
   if (p.kc < 1) return fail("kc must be >= 1");
   if (p.CoutPad % conv_tc_pick_bn(p.Cout)) return fail("CoutPad must be a multiple of the channel tile");
   if (p.fin_out && (p.Cout != 128 || p.stride != 1 || p.oscale != 1 || p.stats)) return fail("fused 1x1 tail needs a plain 128-channel layer");
-  const int BN = p.fin_out ? 128 : pick_bn_for_launch(p, num_sms);
-  if (variant) *variant = BN;
+  const int BN = p.force_bn ? p.force_bn : (p.fin_out ? 128 : pick_bn_for_launch(p, num_sms));
+  if (variant && !p.mtn) *variant = BN;
   // 2-CTA clusters when there are at least two pixel tiles per SM pair to go around
   const int CL = (p.cluster == 2 && (p.Mtot + BM - 1) / BM >= 2) ? 2 : 1;
+  if (p.tail && !p.mtn && CL == 2 && BN == 256 && p.CoutPad == 256 && p.splits == 1) {
+    // Wave quantisation: e.g. 208 pixel tiles = 104 pairs on 74 pair slots run as two rounds, the second 40 % full.
+    // The whole rounds keep the 256-channel tile; the remaining pairs are run with 128-channel tiles (twice as many
+    // work items of ~0.6x the duration) when those fit in one round: 2.0 -> 1.6 rounds.
+    const int m_tiles = (p.Mtot + BM - 1) / BM, pairs = (m_tiles + 1) / 2, slots = p.tail > 1 ? p.tail : num_sms / 2;
+    const int full = pairs / slots, rem = pairs - full * slots;
+    if (full >= 1 && rem > 0 && 2 * rem <= slots) {
+      ConvTcParams q1 = p, q2 = p;
+      q1.mt0 = 0, q1.mtn = 2 * full * slots, q1.force_bn = 256;
+      q2.mt0 = q1.mtn, q2.mtn = m_tiles - q1.mtn, q2.force_bn = 128;
+      int rc1 = launch_conv_tc(q1, x_hi, x_lo, w_hi, w_lo, num_sms, s, err, nullptr);
+      if (rc1) return rc1;
+      return launch_conv_tc(q2, x_hi, x_lo, w_hi, w_lo, num_sms, s, err, nullptr);
+    }
+  }
   ConvTcParams q = p;
   {  // split-K factor: minimise rounds(S) / S over the persistent grid (2 % penalty per extra split for the hand-over)
-    const int m_tiles = (p.Mtot + BM - 1) / BM;
+    const int m_tiles = p.mtn ? p.mtn : (p.Mtot + BM - 1) / BM;
     const int tiles = ((m_tiles + CL - 1) / CL) * CL * (p.CoutPad / BN);
     // k-blocks of KBY bytes and the chunks the kernel sums them in (p.kc counts 128-byte k-blocks)
     const int nk = p.taps * (p.Cin / (KBY / eb)), kcs = p.kc * (128 / KBY);

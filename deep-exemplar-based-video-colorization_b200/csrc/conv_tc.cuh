@@ -32,6 +32,10 @@ struct ConvTcParams {
   const float* fin_w;
   const float* fin_b;
   float* fin_out;
+  int mt0, mtn;   // pixel-tile range [mt0, mt0 + mtn) of this launch (mtn = 0: all tiles)
+  int force_bn;   // channel tile of this launch (0: chosen by the launcher)
+  int tail;       // 1: a two-round 256-channel launch runs its last partial round with 128-channel tiles (see launcher);
+                  // > 1 (tests): same, pretending the GPU has `tail` pair slots
   int splits;     // split-K factor S (1 = off); needs ws / flags below
   float* ws;      // [tiles][BN][128] fp32 partial totals
   int* flags;     // [tiles], value epoch*16 + (splits completed)

@@ -33,7 +33,7 @@ def ab_gate(ours, g):
 
 
 @pytest.fixture(params=["fp32", "tf32x3", "tf32x3-nof16", "tf32x3-cluster1", "tf32x3-cluster1-nof16", "tf32x3-cluster1-k64",
-                        "tf32x3-k64", "tf32x3-split3"])
+                        "tf32x3-k64", "tf32x3-split3", "tf32x3-tail16", "tf32x3-tail"])
 def conv_math(request, ctx):
     """Convolutions on CUDA cores (exact fp32, two-level accumulation) and on tcgen05 (3xTF32 operand split),
     the latter as single CTAs (64-byte and 128-byte K stages) and as CTA pairs (tcgen05.mma.cta_group::2).
@@ -46,6 +46,8 @@ def conv_math(request, ctx):
         ctx.debug_flag("tc_kbytes", 64 if request.param.endswith("k64") else 128)
         ctx.debug_flag("tc_splits", 3 if request.param.endswith("split3") else 1)
         ctx.debug_flag("tc_f16", 0 if request.param.endswith("nof16") else 1)
+        # tail rounds of 256-channel launches on 128-channel tiles: forced at small sizes by pretending 16 pair slots
+        ctx.debug_flag("tc_tail", 16 if request.param.endswith("tail16") else (1 if request.param.endswith("-tail") else 0))
     else:
         ctx.set_math(conv=dvc.MATH_FP32, corr=dvc.MATH_FP32)
     yield request.param
@@ -53,6 +55,7 @@ def conv_math(request, ctx):
     ctx.debug_flag("tc_kbytes", 128)
     ctx.debug_flag("tc_splits", 1)
     ctx.debug_flag("tc_f16", 1)
+    ctx.debug_flag("tc_tail", 0)
     ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
 
 
