@@ -830,7 +830,8 @@ static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const c
     DVC_TRY(run_conv(c, w2, mid, raw, o2, s));
     XfOpt x2;
     x2.pad_mode = PAD_REFLECT, x2.stats = st2, x2.count = (double)h * w, x2.act = 2, x2.slope = sl, x2.res = &xa;
-    chain_bound += in_bound;  // out = PReLU(IN(..)) + residual (NonlocalNet.py:44-51)
+    // out = PReLU(IN(conv2(..)) + x) (NonlocalNet.py:341-352): |out| <= (sqrt(hw) + |x|max) * max(1, |slope|)
+    chain_bound = (chain_bound + sqrt((double)h * w)) * fmax(1.0, fabs(sl));
     xb.e16 = e16_for(chain_bound);
     DVC_TRY(run_xform(c, raw, xb, x2, s));
     std::swap(xa, xb);
@@ -1510,6 +1511,27 @@ extern "C" int dvc_upsample2_scaled(dvc_ctx* c, const float* dev_src, int planes
   CUDA_TRY(c, cudaSetDevice(c->device));
   launch_upsample2(dev_src, dev_dst, planes, h, w, scale, (cudaStream_t)stream);
   return check_launch(c, "upsample2");
+}
+
+extern "C" int dvc_lab_to_rgb8(dvc_ctx* c, const float* dev_l, const float* dev_ab, int B, int H, int W, unsigned char* dev_rgb,
+                               void* stream) {
+  if (!c || !dev_l || !dev_ab || !dev_rgb || B < 1 || H < 1 || W < 1) return c ? fail(c, DVC_ERR_ARG, "lab_to_rgb8: bad argument") : DVC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  // rgb_from_xyz = inv(xyz_from_rgb) (skimage.color.colorconv), by the adjugate in double precision
+  const double a[9] = {0.412453, 0.357580, 0.180423, 0.212671, 0.715160, 0.072169, 0.019334, 0.119193, 0.950227};
+  const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+  const double inv[9] = {(a[4] * a[8] - a[5] * a[7]) / det, (a[2] * a[7] - a[1] * a[8]) / det, (a[1] * a[5] - a[2] * a[4]) / det,
+                         (a[5] * a[6] - a[3] * a[8]) / det, (a[0] * a[8] - a[2] * a[6]) / det, (a[2] * a[3] - a[0] * a[5]) / det,
+                         (a[3] * a[7] - a[4] * a[6]) / det, (a[1] * a[6] - a[0] * a[7]) / det, (a[0] * a[4] - a[1] * a[3]) / det};
+  launch_lab_to_rgb8(dev_l, dev_ab, dev_rgb, B, H, W, inv, (cudaStream_t)stream);
+  return check_launch(c, "lab_to_rgb8");
+}
+
+extern "C" int dvc_rgb8_to_lab(dvc_ctx* c, const unsigned char* dev_rgb, int B, int H, int W, float* dev_lab, void* stream) {
+  if (!c || !dev_rgb || !dev_lab || B < 1 || H < 1 || W < 1) return c ? fail(c, DVC_ERR_ARG, "rgb8_to_lab: bad argument") : DVC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  launch_rgb8_to_lab(dev_rgb, dev_lab, B, H, W, (cudaStream_t)stream);
+  return check_launch(c, "rgb8_to_lab");
 }
 
 // ---- exemplar operands for the NCCL broadcast -----------------------------------------------------

@@ -209,6 +209,11 @@ void launch_transpose_cn(const float* src, float* dst, int B, int C, int N, cuda
 // pre / post-processing around the nets (test.py:58,71 and 100-102)
 void launch_resize_half(const float* src, float* dst, int planes, int H, int W, cudaStream_t s);
 void launch_upsample2(const float* src, float* dst, int planes, int h, int w, float scale, cudaStream_t s);
+// sRGB uint8 HWC -> centred Lab NCHW fp32 (skimage.color.rgb2lab semantics in float64, then L - 50)
+void launch_rgb8_to_lab(const unsigned char* rgb, float* lab, int B, int H, int W, cudaStream_t s);
+// Lab -> sRGB uint8 HWC in float64 (skimage.color.lab2rgb semantics); rgb_from_xyz: row-major 3x3
+void launch_lab_to_rgb8(const float* l, const float* ab, unsigned char* rgb, int B, int H, int W, const double* rgb_from_xyz,
+                        cudaStream_t s);
 
 int64_t launch_counter_add(int64_t n);  // global launch counter (introspection)
 

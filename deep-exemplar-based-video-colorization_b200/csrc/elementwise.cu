@@ -697,6 +697,80 @@ void launch_make_last(const float* IA_l, const float* ab, float* last, int B, in
   launch_counter_add(1);
 }
 
+namespace {
+struct Mat3 {
+  double m[9];
+};
+// util.py:134-151 -> skimage.color.lab2rgb, all in float64 like the reference; one thread per pixel
+__global__ void __launch_bounds__(256) lab_to_rgb8_kernel(const float* __restrict__ l, const float* __restrict__ ab,
+                                                          unsigned char* __restrict__ rgb, int HW, const Mat3 M) {
+  const int b = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const double L = (double)l[(size_t)b * HW + i] + 50.0;  // l_norm = 1, l_mean = 50 (util.py:15-18)
+    const double A = (double)ab[((size_t)b * 2 + 0) * HW + i], Bq = (double)ab[((size_t)b * 2 + 1) * HW + i];
+    double f[3];
+    f[1] = (L + 16.0) / 116.0;
+    f[0] = A / 500.0 + f[1];
+    f[2] = f[1] - Bq / 200.0;
+    if (f[2] < 0.0) f[2] = 0.0;
+    const double white[3] = {0.95047, 1.0, 1.08883};
+    double xyz[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      xyz[k] = (f[k] > 0.2068966 ? f[k] * f[k] * f[k] : (f[k] - 16.0 / 116.0) / 7.787) * white[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double v = xyz[0] * M.m[k * 3 + 0] + xyz[1] * M.m[k * 3 + 1] + xyz[2] * M.m[k * 3 + 2];
+      v = v > 0.0031308 ? 1.055 * pow(v, 1.0 / 2.4) - 0.055 : v * 12.92;
+      v = fmin(fmax(v, 0.0), 1.0);
+      rgb[((size_t)b * HW + i) * 3 + k] = (unsigned char)(v * 255.0);
+    }
+  }
+}
+}  // namespace
+
+namespace {
+// util_distortion.py:18-23 -> skimage.color.rgb2lab in float64, then ToTensor (.float()) and Normalize (L - 50)
+__global__ void __launch_bounds__(256) rgb8_to_lab_kernel(const unsigned char* __restrict__ rgb, float* __restrict__ lab, int HW) {
+  const int b = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    double c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double v = (double)rgb[((size_t)b * HW + i) * 3 + k] / 255.0;
+      c[k] = v > 0.04045 ? pow((v + 0.055) / 1.055, 2.4) : v / 12.92;
+    }
+    const double M[9] = {0.412453, 0.357580, 0.180423, 0.212671, 0.715160, 0.072169, 0.019334, 0.119193, 0.950227};
+    const double white[3] = {0.95047, 1.0, 1.08883};
+    double f[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double t = (c[0] * M[k * 3 + 0] + c[1] * M[k * 3 + 1] + c[2] * M[k * 3 + 2]) / white[k];
+      f[k] = t > 0.008856 ? cbrt(t) : 7.787 * t + 16.0 / 116.0;
+    }
+    const float L = (float)(116.0 * f[1] - 16.0), A = (float)(500.0 * (f[0] - f[1])), Bq = (float)(200.0 * (f[1] - f[2]));
+    lab[((size_t)b * 3 + 0) * HW + i] = L - 50.0f;
+    lab[((size_t)b * 3 + 1) * HW + i] = A;
+    lab[((size_t)b * 3 + 2) * HW + i] = Bq;
+  }
+}
+}  // namespace
+
+void launch_rgb8_to_lab(const unsigned char* rgb, float* lab, int B, int H, int W, cudaStream_t s) {
+  dim3 grid(grid_for((long)H * W, 256), B);
+  rgb8_to_lab_kernel<<<grid, 256, 0, s>>>(rgb, lab, H * W);
+  launch_counter_add(1);
+}
+
+void launch_lab_to_rgb8(const float* l, const float* ab, unsigned char* rgb, int B, int H, int W, const double* rgb_from_xyz,
+                        cudaStream_t s) {
+  Mat3 M;
+  for (int i = 0; i < 9; ++i) M.m[i] = rgb_from_xyz[i];
+  dim3 grid(grid_for((long)H * W, 256), B);
+  lab_to_rgb8_kernel<<<grid, 256, 0, s>>>(l, ab, rgb, H * W, M);
+  launch_counter_add(1);
+}
+
 void launch_resize_half(const float* src, float* dst, int planes, int H, int W, cudaStream_t s) {
   resize_half_kernel<<<grid_for((long)planes * (H / 2) * (W / 2), 256), 256, 0, s>>>(src, dst, planes, H, W);
   launch_counter_add(1);

@@ -22,7 +22,7 @@ EXPORTED = [
     "dvc_set_exemplar", "dvc_colorize_frames", "dvc_colorize_clip", "dvc_exemplar_pack_size",
     "dvc_exemplar_export", "dvc_exemplar_import", "dvc_launch_count", "dvc_profile_corr", "dvc_corr_mean_ms",
     "dvc_debug_set_flag", "dvc_debug_get_buffer", "dvc_profile_conv", "dvc_conv_profile",
-    "dvc_resize_half", "dvc_upsample2_scaled",
+    "dvc_resize_half", "dvc_upsample2_scaled", "dvc_lab_to_rgb8", "dvc_rgb8_to_lab",
 ]
 
 _lib = None
@@ -75,6 +75,8 @@ def load_library():
         lib.dvc_corr_mean_ms.restype = ctypes.c_double
         lib.dvc_resize_half.argtypes = [c_void, c_void, c_int, c_int, c_int, c_void, c_void]
         lib.dvc_upsample2_scaled.argtypes = [c_void, c_void, c_int, c_int, c_int, c_float, c_void, c_void]
+        lib.dvc_lab_to_rgb8.argtypes = [c_void, c_void, c_void, c_int, c_int, c_int, c_void, c_void]
+        lib.dvc_rgb8_to_lab.argtypes = [c_void, c_void, c_int, c_int, c_int, c_void, c_void]
         lib.dvc_profile_conv.argtypes = [c_void, c_int]
         lib.dvc_conv_profile.argtypes = [c_void, c_int, c_int, P(ctypes.c_double), P(ctypes.c_double)]
         lib.dvc_debug_set_flag.argtypes = [c_void, ctypes.c_char_p, c_int]
@@ -271,6 +273,30 @@ class Context:
         out = torch.empty(B, C, 2 * h, 2 * w, device=x.device, dtype=torch.float32)
         self._check(self.lib.dvc_upsample2_scaled(self.h, _ptr(x), B * C, h, w, float(scale), _ptr(out), _stream(x.device)),
                     "dvc_upsample2_scaled")
+        return out
+
+    def lab_to_rgb8(self, l, ab):
+        """batch_lab2rgb_transpose_mc (utils/util.py:140-151) for CUDA l [B,1,H,W] (centred) and ab [B,2,H,W]:
+        uint8 [B,H,W,3] sRGB, computed in float64 like skimage.color.lab2rgb."""
+        l, ab = _dev_f32(l, "lab_to_rgb8 l"), _dev_f32(ab, "lab_to_rgb8 ab")
+        B, _, H, W = l.shape
+        if tuple(ab.shape) != (B, 2, H, W) or l.shape[1] != 1:
+            raise DvcError("lab_to_rgb8: expected l [B,1,H,W] and ab [B,2,H,W]")
+        out = torch.empty(B, H, W, 3, device=l.device, dtype=torch.uint8)
+        self._check(self.lib.dvc_lab_to_rgb8(self.h, _ptr(l), _ptr(ab), B, H, W, ctypes.c_void_p(out.data_ptr()), _stream(l.device)),
+                    "dvc_lab_to_rgb8")
+        return out
+
+    def rgb8_to_lab(self, rgb):
+        """RGB2Lab + ToTensor + Normalize of test.py:44-45 for a CUDA uint8 [B,H,W,3] tensor: float32 [B,3,H,W] with
+        centred L, computed in float64 like skimage.color.rgb2lab."""
+        if not (isinstance(rgb, torch.Tensor) and rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.dim() == 4 and rgb.shape[3] == 3):
+            raise DvcError("rgb8_to_lab: expected a CUDA uint8 tensor [B,H,W,3]")
+        rgb = rgb.contiguous()
+        B, H, W, _ = rgb.shape
+        out = torch.empty(B, 3, H, W, device=rgb.device, dtype=torch.float32)
+        self._check(self.lib.dvc_rgb8_to_lab(self.h, ctypes.c_void_p(rgb.data_ptr()), B, H, W, _ptr(out), _stream(rgb.device)),
+                    "dvc_rgb8_to_lab")
         return out
 
     # ---- multi-GPU: exemplar operands as one flat buffer (broadcast with torch.distributed / NCCL) ----

@@ -132,6 +132,18 @@ int dvc_resize_half(dvc_ctx* ctx, const float* dev_src, int planes, int H, int W
 int dvc_upsample2_scaled(dvc_ctx* ctx, const float* dev_src, int planes, int h, int w, float scale, float* dev_dst,
                          void* stream);
 
+/* Output colour conversion of test.py:116-119 = utils/util.py:134-151 (batch_lab2rgb_transpose_mc for one image):
+ * Lab = (l + 50, ab) -> skimage.color.lab2rgb (float64: D65 / 2-degree white point, z < 0 -> 0, the 0.2068966 cube
+ * threshold, rgb_from_xyz = inv(xyz_from_rgb), sRGB gamma) -> clip [0,1] -> * 255 -> truncation to uint8.
+ * dev_l [B,1,H,W] (centred L), dev_ab [B,2,H,W] -> dev_rgb [B,H,W,3] uint8 (the layout cv2 / PIL write). */
+int dvc_lab_to_rgb8(dvc_ctx* ctx, const float* dev_l, const float* dev_ab, int B, int H, int W, unsigned char* dev_rgb,
+                    void* stream);
+
+/* Ingest colour conversion of test.py:44-45 = RGB2Lab + ToTensor + Normalize (utils/util_distortion.py:18-23,85-100):
+ * skimage.color.rgb2lab in float64 (uint8 / 255, inverse sRGB gamma, xyz_from_rgb, D65 / 2-degree white point,
+ * 0.008856 cube-root threshold), cast to float32, then L - 50.  dev_rgb [B,H,W,3] uint8 -> dev_lab [B,3,H,W]. */
+int dvc_rgb8_to_lab(dvc_ctx* ctx, const unsigned char* dev_rgb, int B, int H, int W, float* dev_lab, void* stream);
+
 /* ---- multi-GPU: exemplar operands travel once per clip ----------------------- */
 
 /* Size in floats of the packed exemplar operands (phi_hat planes + pooled Lab) for an HxW exemplar. */

@@ -21,6 +21,12 @@ writes tests/golden/*.npz.  tests/test_oracle_golden.py re-checks this file agai
 vectors on every run (CPU).  The reference itself ships no tests and no golden vectors
 (SURVEY.md §4), so these generated vectors are the only pin available.
 
+PARITY UNPINNED for two helpers outside the net path: `lab_to_rgb8` and `rgb8_to_lab` (the colour conversions of
+test.py:44-45,116-119) restate skimage.color.{lab2rgb,rgb2lab}, a dependency that is NOT installed in this image
+ and whose outputs therefore cannot be generated here; they are anchored on closed-form values, the
+round trip and the reference's own fp32 torch twin tensor_lab2rgb (tests/test_oracle_golden.py).  Everything on the
+net path is pinned as described above.
+
 The N x N correlation is evaluated in query-row chunks (`row_chunk`) so that 480x864
 (N=25920) and larger fit in host memory; per-row results are identical to the unchunked
 formulation because every row of NonlocalNet.py:477-497 is independent.
@@ -314,6 +320,56 @@ def resize_half(x):
 def upsample2_scaled(ab, scale=1.25):
     """test.py:100-102: F.interpolate(ab, scale_factor=2, mode="bilinear") * 1.25."""
     return F.interpolate(ab, scale_factor=2, mode="bilinear") * scale
+
+
+def lab_to_rgb8(l, ab):
+    """utils/util.py:140-151 (`batch_lab2rgb_transpose_mc`, one image per batch entry): Lab = (l + 50, ab) in float64 ->
+    skimage.color.lab2rgb -> clip -> * 255 -> uint8 (truncation), returned as [B,H,W,3].
+
+    PARITY UNPINNED for this function: `skimage` is not installed in this image, so the conversion is
+    restated from skimage.color.colorconv (lab2xyz: D65 / observer "2" white point (0.95047, 1, 1.08883), z < 0 -> 0,
+    threshold 0.2068966, (t - 16/116) / 7.787; xyz2rgb: rgb_from_xyz = inv(xyz_from_rgb), gamma threshold 0.0031308)
+    and anchored on the reference's own torch twin `tensor_lab2rgb` (utils/util.py:379-414, pinned bit-exactly by
+    tests/golden) in tests/test_oracle_golden.py."""
+    import numpy as np
+
+    lab = np.concatenate([l.double().numpy() + 50.0, ab.double().numpy()], axis=1).transpose(0, 2, 3, 1)  # [B,H,W,3]
+    L, A, Bq = lab[..., 0], lab[..., 1], lab[..., 2]
+    y = (L + 16.0) / 116.0
+    x = (A / 500.0) + y
+    z = y - (Bq / 200.0)
+    z = np.where(z < 0, 0.0, z)
+    out = np.stack([x, y, z], axis=-1)
+    mask = out > 0.2068966
+    out = np.where(mask, np.power(out, 3.0), (out - 16.0 / 116.0) / 7.787)
+    out = out * np.array([0.95047, 1.0, 1.08883])
+    xyz_from_rgb = np.array([[0.412453, 0.357580, 0.180423], [0.212671, 0.715160, 0.072169], [0.019334, 0.119193, 0.950227]])
+    arr = out @ np.linalg.inv(xyz_from_rgb).T
+    mask = arr > 0.0031308
+    arr = np.where(mask, 1.055 * np.power(np.where(mask, arr, 1.0), 1 / 2.4) - 0.055, arr * 12.92)
+    return torch.from_numpy((np.clip(arr, 0, 1) * 255).astype("uint8"))
+
+
+def rgb8_to_lab(rgb):
+    """test.py:44-45: RGB2Lab (util_distortion.py:18-23, skimage.color.rgb2lab in float64) -> ToTensor (lib/functional.py:
+    85-103, `.float()` without /255) -> Normalize (util_distortion.py:85-92: L - 50).  rgb: uint8 [B,H,W,3] -> float32
+    [B,3,H,W].  PARITY UNPINNED (skimage absent): restated from skimage.color.colorconv (rgb2xyz: uint8 / 255, inverse
+    gamma threshold 0.04045; xyz2lab: D65 / observer "2" white point, threshold 0.008856, np.cbrt, 7.787 t + 16/116)."""
+    import numpy as np
+
+    arr = rgb.numpy().astype(np.float64) / 255.0
+    mask = arr > 0.04045
+    arr = np.where(mask, np.power((np.where(mask, arr, 1.0) + 0.055) / 1.055, 2.4), arr / 12.92)
+    xyz_from_rgb = np.array([[0.412453, 0.357580, 0.180423], [0.212671, 0.715160, 0.072169], [0.019334, 0.119193, 0.950227]])
+    xyz = arr @ xyz_from_rgb.T
+    t = xyz / np.array([0.95047, 1.0, 1.08883])
+    mask = t > 0.008856
+    f = np.where(mask, np.cbrt(t), 7.787 * t + 16.0 / 116.0)
+    x, y, z = f[..., 0], f[..., 1], f[..., 2]
+    lab = np.stack([116.0 * y - 16.0, 500.0 * (x - y), 200.0 * (y - z)], axis=1)  # [B,3,H,W] float64
+    out = torch.from_numpy(lab).float()
+    out[:, 0:1] = out[:, 0:1] - 50.0
+    return out
 
 
 def legal_shape(H, W):

@@ -37,3 +37,51 @@ def test_half_resolution_pipeline_roundtrip(ctx):
     up = ctx.upsample2_scaled(ab)
     assert up.shape == (1, 2, 64, 96) and torch.isfinite(up).all()
     assert torch.allclose(up.cpu(), O.upsample2_scaled(ab.cpu()), atol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 48), (2, 216, 384), (1, 1, 1)])
+def test_lab_to_rgb8_matches_float64_oracle(ctx, shape):
+    """Output conversion of test.py:116-119 (utils/util.py:140-151): float64 skimage-style Lab -> sRGB -> uint8
+    truncation.  CUDA's and numpy's double pow() may differ in the last ulp, which can flip a truncation only when
+    v * 255 sits within ~1e-13 of an integer: allow one level on at most 1e-5 of the values."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(11)
+    l = torch.rand(B, 1, H, W, generator=g) * 100 - 50
+    ab = (torch.rand(B, 2, H, W, generator=g) * 2 - 1) * 110  # includes out-of-gamut colours (clipped channels)
+    ref = O.lab_to_rgb8(l, ab)
+    out = ctx.lab_to_rgb8(l.cuda(), ab.cuda()).cpu()
+    assert out.shape == ref.shape == (B, H, W, 3) and out.dtype == torch.uint8
+    d = (out.int() - ref.int()).abs()
+    assert int(d.max()) <= 1
+    assert float((d > 0).float().mean()) <= 1e-5
+
+
+def test_post_processing_chain_on_device(ctx):
+    """test.py:99-119 without the WLS filter: ab x2 * 1.25 -> Lab -> RGB uint8, all on the device."""
+    big = make_lab(7, 1, 64, 96)
+    ab = torch.randn(1, 2, 32, 48, generator=torch.Generator().manual_seed(3)) * 20
+    up = ctx.upsample2_scaled(ab.cuda())
+    rgb = ctx.lab_to_rgb8(big[:, 0:1].cuda(), up).cpu()
+    ref = O.lab_to_rgb8(big[:, 0:1], O.upsample2_scaled(ab))
+    d = (rgb.int() - ref.int()).abs()
+    assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-3  # fp32 up-sampling differs by ~1e-6 before truncation
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 48), (2, 216, 384)])
+def test_rgb8_to_lab_matches_float64_oracle(ctx, shape):
+    """Ingest conversion of test.py:44-45 (skimage rgb2lab in float64 -> float32 -> L - 50)."""
+    B, H, W = shape
+    rgb = torch.randint(0, 256, (B, H, W, 3), generator=torch.Generator().manual_seed(12), dtype=torch.uint8)
+    ref = O.rgb8_to_lab(rgb)
+    out = ctx.rgb8_to_lab(rgb.cuda()).cpu()
+    assert out.shape == ref.shape == (B, 3, H, W)
+    assert (out - ref).abs().max() <= 2e-5  # one fp32 ulp at |Lab| <= 128 is 7.6e-6
+
+
+def test_colour_round_trip_on_device(ctx):
+    """rgb8 -> Lab -> rgb8 reproduces every 8-bit colour of a ramp up to one level (truncating output conversion)."""
+    g = torch.arange(0, 256, dtype=torch.uint8)
+    rgb = torch.stack((g, g.flip(0), (g.int() * 7 % 256).to(torch.uint8)), -1).view(1, 16, 16, 3)
+    lab = ctx.rgb8_to_lab(rgb.cuda())
+    back = ctx.lab_to_rgb8(lab[:, 0:1].contiguous(), lab[:, 1:3].contiguous()).cpu()
+    assert int((back.int() - rgb.int()).abs().max()) <= 1

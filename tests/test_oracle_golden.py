@@ -96,3 +96,38 @@ def test_oracle_bit_exact_against_live_reference(sds):
         fBo = O.exemplar_features(sds["vgg"], IB)
         ab, warped, sim, fA = O.frame_colorization(sds, IA, IB, last, fBo)
     assert torch.equal(ab, ab_ref) and torch.equal(warped, warped_ref)
+
+
+def test_lab_to_rgb8_oracle_anchors():
+    """The float64 output conversion (utils/util.py:140-151) has no pinned reference here (skimage is absent), so it is
+    anchored on (a) closed-form values and (b) the reference's own fp32 torch twin `tensor_lab2rgb` (util.py:379-414),
+    which the golden vectors pin bit-exactly: same formula, so the uint8 results agree up to one level where the fp32
+    and float64 evaluations straddle a truncation boundary."""
+    l = torch.tensor([-50.0, 0.0, 50.0, 3.0]).view(4, 1, 1, 1)
+    ab = torch.zeros(4, 2, 1, 1)
+    got = O.lab_to_rgb8(l, ab)[:, 0, 0, :]
+    assert got[0].tolist() == [0, 0, 0]              # L = 0: black
+    assert min(got[2].tolist()) >= 254               # L = 100: white (a channel just below 1.0 truncates to 254)
+    assert got[1].tolist() == [118, 118, 118]        # L = 50: Y = 0.1842 -> sRGB 0.4663 -> 118.9
+    g = torch.Generator().manual_seed(5)
+    l = torch.rand(2, 1, 24, 40, generator=g) * 100 - 50
+    ab = (torch.rand(2, 2, 24, 40, generator=g) * 2 - 1) * 100
+    twin = O.tensor_lab2rgb(torch.cat((l + 50.0, ab), 1))  # [n,3,h,w] in [0,1]
+    twin8 = (twin.clamp(0, 1) * 255).to(torch.uint8).permute(0, 2, 3, 1)
+    d = (O.lab_to_rgb8(l, ab).int() - twin8.int()).abs()
+    assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 2e-2
+
+
+def test_rgb8_to_lab_oracle_anchors():
+    """Closed-form anchors of the (unpinned, skimage-restating) ingest conversion and its inverse."""
+    rgb = torch.tensor([[0, 0, 0], [255, 255, 255], [255, 0, 0]], dtype=torch.uint8).view(1, 1, 3, 3)
+    lab = O.rgb8_to_lab(rgb)[0, :, 0, :]  # [3 channels, 3 pixels]
+    assert abs(float(lab[0, 0]) + 50.0) < 1e-4 and abs(float(lab[1, 0])) < 1e-4            # black: L = 0
+    assert abs(float(lab[0, 1]) - 50.0) < 1e-2 and abs(float(lab[1, 1])) < 1e-2            # white: L = 100, a = b = 0
+    assert abs(float(lab[0, 2]) + 50.0 - 53.24) < 0.02 and abs(float(lab[1, 2]) - 80.09) < 0.05  # sRGB red: (53.24, 80.09, 67.20)
+    assert abs(float(lab[2, 2]) - 67.20) < 0.05
+    g = torch.Generator().manual_seed(8)
+    rgb = torch.randint(0, 256, (1, 20, 30, 3), generator=g, dtype=torch.uint8)
+    lab = O.rgb8_to_lab(rgb)
+    back = O.lab_to_rgb8(lab[:, 0:1], lab[:, 1:3])
+    assert int((back.int() - rgb.int()).abs().max()) <= 1
