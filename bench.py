@@ -82,7 +82,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self, t_begin=None, t_end=None):
+    def stop(self, windows=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         time.sleep(0.06)
@@ -91,7 +91,8 @@ class ClockSampler:
             self.proc.wait(timeout=3)
         except Exception:
             self.proc.kill()
-        rows = [l.split(",") for t, l in self.lines if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.06)]
+        inside = lambda t: windows is None or any(b <= t <= e + 0.06 for b, e in windows)
+        rows = [l.split(",") for t, l in self.lines if inside(t)]
         rows = [[x.strip() for x in r] for r in rows if len(r) >= 7]
         sm = sorted(int(r[0]) for r in rows if r[0].isdigit())
         mx = [int(r[1]) for r in rows if r[1].isdigit()]
@@ -283,7 +284,6 @@ def main():
     t_end = time.perf_counter()
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count(True)
-    clocks = sampler.stop(t_begin, t_end) if sampler else None
 
     # ---------------- leg 2: end to end through the clip API with host buffers ----------------
     host_out = torch.empty(K, 2, H, W).pin_memory()
@@ -291,11 +291,15 @@ def main():
     barrier()
     seg = host_L[Wm:Wm + K]
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin2 = time.perf_counter()
     e2.record()
     ctx.colorize_clip(seg, TEMPERATURE, out=host_out)  # per frame: H2D of L, full path, D2H of ab
     e3.record()
     barrier()
+    t_end2 = time.perf_counter()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    # clocks / throttle reasons sampled inside the two timed regions (value leg and e2e leg)
+    clocks = sampler.stop([(t_begin, t_end), (t_begin2, t_end2)]) if sampler else None
 
     # ---------------- leg 3: per-kernel durations, one stream, no overlap (for the roofline objects) ----------------
     # The clip API overlaps two streams, so a kernel's event-bracketed time there includes its neighbours; the

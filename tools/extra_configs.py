@@ -20,7 +20,7 @@ for side in (128, 256, 512):
     th = torch.nn.functional.normalize(torch.randn(1, 256, N, device="cuda", generator=g), dim=1)
     ph = torch.nn.functional.normalize(torch.randn(1, 256, N, device="cuda", generator=g), dim=1)
     V = torch.randn(1, N, 3, device="cuda", generator=g)
-    for name, mode in (("tf32x3", dvc.MATH_TF32X3), ("bf16x3", dvc.MATH_BF16X3)):
+    for name, mode in (("fp16x3", dvc.MATH_FP16X3), ("tf32x3", dvc.MATH_TF32X3)):
         ctx.set_math(conv=dvc.MATH_TF32X3, corr=mode)
         for T in (1e-10, 0.01):
             if side == 512 and T > 1e-9 and name == "tf32x3":
@@ -31,7 +31,19 @@ for side in (128, 256, 512):
             ms = ctx.corr_mean_ms(True)
             print(f"config5 corr-only features {side}x{side} N={N} {name} T={T:g}: {ms:.3f} ms  {2.0*N*N*259/ms/1e9:.0f} TFLOP/s algorithmic", flush=True)
     del th, ph, V
-ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_TF32X3)
+ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
+
+# ---- config 1: one 256x256 frame (latency) ----
+H, W = 256, 256
+ctx.set_exemplar(make_lab(4321, 1, H, W))
+L1 = make_lab(1234, 1, H, W)[:, 0:1].cuda(); last1 = torch.zeros(1, 3, H, W, device="cuda")
+for _ in range(3): ctx.colorize_frames(L1, last1)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+e0.record()
+for _ in range(10): ctx.colorize_frames(L1, last1)
+e1.record(); torch.cuda.synchronize()
+print(f"config1 256x256 frame (N=4096): {e0.elapsed_time(e1)/10:.3f} ms/frame on one stream", flush=True)
 
 # ---- config 4: one 736x1280 frame (N = 58880) ----
 H, W = 736, 1280
