@@ -319,7 +319,7 @@ template <bool SOFTMAX>
 __global__ void __launch_bounds__(256) corr_merge_kernel(const SplitOut* __restrict__ part, int nsplit, int rows, int NA,
                                                          int NB, int Bphi, float sc, const float4* __restrict__ V,
                                                          float4* __restrict__ y, float* __restrict__ sim,
-                                                         int* __restrict__ argmax) {
+                                                         int* __restrict__ argmax, const CorrPeers peers) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const int b = r / NA;
@@ -335,6 +335,10 @@ __global__ void __launch_bounds__(256) corr_merge_kernel(const SplitOut* __restr
     y[r] = make_float4(v.x, v.y, v.z, 0.f);
     sim[r] = m;
     if (argmax) argmax[r] = idx;
+    for (int g = 0; g < peers.n; ++g) {  // fused all-gather: the row goes to every GPU's full-size result
+      reinterpret_cast<float4*>(peers.y4[g])[peers.row0 + r] = make_float4(v.x, v.y, v.z, 0.f);
+      peers.sim[g][peers.row0 + r] = m;
+    }
   } else {
     float m = -INFINITY;
     for (int s = 0; s < nsplit; ++s) m = fmaxf(m, part[(size_t)s * rows + r].m);
@@ -348,6 +352,10 @@ __global__ void __launch_bounds__(256) corr_merge_kernel(const SplitOut* __restr
     y[r] = make_float4(a0 / ssum, a1 / ssum, a2 / ssum, 0.f);
     sim[r] = m;
     if (argmax) argmax[r] = -1;
+    for (int g = 0; g < peers.n; ++g) {
+      reinterpret_cast<float4*>(peers.y4[g])[peers.row0 + r] = make_float4(a0 / ssum, a1 / ssum, a2 / ssum, 0.f);
+      peers.sim[g][peers.row0 + r] = m;
+    }
   }
 }
 
@@ -460,10 +468,10 @@ int launch_corr_tc(const CorrParams& p, int math, cudaStream_t s, std::string* e
   const int rows = p.B * p.NA;
   if (softmax)
     corr_merge_kernel<true><<<(rows + 255) / 256, 256, 0, s>>>(tp.part, nsplit, rows, p.NA, p.NB, p.Bphi, tp.sc, tp.V,
-                                                                reinterpret_cast<float4*>(p.y), p.sim, p.argmax);
+                                                                reinterpret_cast<float4*>(p.y), p.sim, p.argmax, p.peers);
   else
     corr_merge_kernel<false><<<(rows + 255) / 256, 256, 0, s>>>(tp.part, nsplit, rows, p.NA, p.NB, p.Bphi, tp.sc, tp.V,
-                                                                 reinterpret_cast<float4*>(p.y), p.sim, p.argmax);
+                                                                 reinterpret_cast<float4*>(p.y), p.sim, p.argmax, p.peers);
   launch_counter_add(1);
   return 0;
 }

@@ -124,6 +124,7 @@ struct dvc_ctx {
   // default: tensor cores with fp32-class accuracy (3xTF32); DVC_MATH_FP32 selects the exact CUDA-core engines
   int conv_math = DVC_MATH_TF32X3, corr_math = DVC_MATH_FP16X3;
   int tc_kbytes = 128;    // tensor-core convolutions: K bytes per pipeline stage (64 or 128, see conv_tc.cu)
+  CorrPeers corr_peers;   // fused all-gather targets of dvc_corr_softmax_warp (dvc_corr_set_peer_outputs)
   ScaleCell* cell_next = nullptr;
   int cell_left = 0;
   int tc_tail = 0;        // tensor-core convolutions: 1 = 128-channel tiles for the partial last round of 256-channel
@@ -141,9 +142,10 @@ struct dvc_ctx {
   int tc_epoch[2] = {0, 0};   // split-K hand-over epochs, one flag buffer per arena
   int tc_splits = 1;          // split-K: 1 = off (default: measured no gain once two streams overlap), 0 = automatic, >1 = forced
   // clip driver: frame t+1's VGG/WarpNet/correlation overlaps frame t's ColorVidNet on two internal streams
-  cudaStream_t sA = nullptr, sC = nullptr;
+  cudaStream_t sA = nullptr, sC = nullptr, sU = nullptr, sD = nullptr;  // phase A, phase C, uploads, downloads
   cudaEvent_t evA[4] = {nullptr, nullptr, nullptr, nullptr}, evC[4] = {nullptr, nullptr, nullptr, nullptr}, evFork = nullptr,
-              evJoinA = nullptr, evJoinC = nullptr;
+              evJoinA = nullptr, evJoinC = nullptr, evJoinD = nullptr;
+  cudaEvent_t evU[4] = {nullptr, nullptr, nullptr, nullptr}, evD[4] = {nullptr, nullptr, nullptr, nullptr};
   // exemplar cache
   float* ex_phi = nullptr;  // [N][256]
   float* ex_V = nullptr;    // [N][4]
@@ -1079,11 +1081,16 @@ extern "C" int dvc_destroy(dvc_ctx* c) {
   if (c->sC) cudaStreamDestroy(c->sC);
   for (int i = 0; i < 4; ++i) {
     if (c->evA[i]) cudaEventDestroy(c->evA[i]);
+    if (c->evU[i]) cudaEventDestroy(c->evU[i]);
+    if (c->evD[i]) cudaEventDestroy(c->evD[i]);
     if (c->evC[i]) cudaEventDestroy(c->evC[i]);
   }
   if (c->evFork) cudaEventDestroy(c->evFork);
   if (c->evJoinA) cudaEventDestroy(c->evJoinA);
   if (c->evJoinC) cudaEventDestroy(c->evJoinC);
+  if (c->evJoinD) cudaEventDestroy(c->evJoinD);
+  if (c->sU) cudaStreamDestroy(c->sU);
+  if (c->sD) cudaStreamDestroy(c->sD);
   if (c->ex_phi) cudaFree(c->ex_phi);
   if (c->ex_V) cudaFree(c->ex_V);
   for (auto& ev : c->corr_events) cudaEventDestroy(ev.first), cudaEventDestroy(ev.second);
@@ -1322,8 +1329,68 @@ extern "C" int dvc_corr_softmax_warp(dvc_ctx* c, const float* theta_hat, const f
   CorrParams p{};
   p.theta = (float*)th, p.phi = (float*)ph, p.V = (float*)V4, p.B = B, p.Bphi = Bphi, p.NA = NA, p.NB = NB, p.C = C;
   p.temperature = temperature, p.y = (float*)y4, p.sim = sim, p.argmax = argmax;
+  if (c->corr_peers.n > 0) {
+    if (B != 1) return fail(c, DVC_ERR_SHAPE, "corr: peer outputs need B = 1");
+    if (c->corr_math == DVC_MATH_FP32) return fail(c, DVC_ERR_STATE, "corr: peer outputs need a tensor-core correlation mode");
+    p.peers = c->corr_peers;
+  }
   DVC_TRY(run_corr(c, p, s));
   CUDA_TRY(c, cudaMemcpy2DAsync(y, 12, y4, 16, 12, (size_t)B * NA, cudaMemcpyDeviceToDevice, s));
+  return DVC_OK;
+}
+
+// ---- query-row-sharded correlation: peer-mapped result buffers (CUDA IPC between the per-GPU processes) -----------
+extern "C" int dvc_peer_buffer_create(dvc_ctx* c, int64_t bytes, void** dev_ptr, unsigned char* handle64) {
+  if (!c || !dev_ptr || !handle64 || bytes < 1) return c ? fail(c, DVC_ERR_ARG, "peer_buffer_create: bad argument") : DVC_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  void* p = nullptr;
+  CUDA_TRY(c, cudaMalloc(&p, (size_t)bytes));
+  CUDA_TRY(c, cudaMemset(p, 0, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(c, DVC_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return DVC_OK;
+}
+
+extern "C" int dvc_peer_buffer_open(dvc_ctx* c, const unsigned char* handle64, void** dev_ptr) {
+  if (!c || !dev_ptr || !handle64) return c ? fail(c, DVC_ERR_ARG, "peer_buffer_open: bad argument") : DVC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  CUDA_TRY(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *dev_ptr = p;
+  return DVC_OK;
+}
+
+extern "C" int dvc_peer_buffer_close(dvc_ctx* c, void* opened_ptr) {
+  if (!c || !opened_ptr) return c ? fail(c, DVC_ERR_ARG, "peer_buffer_close: bad argument") : DVC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaIpcCloseMemHandle(opened_ptr));
+  return DVC_OK;
+}
+
+extern "C" int dvc_peer_buffer_destroy(dvc_ctx* c, void* created_ptr) {
+  if (!c || !created_ptr) return c ? fail(c, DVC_ERR_ARG, "peer_buffer_destroy: bad argument") : DVC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  CUDA_TRY(c, cudaFree(created_ptr));
+  return DVC_OK;
+}
+
+extern "C" int dvc_corr_set_peer_outputs(dvc_ctx* c, int n, float* const* y4, float* const* sim, int64_t row0) {
+  if (!c || n < 0 || n > 8 || row0 < 0 || (n > 0 && (!y4 || !sim))) return c ? fail(c, DVC_ERR_ARG, "corr_set_peer_outputs: bad argument") : DVC_ERR_ARG;
+  c->corr_peers = CorrPeers();
+  for (int g = 0; g < n; ++g) {
+    if (!y4[g] || !sim[g]) return fail(c, DVC_ERR_ARG, "corr_set_peer_outputs: null destination");
+    c->corr_peers.y4[g] = y4[g], c->corr_peers.sim[g] = sim[g];
+  }
+  c->corr_peers.n = n, c->corr_peers.row0 = row0;
   return DVC_OK;
 }
 
@@ -1435,7 +1502,12 @@ static int clip_streams(dvc_ctx* c) {
   if (c->sA) return DVC_OK;
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->sA, cudaStreamNonBlocking));
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->sC, cudaStreamNonBlocking));
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->sU, cudaStreamNonBlocking));
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->sD, cudaStreamNonBlocking));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->evJoinD, cudaEventDisableTiming));
   for (int i = 0; i < 4; ++i) {
+    CUDA_TRY(c, cudaEventCreateWithFlags(&c->evU[i], cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&c->evD[i], cudaEventDisableTiming));
     CUDA_TRY(c, cudaEventCreateWithFlags(&c->evA[i], cudaEventDisableTiming));
     CUDA_TRY(c, cudaEventCreateWithFlags(&c->evC[i], cudaEventDisableTiming));
   }
@@ -1447,7 +1519,9 @@ static int clip_streams(dvc_ctx* c) {
 
 // test.py:68-96 for one contiguous segment.  Frame t+1's frame-independent phase (VGG / WarpNet / correlation)
 // runs on stream A while frame t's ColorVidNet -- which needs frame t-1's prediction -- runs on stream C; the
-// low-resolution layers of either leave SMs idle that the other fills.  L / ab may be host (pinned) or device.
+// partial waves of either leave SMs idle that the other fills.  Uploads of L (up to four frames ahead) and downloads
+// of ab run on two copy streams so that neither compute stream ever waits for PCIe.  L / ab may be host (pinned) or
+// device memory.
 extern "C" int dvc_colorize_clip(dvc_ctx* c, const float* L_in, int F, int H, int W, float temperature,
                                  const float* first_last, float* ab_out, void* stream) {
   if (!c || !L_in || !ab_out || F < 1) return c ? fail(c, DVC_ERR_ARG, "colorize_clip: bad argument") : DVC_ERR_ARG;
@@ -1458,9 +1532,9 @@ extern "C" int dvc_colorize_clip(dvc_ctx* c, const float* L_in, int F, int H, in
   const size_t hw = (size_t)H * W;
   const int N = (H / 4) * (W / 4);
   void *dL, *dlast, *dab, *yrows, *simrows;
-  DVC_TRY(get_raw(c, "clip.L", 2 * hw * 4, &dL, s));
+  DVC_TRY(get_raw(c, "clip.L", 4 * hw * 4, &dL, s));   // 4 slots
   DVC_TRY(get_raw(c, "clip.last", 3 * hw * 4, &dlast, s));
-  DVC_TRY(get_raw(c, "clip.ab", 2 * hw * 4, &dab, s));
+  DVC_TRY(get_raw(c, "clip.ab", 2 * 2 * hw * 4, &dab, s));  // 2 slots
   DVC_TRY(get_raw(c, "clip.yrows", (size_t)2 * N * 16, &yrows, s));
   DVC_TRY(get_raw(c, "clip.simrows", (size_t)2 * N * 4, &simrows, s));
   if (first_last)
@@ -1470,28 +1544,41 @@ extern "C" int dvc_colorize_clip(dvc_ctx* c, const float* L_in, int F, int H, in
   CUDA_TRY(c, cudaEventRecord(c->evFork, s));
   CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evFork, 0));
   CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evFork, 0));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->sU, c->evFork, 0));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->sD, c->evFork, 0));
   for (int t = 0; t < F; ++t) {
     const int slot = t & 1;
-    float* Lt = (float*)dL + slot * hw;
+    float* Lt = (float*)dL + (size_t)(t & 3) * hw;
+    float* abt = (float*)dab + (size_t)slot * 2 * hw;
     float* yr = (float*)yrows + (size_t)slot * N * 4;
     float* sr = (float*)simrows + (size_t)slot * N;
-    // ---- stream A: upload + frame-independent phase; slot reuse waits for frame t-2's ColorVidNet ----
+    // ---- upload stream: the L slot was last read by frame t-4's ColorVidNet / make_last ----
+    if (t >= 4) CUDA_TRY(c, cudaStreamWaitEvent(c->sU, c->evC[(t - 4) & 3], 0));
+    CUDA_TRY(c, cudaMemcpyAsync(Lt, L_in + (size_t)t * hw, hw * 4, cudaMemcpyDefault, c->sU));
+    CUDA_TRY(c, cudaEventRecord(c->evU[t & 3], c->sU));
+    // ---- stream A: frame-independent phase; the warp-row slot reuse waits for frame t-2's ColorVidNet ----
+    CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evU[t & 3], 0));
     if (t >= 2) CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evC[(t - 2) & 3], 0));
-    CUDA_TRY(c, cudaMemcpyAsync(Lt, L_in + (size_t)t * hw, hw * 4, cudaMemcpyDefault, c->sA));
     DVC_TRY(frames_phaseA(c, "clipA", Lt, 1, H, W, temperature, yr, sr, c->sA));
     CUDA_TRY(c, cudaEventRecord(c->evA[t & 3], c->sA));
     // ---- stream C: the recurrent phase ----
     CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evA[t & 3], 0));
-    DVC_TRY(frames_phaseC(c, "clipC", Lt, yr, sr, (float*)dlast, 1, H, W, (float*)dab, c->sC));
-    launch_make_last(Lt, (float*)dab, (float*)dlast, 1, H, W, c->sC);  // test.py:96
+    if (t >= 2) CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evD[(t - 2) & 3], 0));  // the ab slot has been downloaded
+    DVC_TRY(frames_phaseC(c, "clipC", Lt, yr, sr, (float*)dlast, 1, H, W, abt, c->sC));
+    launch_make_last(Lt, abt, (float*)dlast, 1, H, W, c->sC);  // test.py:96
     DVC_TRY(check_launch(c, "make_last"));
-    CUDA_TRY(c, cudaMemcpyAsync(ab_out + (size_t)t * 2 * hw, dab, 2 * hw * 4, cudaMemcpyDefault, c->sC));
     CUDA_TRY(c, cudaEventRecord(c->evC[t & 3], c->sC));
+    // ---- download stream ----
+    CUDA_TRY(c, cudaStreamWaitEvent(c->sD, c->evC[t & 3], 0));
+    CUDA_TRY(c, cudaMemcpyAsync(ab_out + (size_t)t * 2 * hw, abt, 2 * hw * 4, cudaMemcpyDefault, c->sD));
+    CUDA_TRY(c, cudaEventRecord(c->evD[t & 3], c->sD));
   }
   CUDA_TRY(c, cudaEventRecord(c->evJoinA, c->sA));
   CUDA_TRY(c, cudaEventRecord(c->evJoinC, c->sC));
+  CUDA_TRY(c, cudaEventRecord(c->evJoinD, c->sD));
   CUDA_TRY(c, cudaStreamWaitEvent(s, c->evJoinA, 0));
   CUDA_TRY(c, cudaStreamWaitEvent(s, c->evJoinC, 0));
+  CUDA_TRY(c, cudaStreamWaitEvent(s, c->evJoinD, 0));
   CUDA_TRY(c, cudaStreamSynchronize(s));
   return DVC_OK;
 }

@@ -192,6 +192,16 @@ void launch_final_ab(const float* x, int H, int W, int P, int C, const float* w 
 void launch_make_last(const float* IA_l, const float* ab, float* last, int B, int H, int W, cudaStream_t s);
 
 // ---- correlation + softmax + warp (K7) ----------------------------------------------------------
+// Peer outputs of a query-row-sharded correlation: the rank that owns query rows
+// [row0, row0 + NA) stores its result rows straight into the full-size result buffers of every GPU of the box
+// (peer-mapped device pointers over NVLink) from the kernel that finalises them -- the all-gather IS the epilogue.
+struct CorrPeers {
+  int n = 0;           // number of destination GPUs (0: off)
+  long long row0 = 0;  // global index of this rank's first query row
+  float* y4[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [N_total][4] each
+  float* sim[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [N_total] each
+};
+
 struct CorrParams {
   const float* theta;  // [B][NA][C]  (position-major, channels contiguous)
   const float* phi;    // [Bphi][NB][C]
@@ -201,6 +211,7 @@ struct CorrParams {
   float* y;     // [B][NA][4]
   float* sim;   // [B][NA]
   int* argmax;  // [B][NA] or nullptr
+  CorrPeers peers;  // optional fused all-gather of (y, sim) rows (B = 1 only)
 };
 void launch_corr_simt(const CorrParams& p, cudaStream_t s);
 // [B][C][N] -> [B][N][C] and back (the C ABI of the stand-alone correlation entry is channel-major)

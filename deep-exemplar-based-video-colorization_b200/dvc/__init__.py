@@ -23,6 +23,8 @@ EXPORTED = [
     "dvc_exemplar_export", "dvc_exemplar_import", "dvc_launch_count", "dvc_profile_corr", "dvc_corr_mean_ms",
     "dvc_debug_set_flag", "dvc_debug_get_buffer", "dvc_profile_conv", "dvc_conv_profile",
     "dvc_resize_half", "dvc_upsample2_scaled", "dvc_lab_to_rgb8", "dvc_rgb8_to_lab",
+    "dvc_peer_buffer_create", "dvc_peer_buffer_open", "dvc_peer_buffer_close", "dvc_peer_buffer_destroy",
+    "dvc_corr_set_peer_outputs",
 ]
 
 _lib = None
@@ -77,6 +79,11 @@ def load_library():
         lib.dvc_upsample2_scaled.argtypes = [c_void, c_void, c_int, c_int, c_int, c_float, c_void, c_void]
         lib.dvc_lab_to_rgb8.argtypes = [c_void, c_void, c_void, c_int, c_int, c_int, c_void, c_void]
         lib.dvc_rgb8_to_lab.argtypes = [c_void, c_void, c_int, c_int, c_int, c_void, c_void]
+        lib.dvc_peer_buffer_create.argtypes = [c_void, c_i64, P(c_void), ctypes.c_char_p]
+        lib.dvc_peer_buffer_open.argtypes = [c_void, ctypes.c_char_p, P(c_void)]
+        lib.dvc_peer_buffer_close.argtypes = [c_void, c_void]
+        lib.dvc_peer_buffer_destroy.argtypes = [c_void, c_void]
+        lib.dvc_corr_set_peer_outputs.argtypes = [c_void, c_int, P(c_void), P(c_void), c_i64]
         lib.dvc_profile_conv.argtypes = [c_void, c_int]
         lib.dvc_conv_profile.argtypes = [c_void, c_int, c_int, P(ctypes.c_double), P(ctypes.c_double)]
         lib.dvc_debug_set_flag.argtypes = [c_void, ctypes.c_char_p, c_int]
@@ -298,6 +305,36 @@ class Context:
         self._check(self.lib.dvc_rgb8_to_lab(self.h, ctypes.c_void_p(rgb.data_ptr()), B, H, W, _ptr(out), _stream(rgb.device)),
                     "dvc_rgb8_to_lab")
         return out
+
+    # ---- query-row-sharded correlation: peer-mapped result buffers (CUDA IPC) ----------------------------
+    def peer_buffer_create(self, nbytes):
+        """(device pointer, 64-byte IPC handle) of a fresh zeroed cudaMalloc allocation other ranks can map."""
+        ptr, handle = ctypes.c_void_p(0), ctypes.create_string_buffer(64)
+        self._check(self.lib.dvc_peer_buffer_create(self.h, int(nbytes), ctypes.byref(ptr), handle), "dvc_peer_buffer_create")
+        return ptr.value, handle.raw
+
+    def peer_buffer_open(self, handle):
+        ptr = ctypes.c_void_p(0)
+        self._check(self.lib.dvc_peer_buffer_open(self.h, ctypes.create_string_buffer(bytes(handle), 64), ctypes.byref(ptr)),
+                    "dvc_peer_buffer_open")
+        return ptr.value
+
+    def peer_buffer_close(self, ptr):
+        self._check(self.lib.dvc_peer_buffer_close(self.h, ctypes.c_void_p(ptr)), "dvc_peer_buffer_close")
+
+    def peer_buffer_destroy(self, ptr):
+        self._check(self.lib.dvc_peer_buffer_destroy(self.h, ctypes.c_void_p(ptr)), "dvc_peer_buffer_destroy")
+
+    def corr_set_peer_outputs(self, y4_ptrs=(), sim_ptrs=(), row0=0):
+        """Route the result rows of the next corr_softmax_warp calls into these peer buffers as well (empty = off)."""
+        n = len(y4_ptrs)
+        ya = (ctypes.c_void_p * max(n, 1))(*[ctypes.c_void_p(p) for p in y4_ptrs])
+        sa = (ctypes.c_void_p * max(n, 1))(*[ctypes.c_void_p(p) for p in sim_ptrs])
+        self._check(self.lib.dvc_corr_set_peer_outputs(self.h, n, ya, sa, int(row0)), "dvc_corr_set_peer_outputs")
+
+    def raw_view(self, ptr, numel):
+        """float32 tensor view of `numel` elements at a device pointer owned by the library."""
+        return _raw_view(ptr, numel, self.device)
 
     # ---- multi-GPU: exemplar operands as one flat buffer (broadcast with torch.distributed / NCCL) ----
     def exemplar_pack_size(self, H, W):

@@ -53,3 +53,66 @@ def colorize_clip_sharded(ctx, host_L, IB_lab, temperature=1e-10, src=0, group=N
     if not seg.is_pinned():
         seg = seg.pin_memory()
     return s, e, ctx.colorize_clip(seg, temperature)
+
+
+class RowShardedCorrelation:
+    """Single-frame scaling of K7 (NonlocalNet.py:477-498) over the GPUs of one box (BASELINE config 4).
+
+    Every query row is independent, so rank r takes the contiguous rows `segment_bounds(N, world, r)` of theta_hat
+    against the full phi_hat / V.  The result rows are not all-gathered afterwards: the kernel that finalises a row
+    stores it into the full-size (y, sim) buffer of EVERY rank through peer-mapped pointers (CUDA IPC allocations,
+    NVLink stores), so after one barrier each rank holds the complete result.  One process per GPU
+    (torch.distributed: NCCL on the GPU box); world size <= 8.
+    """
+
+    def __init__(self, ctx, n_rows, group=None):
+        self.ctx, self.group, self.N = ctx, group, int(n_rows)
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        if self.world > 8:
+            raise ValueError("RowShardedCorrelation: at most 8 ranks (one NVLink box)")
+        self.row0, self.row1 = segment_bounds(self.N, self.world, self.rank)
+        # my full-size result buffers: y4 [N][4] followed by sim [N]
+        self._own, handle = ctx.peer_buffer_create(self.N * 20)
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, handle, group=group)
+        else:
+            handles[0] = handle
+        self._opened = []
+        self._y4, self._sim = [], []
+        for r, h in enumerate(handles):
+            base = self._own if r == self.rank else ctx.peer_buffer_open(h)
+            if r != self.rank:
+                self._opened.append(base)
+            self._y4.append(base)
+            self._sim.append(base + self.N * 16)
+
+    def __call__(self, theta_hat, phi_hat, V, temperature):
+        """theta_hat [1,256,N], phi_hat [1,256,NB], V [1,NB,3] (identical on every rank) -> (y [1,N,3], sim [1,N])."""
+        if theta_hat.shape[0] != 1 or theta_hat.shape[2] != self.N:
+            raise ValueError("RowShardedCorrelation: theta_hat must be [1,C,N]")
+        ctx = self.ctx
+        if self.row1 > self.row0:
+            ctx.corr_set_peer_outputs(self._y4, self._sim, self.row0)
+            try:
+                ctx.corr_softmax_warp(theta_hat[:, :, self.row0:self.row1].contiguous(), phi_hat, V, temperature)
+            finally:
+                ctx.corr_set_peer_outputs()
+        torch.cuda.synchronize(ctx.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)  # every rank's rows have landed in every buffer
+        flat = ctx.raw_view(self._own, self.N * 5)
+        y = flat[: self.N * 4].view(1, self.N, 4)[:, :, :3].clone()
+        sim = flat[self.N * 4:].view(1, self.N).clone()
+        return y, sim
+
+    def close(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)  # nobody may still be writing into a buffer that is about to go away
+        for p in self._opened:
+            self.ctx.peer_buffer_close(p)
+        self._opened = []
+        if self._own:
+            self.ctx.peer_buffer_destroy(self._own)
+            self._own = 0

@@ -146,6 +146,22 @@ int dvc_rgb8_to_lab(dvc_ctx* ctx, const unsigned char* dev_rgb, int B, int H, in
 
 /* ---- multi-GPU: exemplar operands travel once per clip ----------------------- */
 
+/* ---- single-frame scaling: query-row-sharded correlation with a fused all-gather (BASELINE config 4) --
+ * Every row of NonlocalNet.py:477-498 is independent, so G GPUs can each take N/G query rows of one frame against the
+ * full exemplar side.  Instead of an NCCL all-gather after the kernel, the kernel that finalises a result row stores it
+ * into the full-size result buffer of EVERY GPU through peer-mapped pointers (NVLink stores).  The buffers are plain
+ * cudaMalloc allocations shared between the one-process-per-GPU ranks with CUDA IPC. */
+
+/* Allocate `bytes` of device memory and return its IPC handle (64 bytes, cudaIpcMemHandle_t) for the other ranks. */
+int dvc_peer_buffer_create(dvc_ctx* ctx, int64_t bytes, void** dev_ptr, unsigned char* handle64);
+/* Map another rank's buffer (handle from its dvc_peer_buffer_create) into this process; enables peer access. */
+int dvc_peer_buffer_open(dvc_ctx* ctx, const unsigned char* handle64, void** dev_ptr);
+int dvc_peer_buffer_close(dvc_ctx* ctx, void* opened_ptr);
+int dvc_peer_buffer_destroy(dvc_ctx* ctx, void* created_ptr);
+/* Until cleared with n = 0, dvc_corr_softmax_warp (B = 1) additionally stores row r of its result as global row
+ * row0 + r into y4[g] ([N_total][4] floats: L, a, b, 0) and sim[g] ([N_total]) for g < n <= 8. */
+int dvc_corr_set_peer_outputs(dvc_ctx* ctx, int n, float* const* y4, float* const* sim, int64_t row0);
+
 /* Size in floats of the packed exemplar operands (phi_hat planes + pooled Lab) for an HxW exemplar. */
 int64_t dvc_exemplar_pack_size(const dvc_ctx* ctx, int H, int W);
 /* Pack the cached exemplar operands into / install them from a flat device buffer, so that the

@@ -100,6 +100,38 @@ s, e = segment_bounds(9, 2, rank)
 got = [None, None]
 dist.all_gather_object(got, (s, e))
 assert got == [(0, 5), (5, 9)], got
+# query-row-sharded correlation (dvc/clip.py: RowShardedCorrelation): handle exchange, row partition and the peer
+# pointer table, with a stand-in context that emulates "peer memory" through per-rank files (no GPU in this test)
+from dvc.clip import RowShardedCorrelation
+import numpy as np
+class FakeCtx:
+    device = "cpu"
+    def __init__(self, rank, tmp): self.rank, self.tmp, self.routes = rank, tmp, None
+    def peer_buffer_create(self, nbytes):
+        path = os.path.join(self.tmp, f"buf{self.rank}.bin"); np.zeros(nbytes // 4, np.float32).tofile(path)
+        return 1000 + self.rank, path.encode().ljust(64, b"\0")
+    def peer_buffer_open(self, handle): return 1000 + int(handle.rstrip(b"\0").decode()[-5])
+    def peer_buffer_close(self, ptr): pass
+    def peer_buffer_destroy(self, ptr): pass
+    def corr_set_peer_outputs(self, y4=(), sim=(), row0=0): self.routes = (list(y4), list(sim), row0) if y4 else self.routes
+    def corr_softmax_warp(self, th, ph, V, T):
+        y4, sim, row0 = self.routes
+        for base in y4:  # "store into every rank's buffer": row r of the shard -> global row row0 + r
+            path = os.path.join(self.tmp, f"buf{base - 1000}.bin")
+            mm = np.memmap(path, np.float32, "r+")
+            n = th.shape[2]
+            mm[(row0) * 4:(row0 + n) * 4] = np.repeat(np.arange(row0, row0 + n, dtype=np.float32), 4)
+            mm.flush()
+    def raw_view(self, ptr, numel): return torch.from_numpy(np.fromfile(os.path.join(self.tmp, f"buf{ptr - 1000}.bin"), np.float32)[:numel].copy())
+torch.cuda.synchronize = lambda *a, **k: None
+N = 11
+fc = FakeCtx(rank, sys.argv[5])
+sh = RowShardedCorrelation(fc, N)
+assert (sh.row0, sh.row1) == ((0, 6) if rank == 0 else (6, 11))
+assert sh._y4 == [1000, 1001] and sh._sim == [1000 + N * 16, 1001 + N * 16]
+y, sim = sh(torch.zeros(1, 256, N), torch.zeros(1, 256, 4), torch.zeros(1, 4, 3), 1e-10)
+assert torch.equal(y[0, :, 0], torch.arange(N, dtype=torch.float32)), y[0, :, 0]   # both shards landed in MY buffer
+sh.close()
 dist.barrier(); dist.destroy_process_group()
 print("OK", rank)
 """
@@ -111,7 +143,7 @@ def test_exemplar_broadcast_world2_gloo(tmp_path):
     script.write_text(_WORKER)
     pkg = os.path.join(ROOT, "deep-exemplar-based-video-colorization_b200")
     port = str(29500 + os.getpid() % 2000)
-    procs = [subprocess.Popen([sys.executable, str(script), ROOT, pkg, port, str(r)], stdout=subprocess.PIPE,
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, pkg, port, str(r), str(tmp_path)], stdout=subprocess.PIPE,
                               stderr=subprocess.STDOUT) for r in range(2)]
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
