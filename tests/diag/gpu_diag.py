@@ -1,6 +1,6 @@
 """Scratch diagnostics for a GPU box: stage-by-stage error report + rough timings (not a bench)."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "deep-exemplar-based-video-colorization_b200"))
 import numpy as np, torch
 import dvc

@@ -1,6 +1,6 @@
 """Scratch: precision budget of the fp32 CUDA path (plain vs two-level accumulation) against the fp64 oracle."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "deep-exemplar-based-video-colorization_b200"))
 import numpy as np, torch
 import dvc
