@@ -203,6 +203,8 @@ def main():
                     help="K bytes per pipeline stage of the conv engine (64 = twice the stages, measured slower)")
     ap.add_argument("--tc-f16", type=int, default=int(os.environ.get("DVC_TC_F16", "1")),
                     help="1: convolutions with bounded inputs run 3xFP16 on scaled planes; 0: 3xTF32 everywhere")
+    ap.add_argument("--corr-cluster", type=int, default=int(os.environ.get("DVC_CORR_CLUSTER", "2")), choices=[1, 2],
+                    help="2 = CTA pairs (tcgen05.mma.cta_group::2) in the correlation kernel, 1 = single CTAs")
     ap.add_argument("--tc-tail", type=int, default=int(os.environ.get("DVC_TC_TAIL", "0")),
                     help="1: partial last rounds of 256-channel conv launches run on 128-channel tiles; 0: off")
     ap.add_argument("--tc-splits", type=int, default=int(os.environ.get("DVC_TC_SPLITS", "1")),
@@ -243,6 +245,7 @@ def main():
     ctx.debug_flag("tc_splits", args.tc_splits)
     ctx.debug_flag("tc_f16", args.tc_f16)
     ctx.debug_flag("tc_tail", args.tc_tail)
+    ctx.debug_flag("corr_cluster", args.corr_cluster)
 
     K, Wm = args.steps, args.warmup
     # every rank owns its own contiguous segment of synthetic frames (distinct content per rank and per step)

@@ -64,10 +64,17 @@ namespace {
 
 constexpr int BM = 128;        // query rows per CTA (= TMEM lanes)
 constexpr int BN = 256;        // reference positions per score tile (= TMEM columns per accumulator)
-constexpr int STAGES = 2;
-constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 98304
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+// CL = 2: CTA pairs (tcgen05.mma.cta_group::2) on two adjacent 128-row query tiles.  The three MMAs per k-step
+// re-read both operands from shared memory, which binds a single CTA to the 128 B/clk shared-memory port (96 KB of TMA
+// writes + 144 KB of MMA reads per 1536 tensor cycles = 156 B/clk; ncu: tensor pipe 74-82 %).  In a pair each CTA
+// stages its own query rows and HALF of the reference-position tile (104 B/clk), and three 64 KB stages fit.
+template <int CL>
+struct Cfg {
+  static constexpr int STAGES = CL == 2 ? 3 : 2;
+  static constexpr int A_BYTES = BM * 128, B_BYTES = (BN / CL) * 128;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 98304 / 65536
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
 constexpr int NTHREADS = 192;
 
 struct SplitOut {  // per (split, row) partial statistics
@@ -136,14 +143,17 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
 }
 
 // ---- main kernel ---------------------------------------------------------------------------------------
-template <int FMT, bool SOFTMAX>
+template <int FMT, bool SOFTMAX, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
     corr_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
   constexpr bool TF32 = (FMT == 0);
   constexpr int KB = TF32 ? 32 : 64;       // K elements per 128-byte k-block
   constexpr int UMMA_K_BYTES = 32;         // one MMA consumes 32 bytes of K (8 tf32 / 16 bf16)
-  constexpr uint32_t IDESC = tc::umma_idesc(FMT == 0 ? 2u : (FMT == 1 ? 1u : 0u), BM, BN);  // tf32 / bf16 / f16
+  constexpr uint32_t IDESC = tc::umma_idesc(FMT == 0 ? 2u : (FMT == 1 ? 1u : 0u), BM * CL, BN);  // tf32 / bf16 / f16
+  constexpr int STAGES = Cfg<CL>::STAGES, A_BYTES = Cfg<CL>::A_BYTES, B_BYTES = Cfg<CL>::B_BYTES;
+  constexpr int STAGE_BYTES = Cfg<CL>::STAGE_BYTES;
+  const int crank = (CL == 2) ? (int)tc::cluster_ctarank() : 0;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -170,15 +180,22 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc::tma_prefetch_desc(&tmBh);
     tc::tma_prefetch_desc(&tmBl);
     for (int i = 0; i < STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
-    for (int i = 0; i < 2; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 4);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 4 * CL);  // pair: both epilogues
     tc::fence_barrier_init();
   }
+  if (CL == 2) tc::cluster_sync_all();  // both CTAs are resident before the pair allocation
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, 512);
-    tc::tmem_relinquish();
+    if (CL == 2) {
+      tc::tmem_alloc_pair(tmem_slot, 512);
+      tc::tmem_relinquish_pair();
+    } else {
+      tc::tmem_alloc(tmem_slot, 512);
+      tc::tmem_relinquish();
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (CL == 2) tc::cluster_sync_all();  // the peer's barriers are initialised before any remote arrive reaches them
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -193,11 +210,20 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           tc::mbar_wait(&empty[stage], phase ^ 1);
           if (tc::elect_one()) {
             uint8_t* st = smem + stage * STAGE_BYTES;
-            tc::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-            tc::tma_load_2d(st, &tmAh, &full[stage], kb * KB, b * p.NA + m0);
-            tc::tma_load_2d(st + A_BYTES, &tmAl, &full[stage], kb * KB, b * p.NA + m0);
-            tc::tma_load_2d(st + 2 * A_BYTES, &tmBh, &full[stage], kb * KB, col0);
-            tc::tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmBl, &full[stage], kb * KB, col0);
+            if (CL == 1) {
+              tc::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+              tc::tma_load_2d(st, &tmAh, &full[stage], kb * KB, b * p.NA + m0);
+              tc::tma_load_2d(st + A_BYTES, &tmAl, &full[stage], kb * KB, b * p.NA + m0);
+              tc::tma_load_2d(st + 2 * A_BYTES, &tmBh, &full[stage], kb * KB, col0);
+              tc::tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmBl, &full[stage], kb * KB, col0);
+            } else {  // my query rows and my half of the reference positions; the leader's barrier counts all bytes
+              if (crank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+              const int hrow = crank * (BN / 2);
+              tc::tma_load_2d_pair(st, &tmAh, &full[stage], kb * KB, b * p.NA + m0);
+              tc::tma_load_2d_pair(st + A_BYTES, &tmAl, &full[stage], kb * KB, b * p.NA + m0);
+              tc::tma_load_2d_pair(st + 2 * A_BYTES, &tmBh, &full[stage], kb * KB, col0 + hrow);
+              tc::tma_load_2d_pair(st + 2 * A_BYTES + B_BYTES, &tmBl, &full[stage], kb * KB, col0 + hrow);
+            }
           }
           __syncwarp();
           if (++stage == STAGES) stage = 0, phase ^= 1;
@@ -205,8 +231,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (warp-convergent loop, one elected lane issues) =================
-    {
+    // ================= MMA issuer (warp-convergent loop, one elected lane issues; pair: leader CTA only) =====
+    if (CL == 1 || crank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
@@ -226,12 +252,23 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             for (int kk = 0; kk < 128 / UMMA_K_BYTES; ++kk) {
               const uint64_t adv = (uint64_t)((kk * UMMA_K_BYTES) >> 4);  // start-address field is in 16-byte units
               // small cross terms first, the dominant hi.hi term last
-              tc::umma_ss<TF32>(d, dAl + adv, dBh + adv, IDESC, (kb | kk) ? 1u : 0u);
-              tc::umma_ss<TF32>(d, dAh + adv, dBl + adv, IDESC, 1u);
-              tc::umma_ss<TF32>(d, dAh + adv, dBh + adv, IDESC, 1u);
+              if (CL == 1) {
+                tc::umma_ss<TF32>(d, dAl + adv, dBh + adv, IDESC, (kb | kk) ? 1u : 0u);
+                tc::umma_ss<TF32>(d, dAh + adv, dBl + adv, IDESC, 1u);
+                tc::umma_ss<TF32>(d, dAh + adv, dBh + adv, IDESC, 1u);
+              } else {
+                tc::umma_ss_pair<TF32>(d, dAl + adv, dBh + adv, IDESC, (kb | kk) ? 1u : 0u);
+                tc::umma_ss_pair<TF32>(d, dAh + adv, dBl + adv, IDESC, 1u);
+                tc::umma_ss_pair<TF32>(d, dAh + adv, dBh + adv, IDESC, 1u);
+              }
             }
-            tc::umma_commit(&empty[stage]);  // smem stage reusable once these MMAs have read it
-            if (kb == nkb - 1) tc::umma_commit(&tfull[buf]);
+            if (CL == 1) {
+              tc::umma_commit(&empty[stage]);  // smem stage reusable once these MMAs have read it
+              if (kb == nkb - 1) tc::umma_commit(&tfull[buf]);
+            } else {
+              tc::umma_commit_pair_mc(&empty[stage], 3);
+              if (kb == nkb - 1) tc::umma_commit_pair_mc(&tfull[buf], 3);
+            }
           }
           __syncwarp();
           if (++stage == STAGES) stage = 0, phase ^= 1;
@@ -297,7 +334,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+      if (lane == 0) {
+        if (CL == 1)
+          tc::mbar_arrive(&tempty[buf]);
+        else
+          tc::mbar_arrive_leader(&tempty[buf]);
+      }
     }
     if (row < p.NA) {
       SplitOut o;
@@ -308,9 +350,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 
   tc::tc_fence_before();
   __syncthreads();
+  if (CL == 2) tc::cluster_sync_all();  // the leader's MMAs read the peer's shared memory until the very end
   if (warp == 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 512);
+    if (CL == 2)
+      tc::tmem_dealloc_pair(tmem_base, 512);
+    else
+      tc::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -377,23 +423,34 @@ int ws_get(int i, size_t bytes, void** out) {
   return 0;
 }
 
-template <int FMT, bool SOFTMAX>
-int launch_main(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl,
-                const TcParams& tp, dim3 grid, cudaStream_t s) {
+template <int FMT, bool SOFTMAX, int CL>
+int launch_main_cl(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl,
+                   const TcParams& tp, dim3 grid, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(corr_tc_kernel<FMT, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) !=
+    if (cudaFuncSetAttribute(corr_tc_kernel<FMT, SOFTMAX, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CL>::SMEM_BYTES) !=
         cudaSuccess)
       return -1;
     attr = true;
   }
-  corr_tc_kernel<FMT, SOFTMAX><<<grid, NTHREADS, SMEM_BYTES, s>>>(mAh, mAl, mBh, mBl, tp);
-  return 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<CL>::SMEM_BYTES, cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, corr_tc_kernel<FMT, SOFTMAX, CL>, mAh, mAl, mBh, mBl, tp) == cudaSuccess ? 0 : -2;
+}
+template <int FMT, bool SOFTMAX>
+int launch_main(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl,
+                const TcParams& tp, dim3 grid, int cl, cudaStream_t s) {
+  return cl == 2 ? launch_main_cl<FMT, SOFTMAX, 2>(mAh, mAl, mBh, mBl, tp, grid, s)
+                 : launch_main_cl<FMT, SOFTMAX, 1>(mAh, mAl, mBh, mBl, tp, grid, s);
 }
 
 }  // namespace
 
-int launch_corr_tc(const CorrParams& p, int math, cudaStream_t s, std::string* err) {
+int launch_corr_tc(const CorrParams& p, int math, int cluster, cudaStream_t s, std::string* err) {
   auto fail = [&](const char* m) {
     if (err) *err = m;
     return -1;
@@ -408,7 +465,8 @@ int launch_corr_tc(const CorrParams& p, int math, cudaStream_t s, std::string* e
     return fail("workspace allocation failed");
 
   // column-range splits so that (row blocks x batch x splits) fills the 148 SMs in whole waves
-  const int row_blocks = (p.NA + BM - 1) / BM;
+  const int cl = cluster == 2 ? 2 : 1;
+  const int row_blocks = ((p.NA + BM - 1) / BM + cl - 1) / cl * cl;  // pairs: an even number of 128-row query tiles
   const int ntiles = (p.NB + BN - 1) / BN;
   int nsplit = 1;
   {
@@ -444,8 +502,8 @@ int launch_corr_tc(const CorrParams& p, int math, cudaStream_t s, std::string* e
   CUtensorMap mAh, mAl, mBh, mBl;
   const uint32_t boxk = tf32 ? 32 : 64;
   if (encode_tmap_2d(&mAh, Ah, (uint64_t)p.B * p.NA, p.C, BM, boxk, eb) || encode_tmap_2d(&mAl, Al, (uint64_t)p.B * p.NA, p.C, BM, boxk, eb) ||
-      encode_tmap_2d(&mBh, Bh, (uint64_t)p.Bphi * p.NB, p.C, BN, boxk, eb) ||
-      encode_tmap_2d(&mBl, Bl, (uint64_t)p.Bphi * p.NB, p.C, BN, boxk, eb))
+      encode_tmap_2d(&mBh, Bh, (uint64_t)p.Bphi * p.NB, p.C, BN / cl, boxk, eb) ||
+      encode_tmap_2d(&mBl, Bl, (uint64_t)p.Bphi * p.NB, p.C, BN / cl, boxk, eb))
     return fail("cuTensorMapEncodeTiled failed");
 
   TcParams tp;
@@ -458,12 +516,12 @@ int launch_corr_tc(const CorrParams& p, int math, cudaStream_t s, std::string* e
   const bool softmax = !(p.temperature <= 2e-10f);
   int rc;
   if (fmt == 0)
-    rc = softmax ? launch_main<0, true>(mAh, mAl, mBh, mBl, tp, grid, s) : launch_main<0, false>(mAh, mAl, mBh, mBl, tp, grid, s);
+    rc = softmax ? launch_main<0, true>(mAh, mAl, mBh, mBl, tp, grid, cl, s) : launch_main<0, false>(mAh, mAl, mBh, mBl, tp, grid, cl, s);
   else if (fmt == 1)
-    rc = softmax ? launch_main<1, true>(mAh, mAl, mBh, mBl, tp, grid, s) : launch_main<1, false>(mAh, mAl, mBh, mBl, tp, grid, s);
+    rc = softmax ? launch_main<1, true>(mAh, mAl, mBh, mBl, tp, grid, cl, s) : launch_main<1, false>(mAh, mAl, mBh, mBl, tp, grid, cl, s);
   else
-    rc = softmax ? launch_main<2, true>(mAh, mAl, mBh, mBl, tp, grid, s) : launch_main<2, false>(mAh, mAl, mBh, mBl, tp, grid, s);
-  if (rc) return fail("cudaFuncSetAttribute(max dynamic smem) failed");
+    rc = softmax ? launch_main<2, true>(mAh, mAl, mBh, mBl, tp, grid, cl, s) : launch_main<2, false>(mAh, mAl, mBh, mBl, tp, grid, cl, s);
+  if (rc) return fail(rc == -1 ? "cudaFuncSetAttribute(max dynamic smem) failed" : "cudaLaunchKernelEx failed");
   launch_counter_add(1);
   const int rows = p.B * p.NA;
   if (softmax)

@@ -6,5 +6,6 @@
 
 namespace dvc {
 // math = DVC_MATH_TF32X3 or DVC_MATH_BF16X3.  Returns 0 on success, non-zero with *err set otherwise.
-int launch_corr_tc(const CorrParams& p, int math, cudaStream_t s, std::string* err);
+// cluster: 2 = CTA pairs (tcgen05.mma.cta_group::2) on adjacent query-row tiles, 1 = single CTAs
+int launch_corr_tc(const CorrParams& p, int math, int cluster, cudaStream_t s, std::string* err);
 }  // namespace dvc

@@ -127,6 +127,7 @@ struct dvc_ctx {
   CorrPeers corr_peers;   // fused all-gather targets of dvc_corr_softmax_warp (dvc_corr_set_peer_outputs)
   ScaleCell* cell_next = nullptr;
   int cell_left = 0;
+  int corr_cluster = 2;   // correlation: 2 = CTA pairs (tcgen05.mma.cta_group::2), 1 = single CTAs
   int tc_tail = 0;        // tensor-core convolutions: 1 = 128-channel tiles for the partial last round of 256-channel
                           // launches (-1.3 % on one stream, +1.6 % in the two-stream clip pipeline: off by default)
   int tc_f16 = 1;         // tensor-core convolutions: fp16 hi/lo planes for layers with provably bounded inputs
@@ -865,7 +866,7 @@ static int run_corr(dvc_ctx* c, const CorrParams& p, cudaStream_t s) {
     launch_corr_simt(p, s);
   } else {
     std::string err;
-    if (launch_corr_tc(p, c->corr_math, s, &err) != 0) return fail(c, DVC_ERR_CUDA, "corr_tc: " + err);
+    if (launch_corr_tc(p, c->corr_math, c->corr_cluster, s, &err) != 0) return fail(c, DVC_ERR_CUDA, "corr_tc: " + err);
   }
   DVC_TRY(check_launch(c, "corr"));
   if (c->prof_corr) {
@@ -1115,6 +1116,7 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!c || !name) return DVC_ERR_ARG;
   if (!strcmp(name, "two_level")) { c->two_level = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_kc")) { c->tc_kc = value < 1 ? 1 : value; return DVC_OK; }
+  if (!strcmp(name, "corr_cluster")) { c->corr_cluster = value == 1 ? 1 : 2; return DVC_OK; }
   if (!strcmp(name, "tc_tail")) { c->tc_tail = value < 0 ? 0 : value; return DVC_OK; }  // > 1: pretend pair-slot count (tests)
   if (!strcmp(name, "tc_f16")) { c->tc_f16 = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_splits")) { c->tc_splits = value < 0 ? 0 : (value > 8 ? 8 : value); return DVC_OK; }

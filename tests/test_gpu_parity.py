@@ -85,14 +85,18 @@ def test_vgg19_all_keys_and_no_preprocess(ctx, conv_math, sds):
 
 
 # ------------------------------------------------------------------------------------------ K7
-@pytest.fixture(params=["fp32", "tf32x3", "bf16x3", "fp16x3"])
+@pytest.fixture(params=["fp32", "tf32x3", "bf16x3", "fp16x3", "tf32x3-single", "fp16x3-single"])
 def corr_math(request, ctx):
-    """Run the correlation tests on the CUDA-core kernel and on both tcgen05 operand-split modes."""
+    """Run the correlation tests on the CUDA-core kernel and on the tcgen05 operand-split modes, as CTA pairs
+    (cta_group::2, the default) and as single CTAs."""
     import dvc
 
-    mode = {"fp32": dvc.MATH_FP32, "tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3, "fp16x3": dvc.MATH_FP16X3}[request.param]
+    name = request.param.replace("-single", "")
+    mode = {"fp32": dvc.MATH_FP32, "tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3, "fp16x3": dvc.MATH_FP16X3}[name]
     ctx.set_math(conv=dvc.MATH_TF32X3, corr=mode)
-    yield request.param
+    ctx.debug_flag("corr_cluster", 1 if request.param.endswith("-single") else 2)
+    yield name
+    ctx.debug_flag("corr_cluster", 2)
     ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
 
 
