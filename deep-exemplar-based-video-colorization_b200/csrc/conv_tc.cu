@@ -1,20 +1,27 @@
-// Convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA): DVC_MATH_TF32X3.
+// Convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA): DVC_MATH_TF32X3 (and its 3xFP16 default).
 //
 // Same flat shifted GEMM as conv_simt.cu (Y[p, co] = sum_tap sum_ci X[p + off(tap), ci] W[tap][ci][co] over the
-// padded pixel index p), with fp32-class accuracy from three kind::tf32 MMAs per product on hi/lo split
-// operands (x = hi + lo, both exactly representable in tf32):  hi.hi + hi.lo + lo.hi  -> one fp32 TMEM tile.
-// Activations therefore live in HBM as two padded-NHWC planes (hi, lo); weights are split once at load time.
+// padded pixel index p), with fp32-class accuracy from three 16/19-bit MMAs per product on hi/lo split operands
+// (x = hi + lo):  lo.hi + hi.lo + hi.hi  -> one fp32 TMEM tile.  Activations therefore live in HBM as two
+// padded-NHWC planes; weights are split once at load time.  Default operand format: fp16 planes of x * 2^e with an
+// exact power-of-two scale e (a host constant for tensors with a proven bound, else derived on the device from the
+// measured max |input| and the weights' L1 norm: dvc_internal.cuh, DynOut); tf32 planes (fp32 words) remain for
+// inputs without a known bound.
 //
-// Persistent kernel, one CTA per SM, static round-robin over the (pixel tile, channel tile) grid:
-//   warp 0      TMA producer: per (tap, 32-channel k-block) loads X_hi, X_lo [128 px x 128 B] at row offset
-//               off(tap) -- negative / past-the-end rows are zero-filled by TMA -- and W_hi, W_lo [BN x 128 B],
-//               SWIZZLE_128B, into an mbarrier ring (2/3/4 stages for BN = 256/128/64).
-//   warp 1      TMEM owner + MMA issuer: 4 k-steps x 3 tcgen05.mma (M128 x N=BN x K8) per stage into one of two
-//               TMEM accumulators; tcgen05.commit frees the stage / publishes the tile.
-//   warps 2..5  epilogue (overlaps the next tile's MMAs): thread t owns output pixel t of the tile: tcgen05.ld 32
-//               channels at a time, + bias, + skip addend, activation, InstanceNorm statistics (warp shuffle ->
-//               shared atomics -> one double atomic per channel and tile), masked store of the interior pixel as
-//               fp32 or as hi/lo planes for the next tensor-core layer.
+// Persistent kernel, one CTA per SM, CTA PAIRS by default (tcgen05.mma.cta_group::2 on two adjacent pixel tiles),
+// static round-robin over the (pixel-tile pair, channel tile) grid; 384 threads:
+//   warp 0       TMA producer: per (tap, 128-byte k-block) loads X_hi, X_lo [128 px x 128 B] at row offset
+//                off(tap) -- negative / past-the-end rows are zero-filled by TMA -- and W_hi, W_lo [BN(/2) x 128 B],
+//                SWIZZLE_128B, into an mbarrier ring; in a pair every CTA loads its own pixel rows and half of the
+//                channel rows, all bytes are counted on the leader's barrier.
+//   warp 1       TMEM owner + MMA issuer (leader CTA of a pair): 4 k-steps x 3 tcgen05.mma per k-block (the two cross
+//                terms of the whole k-block first, hi.hi last) into a ring of 512/BN TMEM accumulators;
+//                tcgen05.commit (multicast in a pair) frees the stage / publishes the chunk.
+//   warps 4..11  epilogue: every chunk (kc k-blocks) the TMEM partial sum is added to fp32 register totals with
+//                round-to-nearest adds (the TMEM accumulator truncates); then + bias, + skip addend, activation,
+//                InstanceNorm statistics (transpose-reduce in registers -> one double atomic per channel and tile),
+//                measured max |y|, masked store of the interior pixel as fp32 / tf32 planes / fp16 planes -- or the
+//                fused 1x1 + tanh tail of ColorVidNet instead of a store.
 // Replaces nn.Conv2d (+ReLU/LeakyReLU/skip add) at NonlocalNet.py:235-255,364-423 and ColorVidNet.py:96-143.
 #include <cuda.h>
 #include <cuda_fp16.h>

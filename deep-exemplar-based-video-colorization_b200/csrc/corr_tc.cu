@@ -8,8 +8,9 @@
 // all three accumulated into the same fp32 TMEM tile.  A third format, FP16X3, splits x * 2^14 into two fp16 planes
 // (theta_hat / phi_hat are unit vectors, so the fixed power-of-two scale is exact and cannot overflow): the same
 // 2 x 11 significant bits as tf32 at twice the MMA rate and half the operand bytes; scores come out times 2^28.
-// DVC_MATH_TF32X3 is the parity mode (|df| ~ 1e-7,
-// fp32 class), DVC_MATH_BF16X3 the fast mode (|df| ~ 2e-6).
+// FP16X3 is the default (|df| ~ 5e-7, argmax identical to fp64 on every test); DVC_MATH_TF32X3 (|df| ~ 1e-7) and
+// DVC_MATH_BF16X3 (|df| ~ 2e-6) are selectable.  By default two CTAs on adjacent query tiles run as a pair
+// (tcgen05.mma.cta_group::2, each staging half of the reference tile; Cfg<2> below); the single-CTA form:
 //
 // Kernel structure (one CTA = 128 query rows x a range of 256-column tiles of reference positions):
 //   warp 0      TMA producer: per k-block (128 bytes of K) loads A_hi, A_lo [128 x 128B] and B_hi, B_lo [256 x 128B]
