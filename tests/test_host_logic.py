@@ -175,3 +175,16 @@ print("RESOLVED")
     pkg = os.path.join(ROOT, "deep-exemplar-based-video-colorization_b200")
     out = subprocess.run([sys.executable, "-c", code, pkg], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "RESOLVED" in out.stdout, out.stdout + out.stderr
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/dvc.h is the drop-in boundary: it must compile as C99 (extern "C" only under __cplusplus, no C++ types),
+    and every prototype must take plain pointers / sizes."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "dvc.h"\nint main(void) { return dvc_version() == 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    hdr = open(os.path.join(inc, "dvc.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)  # prototypes only, comments stripped
+    assert "torch" not in code.lower() and "std::" not in code and "at::" not in code and "Tensor" not in code
