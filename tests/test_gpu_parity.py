@@ -196,6 +196,33 @@ def test_colorvidnet_module_vs_golden(ctx, conv_math, name):
 
 
 # ------------------------------------------------------------------------------------------ fused frame path
+@pytest.mark.parametrize("scale", [1e-4, 3e-2, 1.0, 4e2, 1e5])
+def test_device_derived_scales_follow_the_input_magnitude(ctx, sds, scale):
+    """The fp16 hi/lo planes of the conv -> ReLU -> conv chains get their exponent on the device from the measured
+    max |input| (DynOut): the same network input scaled by 1e-4 ... 1e5 must come out as accurate as at scale 1
+    (compared with the fp64 oracle on the same scaled input; the first InstanceNorm removes the scale, so the fp32
+    reference's own distance to fp64 is the yardstick).  Also covers VGG19, whose outputs scale linearly."""
+    import dvc
+
+    ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(1, 7, 32, 48, generator=g) * 30 * scale
+    with torch.no_grad():
+        ref64 = O.colorvidnet_forward({k: v.double() for k, v in sds["color"].items()}, x.double()).numpy()
+        ref32 = O.colorvidnet_forward(sds["color"], x).numpy()
+    out = ctx.colorvidnet_forward(x.cuda()).cpu().numpy()
+    floor = np.abs(ref32.astype(np.float64) - ref64).max()
+    err = np.abs(out.astype(np.float64) - ref64).max()
+    assert np.isfinite(out).all() and err <= max(1e-3, 2.0 * floor), (scale, err, floor)
+    rgb = (torch.rand(1, 3, 32, 48, generator=g) * scale)
+    with torch.no_grad():
+        f64 = O.vgg19_forward({k: v.double() for k, v in sds["vgg"].items()}, rgb.double(), preprocess=False)
+    outs = ctx.vgg19_forward(rgb.cuda(), ["r12", "r22", "r32", "r42", "r52"], False)
+    for o, r in zip(outs, f64):
+        r = r.numpy()
+        assert np.abs(o.cpu().numpy().astype(np.float64) - r).max() <= 1e-4 * max(np.abs(r).max(), 1e-30)
+
+
 @pytest.mark.parametrize("name", ["small_32x48", "padbranch_40x64", "softmax_32x64", "softmax5_48x48", "default_216x384"])
 def test_fused_frame_vs_golden(ctx, conv_math, name):
     g = load_golden(name)
