@@ -28,6 +28,7 @@
 #include <math.h>
 
 #include "conv_tc.cuh"
+#include "corr_tc.cuh"
 #include "tc_common.cuh"
 
 namespace dvc {
@@ -511,12 +512,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 template <int BN, int CL, int KBY, bool F16>
 int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap& mWh, const CUtensorMap& mWl,
               const ConvTcParams& p, int num_sms, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_mask = 0;  // the attribute is per device
+  if (first_use_on_device(&attr_mask)) {
     if (cudaFuncSetAttribute(conv_tc_kernel<BN, CL, KBY, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, KBY, CL>::SMEM_BYTES) !=
         cudaSuccess)
       return -1;
-    attr = true;
   }
   const int m_tiles = p.mtn ? p.mtn : (p.Mtot + BM - 1) / BM;
   const int items = ((m_tiles + CL - 1) / CL) * (p.CoutPad / BN) * p.splits;

@@ -11,6 +11,7 @@
 //   SOFTMAX mode: flash-style online softmax (running max, running sum, 3 weighted colour sums).
 #include <math.h>
 
+#include "corr_tc.cuh"
 #include "dvc_internal.cuh"
 
 namespace dvc {
@@ -209,11 +210,10 @@ __global__ void __launch_bounds__(256) corr_simt_kernel(const CorrParams p) {
 void launch_corr_simt(const CorrParams& p, cudaStream_t s) {
   const size_t smem = ((size_t)p.C * BM + 2 * BK * BN) * sizeof(float) + BN * sizeof(float4);
   dim3 grid((p.NA + BM - 1) / BM, p.B);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;  // the attribute is per device
+  if (first_use_on_device(&attr_mask)) {
     cudaFuncSetAttribute(corr_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(corr_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
   }
   if (p.temperature <= 2e-10f)
     corr_simt_kernel<false><<<grid, 256, smem, s>>>(p);

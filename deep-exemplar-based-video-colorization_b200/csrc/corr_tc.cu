@@ -406,33 +406,26 @@ __global__ void __launch_bounds__(256) corr_merge_kernel(const SplitOut* __restr
   }
 }
 
-// workspace cache (planes + partials), grown on demand; one per process/device like the context
-struct TcWorkspace {
-  void* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t cap[5] = {0, 0, 0, 0, 0};
-};
-TcWorkspace g_ws;
-
-int ws_get(int i, size_t bytes, void** out) {
-  if (g_ws.cap[i] < bytes) {
-    if (g_ws.buf[i]) cudaFree(g_ws.buf[i]);
-    g_ws.buf[i] = nullptr;
-    if (cudaMalloc(&g_ws.buf[i], bytes) != cudaSuccess) return -1;
-    g_ws.cap[i] = bytes;
+int ws_get(CorrWorkspace* ws, int i, size_t bytes, void** out) {
+  if (ws->cap[i] < bytes) {  // growth outside dvc_set_exemplar's reservation: a stand-alone call with a new shape
+    if (ws->buf[i]) cudaFree(ws->buf[i]);
+    ws->buf[i] = nullptr, ws->cap[i] = 0;
+    if (i == 2 || i == 3) ws->phi_src = nullptr, ws->phi_version = -1;
+    if (cudaMalloc(&ws->buf[i], bytes) != cudaSuccess) return -1;
+    ws->cap[i] = bytes;
   }
-  *out = g_ws.buf[i];
+  *out = ws->buf[i];
   return 0;
 }
 
 template <int FMT, bool SOFTMAX, int CL>
 int launch_main_cl(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl,
                    const TcParams& tp, dim3 grid, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_mask = 0;  // the attribute is per device
+  if (first_use_on_device(&attr_mask)) {
     if (cudaFuncSetAttribute(corr_tc_kernel<FMT, SOFTMAX, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CL>::SMEM_BYTES) !=
         cudaSuccess)
       return -1;
-    attr = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid, cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<CL>::SMEM_BYTES, cfg.stream = s;
@@ -451,7 +444,36 @@ int launch_main(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMa
 
 }  // namespace
 
-int launch_corr_tc(const CorrParams& p, int math, int cluster, cudaStream_t s, std::string* err) {
+bool first_use_on_device(unsigned long long* mask) {
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
+int corr_ws_reserve(CorrWorkspace* ws, int B, int Bphi, int NA, int NB) {
+  void* d;
+  const size_t ea = (size_t)B * NA * 256 * 4, ephi = (size_t)Bphi * NB * 256 * 4;  // tf32 words: the widest format
+  const size_t part = (size_t)16 * B * NA * sizeof(SplitOut);                       // at most 16 column splits
+  if (ws_get(ws, 0, ea, &d) || ws_get(ws, 1, ea, &d) || ws_get(ws, 2, ephi, &d) || ws_get(ws, 3, ephi, &d) || ws_get(ws, 4, part, &d))
+    return -1;
+  return 0;
+}
+
+void corr_ws_free(CorrWorkspace* ws) {
+  for (int i = 0; i < 5; ++i) {
+    if (ws->buf[i]) cudaFree(ws->buf[i]);
+    ws->buf[i] = nullptr, ws->cap[i] = 0;
+  }
+  ws->phi_src = nullptr, ws->phi_version = -1;
+}
+
+int launch_corr_tc(const CorrParams& p, int math, int cluster, CorrWorkspace* ws, long long phi_version, cudaStream_t s,
+                   std::string* err) {
   auto fail = [&](const char* m) {
     if (err) *err = m;
     return -1;
@@ -462,7 +484,7 @@ int launch_corr_tc(const CorrParams& p, int math, int cluster, cudaStream_t s, s
   const int eb = tf32 ? 4 : 2;
   const size_t ea = (size_t)p.B * p.NA * p.C, ephi = (size_t)p.Bphi * p.NB * p.C;
   void *Ah, *Al, *Bh, *Bl, *part;
-  if (ws_get(0, ea * eb, &Ah) || ws_get(1, ea * eb, &Al) || ws_get(2, ephi * eb, &Bh) || ws_get(3, ephi * eb, &Bl))
+  if (ws_get(ws, 0, ea * eb, &Ah) || ws_get(ws, 1, ea * eb, &Al) || ws_get(ws, 2, ephi * eb, &Bh) || ws_get(ws, 3, ephi * eb, &Bl))
     return fail("workspace allocation failed");
 
   // column-range splits so that (row blocks x batch x splits) fills the 148 SMs in whole waves
@@ -485,20 +507,24 @@ int launch_corr_tc(const CorrParams& p, int math, int cluster, cudaStream_t s, s
   }
   const int tps = (ntiles + nsplit - 1) / nsplit;
   nsplit = (ntiles + tps - 1) / tps;
-  if (ws_get(4, (size_t)nsplit * p.B * p.NA * sizeof(SplitOut), &part)) return fail("workspace allocation failed");
+  if (ws_get(ws, 4, (size_t)nsplit * p.B * p.NA * sizeof(SplitOut), &part)) return fail("workspace allocation failed");
 
   const int grid1 = 148 * 8;
+  // the reference side's planes survive from launch to launch while (pointer, version, format, size) are unchanged
+  const bool phi_cached = phi_version >= 0 && ws->phi_src == p.phi && ws->phi_version == phi_version && ws->phi_fmt == fmt &&
+                          ws->phi_elems == ephi;
   if (fmt == 0) {
     split_planes_kernel<0><<<grid1, 256, 0, s>>>(p.theta, Ah, Al, ea / 4);
-    split_planes_kernel<0><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
+    if (!phi_cached) split_planes_kernel<0><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
   } else if (fmt == 1) {
     split_planes_kernel<1><<<grid1, 256, 0, s>>>(p.theta, Ah, Al, ea / 4);
-    split_planes_kernel<1><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
+    if (!phi_cached) split_planes_kernel<1><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
   } else {
     split_planes_kernel<2><<<grid1, 256, 0, s>>>(p.theta, Ah, Al, ea / 4);
-    split_planes_kernel<2><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
+    if (!phi_cached) split_planes_kernel<2><<<grid1, 256, 0, s>>>(p.phi, Bh, Bl, ephi / 4);
   }
-  launch_counter_add(2);
+  launch_counter_add(phi_cached ? 1 : 2);
+  ws->phi_src = phi_version >= 0 ? p.phi : nullptr, ws->phi_version = phi_version, ws->phi_fmt = fmt, ws->phi_elems = ephi;
 
   CUtensorMap mAh, mAl, mBh, mBl;
   const uint32_t boxk = tf32 ? 32 : 64;

@@ -5,7 +5,26 @@
 #include "dvc_internal.cuh"
 
 namespace dvc {
-// math = DVC_MATH_TF32X3 or DVC_MATH_BF16X3.  Returns 0 on success, non-zero with *err set otherwise.
+// Operand planes and split partials of the correlation: owned by the context (one per device), grown only by
+// corr_ws_reserve -- dvc_set_exemplar / dvc_exemplar_import pre-size it, so the frame loop never allocates.
+struct CorrWorkspace {
+  void* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // A_hi, A_lo, B_hi, B_lo, split partials
+  size_t cap[5] = {0, 0, 0, 0, 0};
+  // the exemplar side is constant over a clip: its planes are split once per (pointer, version, format)
+  const void* phi_src = nullptr;
+  long long phi_version = -1;
+  int phi_fmt = -1;
+  size_t phi_elems = 0;
+};
+// reserve for B x NA query rows against Bphi x NB reference rows (any math mode, any split count); 0 on success
+int corr_ws_reserve(CorrWorkspace* ws, int B, int Bphi, int NA, int NB);
+void corr_ws_free(CorrWorkspace* ws);
+// math = DVC_MATH_TF32X3 / BF16X3 / FP16X3.  Returns 0 on success, non-zero with *err set otherwise.
 // cluster: 2 = CTA pairs (tcgen05.mma.cta_group::2) on adjacent query-row tiles, 1 = single CTAs
-int launch_corr_tc(const CorrParams& p, int math, int cluster, cudaStream_t s, std::string* err);
+// phi_version >= 0: the caller guarantees that p.phi's contents change only together with phi_version (the planes of
+// the reference side are then reused across launches); < 0: split every launch
+int launch_corr_tc(const CorrParams& p, int math, int cluster, CorrWorkspace* ws, long long phi_version, cudaStream_t s,
+                   std::string* err);
+// cudaFuncSetAttribute is per device: true once per (kernel instantiation, device) -- `mask` is that kernel's static
+bool first_use_on_device(unsigned long long* mask);
 }  // namespace dvc

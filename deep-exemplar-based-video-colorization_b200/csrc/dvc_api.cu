@@ -128,6 +128,9 @@ struct dvc_ctx {
   ScaleCell* cell_next = nullptr;
   int cell_left = 0;
   int corr_cluster = 2;   // correlation: 2 = CTA pairs (tcgen05.mma.cta_group::2), 1 = single CTAs
+  CorrWorkspace corr_ws;  // operand planes + split partials of the tensor-core correlation (pre-sized by dvc_set_exemplar)
+  long long ex_version = 0;  // bumped whenever ex_phi's contents change (the correlation caches the exemplar's planes)
+  int tc_force_bn = 0;    // tests: channel tile (64 / 128 / 256) forced on every tensor-core convolution it divides
   int tc_tail = 0;        // tensor-core convolutions: 1 = 128-channel tiles for the partial last round of 256-channel
                           // launches (-1.3 % on one stream, +1.6 % in the two-stream clip pipeline: off by default)
   int tc_f16 = 1;         // tensor-core convolutions: fp16 hi/lo planes for layers with provably bounded inputs
@@ -579,6 +582,7 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     t.add = p.add, t.add_lo = o.add ? o.add->lo : nullptr, t.aHp = p.aHp, t.aWp = p.aWp, t.aP = p.aP, t.aC = p.aC;
     t.act = o.act, t.slope = o.slope, t.stats = o.stats, t.kc = c->tc_kc, t.cluster = c->tc_cluster, t.kbytes = c->tc_kbytes;
     t.tail = c->tc_tail;
+    t.force_bn = (c->tc_force_bn && !o.fin_w && w->cout_pad_tc % c->tc_force_bn == 0) ? c->tc_force_bn : 0;
     t.splits = c->tc_splits, t.ws = nullptr, t.flags = nullptr, t.epoch = 0;
     if (c->tc_splits != 1 && (c->tc_splits > 1 || t.Mtot <= 128 * 8 * c->num_sms)) {  // split-K hand-over workspace + flags of this phase's arena (L2-resident, reused by every layer)
       const size_t mt = ((size_t)t.Mtot + 127) / 128 + 1;
@@ -855,7 +859,7 @@ static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const c
 // ------------------------------------------------------------------------------------------------
 // correlation dispatch
 // ------------------------------------------------------------------------------------------------
-static int run_corr(dvc_ctx* c, const CorrParams& p, cudaStream_t s) {
+static int run_corr(dvc_ctx* c, const CorrParams& p, cudaStream_t s, long long phi_version = -1) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->prof_corr) {
     CUDA_TRY(c, cudaEventCreate(&e0));
@@ -866,7 +870,8 @@ static int run_corr(dvc_ctx* c, const CorrParams& p, cudaStream_t s) {
     launch_corr_simt(p, s);
   } else {
     std::string err;
-    if (launch_corr_tc(p, c->corr_math, c->corr_cluster, s, &err) != 0) return fail(c, DVC_ERR_CUDA, "corr_tc: " + err);
+    if (launch_corr_tc(p, c->corr_math, c->corr_cluster, &c->corr_ws, phi_version, s, &err) != 0)
+      return fail(c, DVC_ERR_CUDA, "corr_tc: " + err);
   }
   DVC_TRY(check_launch(c, "corr"));
   if (c->prof_corr) {
@@ -1094,6 +1099,7 @@ extern "C" int dvc_destroy(dvc_ctx* c) {
   if (c->sD) cudaStreamDestroy(c->sD);
   if (c->ex_phi) cudaFree(c->ex_phi);
   if (c->ex_V) cudaFree(c->ex_V);
+  corr_ws_free(&c->corr_ws);
   for (auto& ev : c->corr_events) cudaEventDestroy(ev.first), cudaEventDestroy(ev.second);
   for (auto& ev : c->conv_events) cudaEventDestroy(ev.e0), cudaEventDestroy(ev.e1);
   delete c;
@@ -1122,6 +1128,11 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!strcmp(name, "tc_splits")) { c->tc_splits = value < 0 ? 0 : (value > 8 ? 8 : value); return DVC_OK; }
   if (!strcmp(name, "tc_kbytes")) { c->tc_kbytes = value == 64 ? 64 : 128; return DVC_OK; }
   if (!strcmp(name, "tc_cluster")) { c->tc_cluster = value == 2 ? 2 : 1; return DVC_OK; }
+  if (!strcmp(name, "tc_force_bn")) {
+    if (value != 0 && value != 64 && value != 128 && value != 256) return fail(c, DVC_ERR_ARG, "tc_force_bn must be 0, 64, 128 or 256");
+    c->tc_force_bn = value;
+    return DVC_OK;
+  }
   return fail(c, DVC_ERR_ARG, std::string("unknown debug flag ") + name);
 }
 
@@ -1308,6 +1319,91 @@ extern "C" int dvc_colorvidnet_forward(dvc_ctx* c, const float* x, int B, int H,
   return colorvid(c, "mcolor", in0, out, s);
 }
 
+// ---- one convolution layer in isolation (test hook) ------------------------------------------------
+// y = act(conv(pad(x)) + bias (+ add)) for the weights `name` of `net`, through exactly the engine, operand format and
+// epilogue the layer programs use (tensor-core mode: fp16 planes with the static exponent of `in_bound`, or tf32 planes
+// with tc_f16 = 0; CUDA-core mode otherwise).  out_planes = 1 stores the result as fp16 hi/lo planes with a
+// device-derived exponent (the conv -> ReLU -> conv chains) and reads it back from them; upconv = 1 runs the four
+// phase convolutions of a nearest-x2 + 3x3 decoder layer; fuse_tail = 1 the conv10_2 + conv10_ab + tanh epilogue
+// (y is then [B][2][H][W]).  stats_out (device, [B][Cout][2] doubles) receives the InstanceNorm sums of the stored values.
+extern "C" int dvc_debug_conv2d(dvc_ctx* c, int net, const char* name, const float* x, int B, int H, int W, int dil, int stride,
+                                int act, float slope, int pad_mode, int upconv, int fuse_tail, float in_bound, int out_planes,
+                                const float* add, float* y, double* stats_out, void* stream) {
+  if (!c || !name || !x || !y || net < 0 || net > 2 || B < 1 || H < 1 || W < 1 || dil < 1 || (stride != 1 && stride != 2))
+    return c ? fail(c, DVC_ERR_ARG, "debug_conv2d: bad argument") : DVC_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const ConvW* w;
+  DVC_TRY(need_conv(c, net, name, &w));
+  DVC_TRY(stats_begin(c, s));
+  const bool tcm = tc_mode(c) && w->wt_hi, f16 = tcm && c->tc_f16;
+  if ((upconv || fuse_tail) && !tcm) return fail(c, DVC_ERR_STATE, "debug_conv2d: phase / fused-tail layers need the tensor-core engine");
+  if (out_planes && !f16) return fail(c, DVC_ERR_STATE, "debug_conv2d: device-scaled output planes need the fp16 engine");
+  Act x0, xp, yo, addA;
+  DVC_TRY(get_act(c, "dbg.x0", B, H, W, w->cin_pad, 0, &x0, s));
+  launch_nchw_to_act(x, w->cin, x0.d, nullptr, B, H, W, w->cin_pad, 0, PAD_ZERO, 0, s);
+  DVC_TRY(check_launch(c, "nchw_to_act"));
+  DVC_TRY(get_act(c, "dbg.xp", B, H, W, w->cin_pad, w->k == 3 ? dil : 1, &xp, s, tcm ? (f16 ? 2 : 1) : 0));
+  xp.e16 = e16_for(in_bound > 0.f ? in_bound : 1.0);
+  XfOpt xo;
+  xo.pad_mode = pad_mode ? PAD_REFLECT : PAD_ZERO;
+  DVC_TRY(run_xform(c, x0, xp, xo, s));
+  const int Ho = upconv ? 2 * H : (H + stride - 1) / stride, Wo = upconv ? 2 * W : (W + stride - 1) / stride;
+  ConvOpt o;
+  o.dil = dil, o.stride = stride, o.act = act, o.slope = slope;
+  if (add) {
+    DVC_TRY(get_act(c, "dbg.add", B, Ho, Wo, w->cout_pad, 0, &addA, s));
+    launch_nchw_to_act(add, w->cout, addA.d, nullptr, B, Ho, Wo, w->cout_pad, 0, PAD_ZERO, 0, s);
+    DVC_TRY(check_launch(c, "nchw_to_act"));
+    if (out_planes) {
+      DVC_TRY(cell_alloc(c, &addA.cell, s));
+      launch_amax(addA.d, addA.elems(), addA.cell, s);
+      DVC_TRY(check_launch(c, "amax"));
+    }
+    o.add = &addA;
+  }
+  double* st = nullptr;
+  if (stats_out) {
+    DVC_TRY(stats_alloc(c, B, w->cout, &st, s));
+    o.stats = st;
+  }
+  if (fuse_tail) {
+    const float *wab, *bab;
+    DVC_TRY(need_vec(c, DVC_NET_COLOR, "conv10_ab", &wab));
+    DVC_TRY(need_vec(c, DVC_NET_COLOR, "conv10_ab.bias", &bab));
+    if (w->cout != 128) return fail(c, DVC_ERR_SHAPE, "debug_conv2d: the fused tail needs 128 output channels");
+    yo.B = B, yo.H = Ho, yo.W = Wo, yo.C = w->cout, yo.P = 0;
+    o.fin_w = wab, o.fin_b = bab, o.fin_out = y;
+    return run_conv(c, w, xp, yo, o, s);
+  }
+  DVC_TRY(get_act(c, "dbg.y", B, Ho, Wo, w->cout, out_planes ? 1 : 0, &yo, s, out_planes ? 2 : 0));
+  if (out_planes) DVC_TRY(cell_alloc(c, &yo.cell, s));
+  if (upconv) {
+    float l1 = 0.f;
+    for (int ph = 0; ph < 4; ++ph) {
+      auto it = c->conv[net].find(std::string(name) + "#p" + std::to_string(ph));
+      if (it == c->conv[net].end() || !it->second.w16_hi) return fail(c, DVC_ERR_STATE, std::string("phase weights missing: ") + name);
+      l1 = fmaxf(l1, it->second.l1max);
+    }
+    for (int ph = 0; ph < 4; ++ph) {
+      ConvW pw = c->conv[net][std::string(name) + "#p" + std::to_string(ph)];
+      pw.b = w->b, pw.bmax = w->bmax;
+      ConvOpt op = o;
+      op.phase = ph, op.l1_override = l1;
+      DVC_TRY(run_conv(c, &pw, xp, yo, op, s));
+    }
+  } else {
+    DVC_TRY(run_conv(c, w, xp, yo, o, s));
+  }
+  if (yo.h16)
+    launch_act_to_nchw_h16(yo.h16, yo.l16, yo.cell, yo.H, yo.W, yo.P, yo.C, w->cout, y, B, s);
+  else
+    launch_act_to_nchw(yo.d, yo.lo, yo.H, yo.W, yo.P, yo.C, 0, w->cout, y, B, s);
+  DVC_TRY(check_launch(c, "act_to_nchw"));
+  if (stats_out) CUDA_TRY(c, cudaMemcpyAsync(stats_out, st, (size_t)B * w->cout * 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return DVC_OK;
+}
+
 // ---- stand-alone correlation ---------------------------------------------------------------------
 extern "C" int dvc_corr_softmax_warp(dvc_ctx* c, const float* theta_hat, const float* phi_hat, const float* V, int B,
                                      int Bphi, int NA, int NB, int C, float temperature, float* y, float* sim,
@@ -1438,7 +1534,9 @@ extern "C" int dvc_set_exemplar(dvc_ctx* c, const float* IB_lab, int H, int W, v
   DVC_TRY(warp_side(c, "ex", n, "phi", c->ex_phi, h, w, s));
   launch_avgpool4_lab((float*)lab, c->ex_V, 1, H, W, s);
   DVC_TRY(check_launch(c, "avgpool4"));
-  c->ex_H = H, c->ex_W = W, c->ex_valid = true;
+  c->ex_H = H, c->ex_W = W, c->ex_valid = true, c->ex_version++;
+  // the frame loop must not allocate: size the correlation workspace for one frame against this exemplar now
+  if (corr_ws_reserve(&c->corr_ws, 1, 1, N, N) != 0) return fail(c, DVC_ERR_CUDA, "set_exemplar: correlation workspace allocation failed");
   return DVC_OK;
 }
 
@@ -1461,7 +1559,7 @@ static int frames_phaseA(dvc_ctx* c, const std::string& tag, const float* IA_l, 
   CorrParams p{};
   p.theta = (float*)theta, p.phi = c->ex_phi, p.V = c->ex_V, p.B = B, p.Bphi = 1, p.NA = N, p.NB = N, p.C = 256;
   p.temperature = temperature, p.y = yrows, p.sim = simrows, p.argmax = nullptr;
-  return run_corr(c, p, s);
+  return run_corr(c, p, s, c->ex_version);
 }
 
 // Phase C (the recurrent part): ColorVidNet on [L, warped ab, similarity, previous Lab] (FrameColor.py:63-65).
@@ -1543,45 +1641,61 @@ extern "C" int dvc_colorize_clip(dvc_ctx* c, const float* L_in, int F, int H, in
     CUDA_TRY(c, cudaMemcpyAsync(dlast, first_last, 3 * hw * 4, cudaMemcpyDefault, s));
   else
     CUDA_TRY(c, cudaMemsetAsync(dlast, 0, 3 * hw * 4, s));  // test.py:80
-  CUDA_TRY(c, cudaEventRecord(c->evFork, s));
-  CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evFork, 0));
-  CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evFork, 0));
-  CUDA_TRY(c, cudaStreamWaitEvent(c->sU, c->evFork, 0));
-  CUDA_TRY(c, cudaStreamWaitEvent(c->sD, c->evFork, 0));
-  for (int t = 0; t < F; ++t) {
-    const int slot = t & 1;
-    float* Lt = (float*)dL + (size_t)(t & 3) * hw;
-    float* abt = (float*)dab + (size_t)slot * 2 * hw;
-    float* yr = (float*)yrows + (size_t)slot * N * 4;
-    float* sr = (float*)simrows + (size_t)slot * N;
-    // ---- upload stream: the L slot was last read by frame t-4's ColorVidNet / make_last ----
-    if (t >= 4) CUDA_TRY(c, cudaStreamWaitEvent(c->sU, c->evC[(t - 4) & 3], 0));
-    CUDA_TRY(c, cudaMemcpyAsync(Lt, L_in + (size_t)t * hw, hw * 4, cudaMemcpyDefault, c->sU));
-    CUDA_TRY(c, cudaEventRecord(c->evU[t & 3], c->sU));
-    // ---- stream A: frame-independent phase; the warp-row slot reuse waits for frame t-2's ColorVidNet ----
-    CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evU[t & 3], 0));
-    if (t >= 2) CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evC[(t - 2) & 3], 0));
-    DVC_TRY(frames_phaseA(c, "clipA", Lt, 1, H, W, temperature, yr, sr, c->sA));
-    CUDA_TRY(c, cudaEventRecord(c->evA[t & 3], c->sA));
-    // ---- stream C: the recurrent phase ----
-    CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evA[t & 3], 0));
-    if (t >= 2) CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evD[(t - 2) & 3], 0));  // the ab slot has been downloaded
-    DVC_TRY(frames_phaseC(c, "clipC", Lt, yr, sr, (float*)dlast, 1, H, W, abt, c->sC));
-    launch_make_last(Lt, abt, (float*)dlast, 1, H, W, c->sC);  // test.py:96
-    DVC_TRY(check_launch(c, "make_last"));
-    CUDA_TRY(c, cudaEventRecord(c->evC[t & 3], c->sC));
-    // ---- download stream ----
-    CUDA_TRY(c, cudaStreamWaitEvent(c->sD, c->evC[t & 3], 0));
-    CUDA_TRY(c, cudaMemcpyAsync(ab_out + (size_t)t * 2 * hw, abt, 2 * hw * 4, cudaMemcpyDefault, c->sD));
-    CUDA_TRY(c, cudaEventRecord(c->evD[t & 3], c->sD));
+  // Every exit below goes through the join epilogue: an error in the middle of the loop must not return while copies
+  // or kernels of earlier frames are still writing into ab_out / the slots (a retry would race with them).
+  auto enqueue = [&]() -> int {
+    CUDA_TRY(c, cudaEventRecord(c->evFork, s));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evFork, 0));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evFork, 0));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->sU, c->evFork, 0));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->sD, c->evFork, 0));
+    for (int t = 0; t < F; ++t) {
+      const int slot = t & 1;
+      float* Lt = (float*)dL + (size_t)(t & 3) * hw;
+      float* abt = (float*)dab + (size_t)slot * 2 * hw;
+      float* yr = (float*)yrows + (size_t)slot * N * 4;
+      float* sr = (float*)simrows + (size_t)slot * N;
+      // ---- upload stream: the L slot was last read by frame t-4's ColorVidNet / make_last ----
+      if (t >= 4) CUDA_TRY(c, cudaStreamWaitEvent(c->sU, c->evC[(t - 4) & 3], 0));
+      CUDA_TRY(c, cudaMemcpyAsync(Lt, L_in + (size_t)t * hw, hw * 4, cudaMemcpyDefault, c->sU));
+      CUDA_TRY(c, cudaEventRecord(c->evU[t & 3], c->sU));
+      // ---- stream A: frame-independent phase; the warp-row slot reuse waits for frame t-2's ColorVidNet ----
+      CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evU[t & 3], 0));
+      if (t >= 2) CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evC[(t - 2) & 3], 0));
+      DVC_TRY(frames_phaseA(c, "clipA", Lt, 1, H, W, temperature, yr, sr, c->sA));
+      CUDA_TRY(c, cudaEventRecord(c->evA[t & 3], c->sA));
+      // ---- stream C: the recurrent phase ----
+      CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evA[t & 3], 0));
+      if (t >= 2) CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evD[(t - 2) & 3], 0));  // the ab slot has been downloaded
+      DVC_TRY(frames_phaseC(c, "clipC", Lt, yr, sr, (float*)dlast, 1, H, W, abt, c->sC));
+      launch_make_last(Lt, abt, (float*)dlast, 1, H, W, c->sC);  // test.py:96
+      DVC_TRY(check_launch(c, "make_last"));
+      CUDA_TRY(c, cudaEventRecord(c->evC[t & 3], c->sC));
+      // ---- download stream ----
+      CUDA_TRY(c, cudaStreamWaitEvent(c->sD, c->evC[t & 3], 0));
+      CUDA_TRY(c, cudaMemcpyAsync(ab_out + (size_t)t * 2 * hw, abt, 2 * hw * 4, cudaMemcpyDefault, c->sD));
+      CUDA_TRY(c, cudaEventRecord(c->evD[t & 3], c->sD));
+    }
+    return DVC_OK;
+  };
+  const int rc = enqueue();
+  const std::string first_err = c->err;
+  // join: the caller's stream waits for the four internal streams, then the host waits for the caller's stream
+  bool join_ok = true;
+  join_ok &= cudaEventRecord(c->evJoinA, c->sA) == cudaSuccess && cudaStreamWaitEvent(s, c->evJoinA, 0) == cudaSuccess;
+  join_ok &= cudaEventRecord(c->evJoinC, c->sC) == cudaSuccess && cudaStreamWaitEvent(s, c->evJoinC, 0) == cudaSuccess;
+  join_ok &= cudaEventRecord(c->evJoinD, c->sD) == cudaSuccess && cudaStreamWaitEvent(s, c->evJoinD, 0) == cudaSuccess;
+  join_ok &= cudaEventRecord(c->evFork, c->sU) == cudaSuccess && cudaStreamWaitEvent(s, c->evFork, 0) == cudaSuccess;
+  const cudaError_t se = cudaStreamSynchronize(s);
+  if (rc != DVC_OK) {
+    if (!join_ok || se != cudaSuccess) {  // could not even drain the streams: make sure nothing is in flight
+      cudaStreamSynchronize(c->sA), cudaStreamSynchronize(c->sC), cudaStreamSynchronize(c->sU), cudaStreamSynchronize(c->sD);
+    }
+    c->err = first_err;
+    return rc;
   }
-  CUDA_TRY(c, cudaEventRecord(c->evJoinA, c->sA));
-  CUDA_TRY(c, cudaEventRecord(c->evJoinC, c->sC));
-  CUDA_TRY(c, cudaEventRecord(c->evJoinD, c->sD));
-  CUDA_TRY(c, cudaStreamWaitEvent(s, c->evJoinA, 0));
-  CUDA_TRY(c, cudaStreamWaitEvent(s, c->evJoinC, 0));
-  CUDA_TRY(c, cudaStreamWaitEvent(s, c->evJoinD, 0));
-  CUDA_TRY(c, cudaStreamSynchronize(s));
+  if (!join_ok) return fail(c, DVC_ERR_CUDA, "colorize_clip: joining the internal streams failed");
+  if (se != cudaSuccess) return fail(c, DVC_ERR_CUDA, std::string("colorize_clip: ") + cudaGetErrorString(se));
   return DVC_OK;
 }
 
@@ -1657,6 +1771,7 @@ extern "C" int dvc_exemplar_import(dvc_ctx* c, const float* buf, int64_t n, int 
   }
   CUDA_TRY(c, cudaMemcpyAsync(c->ex_phi, buf, (size_t)N * 256 * 4, cudaMemcpyDeviceToDevice, s));
   CUDA_TRY(c, cudaMemcpyAsync(c->ex_V, buf + N * 256, (size_t)N * 16, cudaMemcpyDeviceToDevice, s));
-  c->ex_H = H, c->ex_W = W, c->ex_valid = true;
+  c->ex_H = H, c->ex_W = W, c->ex_valid = true, c->ex_version++;
+  if (corr_ws_reserve(&c->corr_ws, 1, 1, (int)N, (int)N) != 0) return fail(c, DVC_ERR_CUDA, "exemplar_import: correlation workspace allocation failed");
   return DVC_OK;
 }

@@ -21,7 +21,7 @@ EXPORTED = [
     "dvc_vgg19_forward", "dvc_warpnet_forward", "dvc_colorvidnet_forward", "dvc_corr_softmax_warp",
     "dvc_set_exemplar", "dvc_colorize_frames", "dvc_colorize_clip", "dvc_exemplar_pack_size",
     "dvc_exemplar_export", "dvc_exemplar_import", "dvc_launch_count", "dvc_profile_corr", "dvc_corr_mean_ms",
-    "dvc_debug_set_flag", "dvc_debug_get_buffer", "dvc_profile_conv", "dvc_conv_profile",
+    "dvc_debug_set_flag", "dvc_debug_get_buffer", "dvc_debug_conv2d", "dvc_profile_conv", "dvc_conv_profile",
     "dvc_resize_half", "dvc_upsample2_scaled", "dvc_lab_to_rgb8", "dvc_rgb8_to_lab",
     "dvc_peer_buffer_create", "dvc_peer_buffer_open", "dvc_peer_buffer_close", "dvc_peer_buffer_destroy",
     "dvc_corr_set_peer_outputs",
@@ -88,6 +88,8 @@ def load_library():
         lib.dvc_conv_profile.argtypes = [c_void, c_int, c_int, P(ctypes.c_double), P(ctypes.c_double)]
         lib.dvc_debug_set_flag.argtypes = [c_void, ctypes.c_char_p, c_int]
         lib.dvc_debug_get_buffer.argtypes = [c_void, ctypes.c_char_p, P(c_void), P(c_i64), P(c_int)]
+        lib.dvc_debug_conv2d.argtypes = [c_void, c_int, ctypes.c_char_p, c_void, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                         c_int, c_int, c_int, c_float, c_int, c_void, c_void, c_void, c_void]
         _lib = lib
         return lib
 
@@ -138,6 +140,7 @@ class Context:
 
     def set_weights(self, net, state_dict):
         """Replaces load_state_dict (test.py:150,158-159) for `net` in {NET_VGG, NET_WARP, NET_COLOR}."""
+        self._weight_sig.pop(net, None)  # a drop-in module that synced earlier must re-upload on its next forward
         for key, t in state_dict.items():
             t = t.detach().to(torch.float32).contiguous()
             shape = (ctypes.c_int64 * t.dim())(*t.shape)
@@ -354,6 +357,23 @@ class Context:
     # ---- debug hooks ---------------------------------------------------------------------------------
     def debug_flag(self, name, value):
         self._check(self.lib.dvc_debug_set_flag(self.h, name.encode(), int(value)), "dvc_debug_set_flag")
+
+    def debug_conv2d(self, net, name, x, cout, dil=1, stride=1, act=0, slope=0.0, reflect=False, upconv=False,
+                     fuse_tail=False, in_bound=None, out_planes=False, add=None, want_stats=False):
+        """One convolution layer (weights `name` of `net`) on a CUDA NCHW tensor through the engine the layer programs
+        use (include/dvc.h: dvc_debug_conv2d).  Returns y or (y, stats [B,cout,2] float64)."""
+        x = _dev_f32(x, "debug_conv2d input")
+        B, _, H, W = x.shape
+        Ho, Wo = (2 * H, 2 * W) if upconv else ((H + stride - 1) // stride, (W + stride - 1) // stride)
+        y = torch.empty(B, 2 if fuse_tail else cout, Ho, Wo, device=x.device, dtype=torch.float32)
+        st = torch.zeros(B, cout, 2, device=x.device, dtype=torch.float64) if want_stats else None
+        bound = float(x.abs().max()) if in_bound is None else float(in_bound)
+        add = _dev_f32(add, "debug_conv2d addend") if add is not None else None
+        rc = self.lib.dvc_debug_conv2d(self.h, net, name.encode(), _ptr(x), B, H, W, dil, stride, act, float(slope),
+                                       1 if reflect else 0, 1 if upconv else 0, 1 if fuse_tail else 0, bound,
+                                       1 if out_planes else 0, _ptr(add), _ptr(y), _ptr(st), _stream(x.device))
+        self._check(rc, "dvc_debug_conv2d")
+        return (y, st) if want_stats else y
 
     def debug_buffer(self, name, act=True):
         """Copy of an internal workspace.  act=True: padded NHWC activation -> interior as NCHW [B,C,H,W]."""

@@ -72,8 +72,12 @@ class RowShardedCorrelation:
         if self.world > 8:
             raise ValueError("RowShardedCorrelation: at most 8 ranks (one NVLink box)")
         self.row0, self.row1 = segment_bounds(self.N, self.world, self.rank)
-        # my full-size result buffers: y4 [N][4] followed by sim [N]
-        self._own, handle = ctx.peer_buffer_create(self.N * 20)
+        # my full-size result buffers: y4 [N][4] followed by sim [N], TWO sets used alternately by call parity: a fast
+        # peer may already store the rows of call k+1 while this rank still copies the result of call k out of the
+        # other set (it cannot reach call k+2 before this rank has passed call k+1's barrier, i.e. finished that copy)
+        self._set_bytes = self.N * 20
+        self._calls = 0
+        self._own, handle = ctx.peer_buffer_create(2 * self._set_bytes)
         handles = [None] * self.world
         if self.world > 1:
             dist.all_gather_object(handles, handle, group=group)
@@ -93,8 +97,10 @@ class RowShardedCorrelation:
         if theta_hat.shape[0] != 1 or theta_hat.shape[2] != self.N:
             raise ValueError("RowShardedCorrelation: theta_hat must be [1,C,N]")
         ctx = self.ctx
+        off = (self._calls & 1) * self._set_bytes
+        self._calls += 1
         if self.row1 > self.row0:
-            ctx.corr_set_peer_outputs(self._y4, self._sim, self.row0)
+            ctx.corr_set_peer_outputs([p + off for p in self._y4], [p + off for p in self._sim], self.row0)
             try:
                 ctx.corr_softmax_warp(theta_hat[:, :, self.row0:self.row1].contiguous(), phi_hat, V, temperature)
             finally:
@@ -102,7 +108,7 @@ class RowShardedCorrelation:
         torch.cuda.synchronize(ctx.device)
         if self.world > 1:
             dist.barrier(group=self.group)  # every rank's rows have landed in every buffer
-        flat = ctx.raw_view(self._own, self.N * 5)
+        flat = ctx.raw_view(self._own + off, self.N * 5)
         y = flat[: self.N * 4].view(1, self.N, 4)[:, :, :3].clone()
         sim = flat[self.N * 4:].view(1, self.N).clone()
         return y, sim

@@ -18,6 +18,9 @@ _VGG_CFG = [("conv1_1", 3, 64), ("conv1_2", 64, 64), ("conv2_1", 64, 128), ("con
             ("conv5_1", 512, 512), ("conv5_2", 512, 512), ("conv5_3", 512, 512), ("conv5_4", 512, 512)]
 
 
+_COMPARE = __import__("os").environ.get("DVC_DROPIN_COMPARE", "1") != "0"
+
+
 def _ctx_for(t):
     if not t.is_cuda:
         raise dvc.DvcError("the B200 drop-in modules run on CUDA tensors only (no CPU fallback); call .cuda() like test.py:164-166")
@@ -78,16 +81,25 @@ class WarpNet(nn.Module):
         weights_changed = before != ctx._weight_sig.get(dvc.NET_WARP)
         b_inputs = [B_lab_map, B_relu2_1, B_relu3_1, B_relu4_1, B_relu5_1]
         # The reference recomputes the exemplar side every frame (FrameColor.py:20-36).  Every B-side op is
-        # per-sample, so when the B tensors are bit-identical to the previous call the cached phi / pooled
-        # Lab operands give the identical result; the comparison runs on the device (one sync per call).
+        # per-sample, so when the B tensors are the tensors of the previous call the cached phi / pooled Lab operands
+        # give the identical result.  Two checks, cheapest first:
+        #  (1) identity: same storage, same version counter, same shape -- no device work, no sync.  The previous
+        #      call's tensors are kept referenced, so a NEW tensor can never alias their (recycled) address;
+        #  (2) content: FrameColor.py:33-36 re-normalises the exemplar features every frame into fresh tensors, so
+        #      (1) misses there; one fused device comparison + one host sync per call decides (DVC_DROPIN_COMPARE=0
+        #      turns it off: the B side is then simply recomputed like the reference does).
         reuse = False
         if self._b_cache is not None and not weights_changed and not torch.is_grad_enabled():
-            prev = self._b_cache
-            if all(p.shape == t.shape and p.device == t.device for p, t in zip(prev, b_inputs)):
+            prev_keys, prev = self._b_cache
+            keys = [(t.data_ptr(), t._version, tuple(t.shape), t.device) for t in b_inputs]
+            if keys == prev_keys:
+                reuse = True
+            elif (_COMPARE and all(p.shape == t.shape and p.device == t.device for p, t in zip(prev, b_inputs))
+                  and all(p._version == k[1] for p, k in zip(prev, prev_keys))):  # the kept tensors are still what was cached
                 diff = torch.stack([(p != t).any() for p, t in zip(prev, b_inputs)]).any()
                 reuse = not bool(diff.item())
         y, sim = ctx.warpnet_forward(B_lab_map, [A_relu2_1, A_relu3_1, A_relu4_1, A_relu5_1],
                                      [B_relu2_1, B_relu3_1, B_relu4_1, B_relu5_1], temperature, WTA_scale_weight, reuse)
-        if not reuse:
-            self._b_cache = [t.detach().clone() for t in b_inputs]
+        # keep the caller's tensors referenced (identity check) -- no clone: an in-place edit bumps _version
+        self._b_cache = ([(t.data_ptr(), t._version, tuple(t.shape), t.device) for t in b_inputs], [t.detach() for t in b_inputs])
         return y, sim

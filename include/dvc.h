@@ -190,6 +190,19 @@ int dvc_conv_profile(dvc_ctx* ctx, int variant, int reset, double* total_ms, dou
  *   carry their [B,H,W,C,P] signature in sig5) so tests can check intermediate stages. */
 int dvc_debug_set_flag(dvc_ctx* ctx, const char* name, int value);
 int dvc_debug_get_buffer(dvc_ctx* ctx, const char* name, void** dev_ptr, int64_t* bytes, int* sig5);
+/*   dvc_debug_conv2d: ONE convolution layer (the weights `name` of network `net`, already set with dvc_set_weight) on a
+ *   device NCHW input, through exactly the engine / operand format / epilogue the layer programs would use under the
+ *   current dvc_set_math and debug flags ("tc_force_bn" = 64 / 128 / 256 pins the channel tile) -- the per-layer parity
+ *   tests compare it with an fp64 F.conv2d (nn.Conv2d at NonlocalNet.py:235-255,364-423, ColorVidNet.py:96-143).
+ *   pad_mode 0 = zero padding, 1 = ReflectionPad2d; act 0 none / 1 ReLU / 2 LeakyReLU(slope); in_bound >= max |x|
+ *   (fixes the exact power-of-two scale of the fp16 operand planes); out_planes = 1 stores the result as fp16 hi/lo
+ *   planes with the device-derived exponent and reads it back; upconv = 1: Upsample(2, nearest) + Conv2d(3x3) as four
+ *   phase convolutions (y is [B][Cout][2H][2W]); fuse_tail = 1: conv10_2 + LeakyReLU + conv10_ab + tanh*128 (y is
+ *   [B][2][H][W]); add: optional device NCHW addend of the output's shape; stats_out: optional device [B][Cout][2]
+ *   doubles receiving (sum, sum of squares) over positions. */
+int dvc_debug_conv2d(dvc_ctx* ctx, int net, const char* name, const float* dev_x, int B, int H, int W, int dil, int stride,
+                     int act, float slope, int pad_mode, int upconv, int fuse_tail, float in_bound, int out_planes,
+                     const float* dev_add, float* dev_y, double* dev_stats_out, void* stream);
 
 #ifdef __cplusplus
 }

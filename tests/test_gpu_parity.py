@@ -6,9 +6,12 @@ Tolerances (floating point, stated per SURVEY.md §8c):
   VGG maps        max|d| <= 1e-4 * max|ref|            (fp32 summation-order noise)
   similarity      max|d| <= 2e-5
   warp (T->0)     identical argmax on every row whose fp64 top-2 gap > 1e-5 (tie-aware)
-  final ab        max|ours - ref_fp64| <= max(1e-3, 2 * max|ref_fp32 - ref_fp64|): ColorVidNet with the seeded
+  final ab        max|ours - ref_fp64| <= max(1e-3, k * max|ref_fp32 - ref_fp64|): ColorVidNet with the seeded
                   random weights amplifies a 1e-6 input perturbation to ~1e-3 (measured), so the
                   reference's own fp32 forward sits 1e-3..2e-2 away from fp64; ours must be in the same band.
+                  k = 1.25 for the default engine and the exact-fp32 CUDA-core engine; k = 2 only for
+                  the debug variants of the tensor-core engine (single CTAs, 64-byte stages, split-K, tail rounds,
+                  3xTF32 planes), which are not what ships.
 """
 import numpy as np
 import pytest
@@ -26,23 +29,30 @@ def cu(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def ab_gate(ours, g):
+SHIPPING = ("fp32", "tf32x3", "tf32x3-bn256")  # engines gated at 1.25x the reference's own fp32 noise
+
+
+def ab_gate(ours, g, variant="debug"):
     floor = np.abs(g["ab32"].astype(np.float64) - g["ab64"]).max()
     err = np.abs(ours.astype(np.float64) - g["ab64"]).max()
-    return err, max(1e-3, 2.0 * floor)
+    return err, max(1e-3, (1.25 if variant in SHIPPING else 2.0) * floor)
 
 
-@pytest.fixture(params=["fp32", "tf32x3", "tf32x3-nof16", "tf32x3-cluster1", "tf32x3-cluster1-nof16", "tf32x3-cluster1-k64",
-                        "tf32x3-k64", "tf32x3-split3", "tf32x3-tail16", "tf32x3-tail"])
+@pytest.fixture(params=["fp32", "tf32x3", "tf32x3-bn256", "tf32x3-bn256-cluster1", "tf32x3-bn64", "tf32x3-nof16", "tf32x3-cluster1",
+                        "tf32x3-cluster1-nof16", "tf32x3-cluster1-k64", "tf32x3-k64", "tf32x3-split3", "tf32x3-tail16", "tf32x3-tail"])
 def conv_math(request, ctx):
     """Convolutions on CUDA cores (exact fp32, two-level accumulation) and on tcgen05 (3xTF32 operand split),
     the latter as single CTAs (64-byte and 128-byte K stages) and as CTA pairs (tcgen05.mma.cta_group::2).
-    Layers with provably bounded inputs run 3xFP16 on scaled planes unless "-nof16" turns that off."""
+    Layers with provably bounded inputs run 3xFP16 on scaled planes unless "-nof16" turns that off.
+    "-bn256" pins the 256-channel tile (BN = 256: its own TMEM ring depth, stage count and two-loads-in-flight drain) on
+    every layer with >= 256 output channels -- the tile the 480x864 bench runs on, which the launcher's heuristic
+    never picks at the golden sizes; "-bn64" pins the narrow tile on every layer."""
     import dvc
 
     if request.param.startswith("tf32x3"):
         ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
         ctx.debug_flag("tc_cluster", 1 if "cluster1" in request.param else 2)
+        ctx.debug_flag("tc_force_bn", 256 if "bn256" in request.param else (64 if "bn64" in request.param else 0))
         ctx.debug_flag("tc_kbytes", 64 if request.param.endswith("k64") else 128)
         ctx.debug_flag("tc_splits", 3 if request.param.endswith("split3") else 1)
         ctx.debug_flag("tc_f16", 0 if request.param.endswith("nof16") else 1)
@@ -56,6 +66,7 @@ def conv_math(request, ctx):
     ctx.debug_flag("tc_splits", 1)
     ctx.debug_flag("tc_f16", 1)
     ctx.debug_flag("tc_tail", 0)
+    ctx.debug_flag("tc_force_bn", 0)
     ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
 
 
@@ -191,7 +202,7 @@ def test_colorvidnet_module_vs_golden(ctx, conv_math, name):
     up = lambda a: torch.nn.functional.interpolate(torch.from_numpy(a), scale_factor=4, mode="nearest")
     x = torch.cat((IA[:, 0:1], up(g["warped32"])[:, 1:3], up(g["sim32"]), last), 1)
     out = ctx.colorvidnet_forward(x.cuda()).cpu().numpy()
-    err, tol = ab_gate(out, g)
+    err, tol = ab_gate(out, g, conv_math)
     assert err <= tol, (err, tol)
 
 
@@ -238,7 +249,7 @@ def test_fused_frame_vs_golden(ctx, conv_math, name):
         m = np.broadcast_to(clear[:, None, :], (1, 3, clear.shape[1]))
         nbad = int((np.abs(ys.reshape(1, 3, -1)[m] - g["warped32"].reshape(1, 3, -1)[m]) > 1e-4).sum())
         assert nbad == 0, nbad
-    err, tol = ab_gate(ab.cpu().numpy(), g)
+    err, tol = ab_gate(ab.cpu().numpy(), g, conv_math)
     assert err <= tol, (err, tol)
 
 
