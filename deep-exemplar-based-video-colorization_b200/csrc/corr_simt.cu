@@ -6,8 +6,9 @@
 // whole sweep over the reference positions; phi streams through a double-buffered [8 x 128] tile.
 // Each thread keeps an 8 x 8 block of scores in registers and folds it straight into per-row
 // running statistics:
-//   ARGMAX mode (T <= 2e-10, test.py:94): running (max, argmax); the softmax is exactly one-hot in
-//       fp32 there because distinct fp32 scores differ by > 104 T, so exp() underflows to 0.
+//   ARGMAX mode (T <= 2e-10, test.py:94): running (max, argmax, number of bit-equal maxima, sum of their V rows);
+//       distinct fp32 scores differ by > 104 T there, so the reference's fp32 softmax is one-hot -- or, for
+//       bit-equal maxima (duplicated exemplar columns), the plain mean of their V rows, which is what is returned.
 //   SOFTMAX mode: flash-style online softmax (running max, running sum, 3 weighted colour sums).
 #include <math.h>
 
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(256) corr_simt_kernel(const CorrParams p) {
     As[(k0 + l_k4 + 3) * BM + l_row] = v.w;
   }
 
-  float run_m[8], run_s[8], run_a[8][3];
+  float run_m[8], run_s[8], run_a[8][3];  // ARGMAX mode: run_s = number of maxima, run_a = sum of their V rows
   int run_i[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -114,7 +115,16 @@ __global__ void __launch_bounds__(256) corr_simt_kernel(const CorrParams p) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int col = cbase + ((j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4));
-            if (col < p.NB && acc[i][j] > run_m[i]) run_m[i] = acc[i][j], run_i[i] = col;
+            if (col < p.NB && acc[i][j] >= run_m[i]) {  // rare once the running maximum has settled
+              const float4 v = __ldg(Vg + col);
+              if (acc[i][j] > run_m[i]) {
+                run_m[i] = acc[i][j], run_i[i] = col, run_s[i] = 1.f;
+                run_a[i][0] = v.x, run_a[i][1] = v.y, run_a[i][2] = v.z;
+              } else {
+                run_i[i] = min(run_i[i], col), run_s[i] += 1.f;
+                run_a[i][0] += v.x, run_a[i][1] += v.y, run_a[i][2] += v.z;
+              }
+            }
           }
         } else {
           float tm = run_m[i];
@@ -156,45 +166,50 @@ __global__ void __launch_bounds__(256) corr_simt_kernel(const CorrParams p) {
   }
 
   // ---- merge the 16 column groups of every row (As is free now) ----
-  float* red = smem;  // [128 rows][16 groups][5]
+  float* red = smem;  // [128 rows][16 groups][6]
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int rl = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4));
-    float* r = red + ((size_t)rl * 16 + tx) * 5;
+    float* r = red + ((size_t)rl * 16 + tx) * 6;
     r[0] = run_m[i];
-    if (!SOFTMAX) {
-      r[1] = __int_as_float(run_i[i]);
-    } else {
-      r[1] = run_s[i], r[2] = run_a[i][0], r[3] = run_a[i][1], r[4] = run_a[i][2];
-    }
+    r[1] = run_s[i], r[2] = run_a[i][0], r[3] = run_a[i][1], r[4] = run_a[i][2];
+    if (!SOFTMAX) r[5] = __int_as_float(run_i[i]);
   }
   __syncthreads();
   if (tid < BM && m0 + tid < p.NA) {
-    const float* r = red + (size_t)tid * 16 * 5;
+    const float* r = red + (size_t)tid * 16 * 6;
     const size_t o = (size_t)b * p.NA + m0 + tid;
     if (!SOFTMAX) {
-      float m = r[0];
-      int idx = __float_as_int(r[1]);
-      for (int g = 1; g < 16; ++g) {
-        const float mg = r[g * 5];
-        const int ig = __float_as_int(r[g * 5 + 1]);
-        if (mg > m || (mg == m && ig < idx)) m = mg, idx = ig;
+      float m = -INFINITY;
+      for (int g = 0; g < 16; ++g) m = fmaxf(m, r[g * 6]);
+      int idx = 0x7fffffff;
+      float cnt = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      for (int g = 0; g < 16; ++g)
+        if (r[g * 6] == m && r[g * 6 + 1] > 0.f) {
+          cnt += r[g * 6 + 1], a0 += r[g * 6 + 2], a1 += r[g * 6 + 3], a2 += r[g * 6 + 4];
+          idx = min(idx, __float_as_int(r[g * 6 + 5]));
+        }
+      float4 v;
+      if (cnt == 1.f) {
+        v = __ldg(Vg + idx);
+      } else {
+        const float inv = 1.f / cnt;
+        v = make_float4(a0 * inv, a1 * inv, a2 * inv, 0.f);
       }
-      const float4 v = __ldg(Vg + idx);
       reinterpret_cast<float4*>(p.y)[o] = make_float4(v.x, v.y, v.z, 0.f);
       p.sim[o] = m;
       if (p.argmax) p.argmax[o] = idx;
     } else {
       float m = -INFINITY;
-      for (int g = 0; g < 16; ++g) m = fmaxf(m, r[g * 5]);
+      for (int g = 0; g < 16; ++g) m = fmaxf(m, r[g * 6]);
       float s = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
       int idx = 0;
       float best = -INFINITY;
       for (int g = 0; g < 16; ++g) {
-        const float mg = r[g * 5];
+        const float mg = r[g * 6];
         if (mg == -INFINITY) continue;
         const float w = exp2f((mg - m) * sc);
-        s += w * r[g * 5 + 1], a0 += w * r[g * 5 + 2], a1 += w * r[g * 5 + 3], a2 += w * r[g * 5 + 4];
+        s += w * r[g * 6 + 1], a0 += w * r[g * 6 + 2], a1 += w * r[g * 6 + 3], a2 += w * r[g * 6 + 4];
         if (mg > best) best = mg, idx = g;
       }
       (void)idx;

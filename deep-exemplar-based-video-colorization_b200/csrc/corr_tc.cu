@@ -74,11 +74,50 @@ struct Cfg {
   static constexpr int STAGES = CL == 2 ? 3 : 2;
   static constexpr int A_BYTES = BM * 128, B_BYTES = (BN / CL) * 128;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 98304 / 65536
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int V_RING_BYTES = 2 * BN * 16;  // softmax epilogue: the V rows of the tile in flight, two slots
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + V_RING_BYTES;
 };
-constexpr int NTHREADS = 192;
+// warp 0 TMA, warp 1 MMA, then the epilogue warps: 4 (one per TMEM lane quarter) for the argmax epilogue, 8 for the
+// softmax epilogue (two per lane quarter, each owning 128 of the tile's 256 columns: twice the threads to hide the
+// exp2 / FMA latency chains behind)
+template <bool SOFTMAX>
+struct Epi {
+  static constexpr int WARPS = SOFTMAX ? 8 : 4;
+  static constexpr int HALVES = WARPS / 4;
+  static constexpr int NTHREADS = 64 + 32 * WARPS;
+};
 
-struct SplitOut {  // per (split, row) partial statistics
+// packed fp32 pair arithmetic (Blackwell FFMA2): acc.{x,y} += a.{x,y} * b.{x,y}
+__device__ __forceinline__ void fma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long pack2(float x, float y) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 1-D bulk copy global -> this CTA's shared memory, completing on a local mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+
+// per (split part, row) partial statistics.  Softmax: running max m, sum s of exp weights, weighted colour sums a*.
+// Argmax: max m, lowest column idx attaining it, s = NUMBER of columns whose score equals m bit for bit and a* = the sum
+// of their V rows -- the reference's fp32 softmax(f / 1e-10) averages the V rows of bit-equal maxima (duplicated
+// exemplar columns: letterbox bars, flat regions), NonlocalNet.py:486-497.
+struct SplitOut {
   float m, s, a0, a1, a2;
   int idx;
   float pad0, pad1;
@@ -143,9 +182,48 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
   }
 }
 
+// ---- screened T -> 0 path: operand preparation ---------------------------------------------------------
+// One warp per row of [R][256]: the fp16 hi plane of x * 2^14 (the only operand of the screening pass) and the exact
+// Euclidean norm of what the plane drops, d = x - hi * 2^-14, which bounds the screening error of every score of that
+// row: |f - f_screen| <= |d_a . b| + |a_hi . d_b| <= ||d_a|| ||b|| + ||a_hi|| ||d_b||  (Cauchy-Schwarz).
+// nd[row] = ||d_row|| (rounded up), nh[row] = ||hi_row * 2^-14|| (rounded up); *nd_max = max over rows (float bits).
+__global__ void __launch_bounds__(256) screen_planes_kernel(const float* __restrict__ src, __half* __restrict__ hi, float* __restrict__ nd,
+                                                            float* __restrict__ nh, unsigned int* __restrict__ nd_max,
+                                                            unsigned int* __restrict__ nh_max, int R) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  const float4* sp = reinterpret_cast<const float4*>(src + (size_t)warp * 256);
+  float sd = 0.f, sh = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float4 v = __ldg(sp + k * 32 + lane);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    unsigned short hb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half h = __float2half_rn(x[j] * 16384.0f);
+      hb[j] = __half_as_ushort(h);
+      const float hf = __half2float(h) * 6.103515625e-05f;  // exact: a power-of-two scale
+      const float d = x[j] - hf;                            // exact (Sterbenz / few significant bits)
+      sd = fmaf(d, d, sd), sh = fmaf(hf, hf, sh);
+    }
+    reinterpret_cast<uint2*>(hi + (size_t)warp * 256)[k * 32 + lane] =
+        make_uint2((uint32_t)hb[0] | ((uint32_t)hb[1] << 16), (uint32_t)hb[2] | ((uint32_t)hb[3] << 16));
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, off), sh += __shfl_xor_sync(0xffffffffu, sh, off);
+  if (lane == 0) {
+    // round the norms up generously (fp32 summation error of 256 non-negative terms is < 2^-15 relative)
+    const float a = sqrtf(sd) * 1.0001f + 1e-12f, b = sqrtf(sh) * 1.0001f;
+    nd[warp] = a, nh[warp] = b;
+    atomicMax(nd_max, __float_as_uint(a));
+    atomicMax(nh_max, __float_as_uint(b));
+  }
+}
+
 // ---- main kernel ---------------------------------------------------------------------------------------
 template <int FMT, bool SOFTMAX, int CL>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(Epi<SOFTMAX>::NTHREADS, 1)
     corr_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
   constexpr bool TF32 = (FMT == 0);
@@ -163,7 +241,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   uint64_t* empty = bars + STAGES;       // [STAGES]   MMA -> TMA
   uint64_t* tfull = bars + 2 * STAGES;   // [2]        MMA -> epilogue
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]    epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* vfull = bars + 2 * STAGES + 4;   // [2]    bulk copy of the tile's V rows -> epilogue (softmax)
+  uint64_t* vempty = bars + 2 * STAGES + 6;  // [2]    this CTA's epilogue -> its producer (softmax)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+  float4* v_ring = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES + 256);  // [2][BN]
+  constexpr int EPI_WARPS = Epi<SOFTMAX>::WARPS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -181,7 +263,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc::tma_prefetch_desc(&tmBh);
     tc::tma_prefetch_desc(&tmBl);
     for (int i = 0; i < STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
-    for (int i = 0; i < 2; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 4 * CL);  // pair: both epilogues
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], EPI_WARPS * CL);  // pair: both epilogues
+      tc::mbar_init(&vfull[i], 1), tc::mbar_init(&vempty[i], EPI_WARPS);
+    }
     tc::fence_barrier_init();
   }
   if (CL == 2) tc::cluster_sync_all();  // both CTAs are resident before the pair allocation
@@ -228,6 +313,20 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           }
           __syncwarp();
           if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        if (SOFTMAX) {
+          // the V rows of this tile's columns for my own epilogue.  Issued after the tile's last k-block: by then the
+          // MMAs of this tile have started, so the slot (freed together with the accumulator of tile t-2) is free and
+          // the wait below never delays the operand prefetch.
+          const int buf = t & 1;
+          tc::mbar_wait(&vempty[buf], ((t >> 1) & 1) ^ 1);
+          if (tc::elect_one()) {
+            const int c0 = (t0 + t) * BN;
+            const uint32_t bytes = (uint32_t)min(BN, p.NB - c0) * 16u;
+            tc::mbar_arrive_expect_tx(&vfull[buf], bytes);
+            bulk_load_1d(v_ring + buf * BN, p.V + (size_t)bphi * p.NB + c0, bytes, &vfull[buf]);
+          }
+          __syncwarp();
         }
       }
     }
@@ -277,27 +376,34 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       }
     }
   } else {
-    // ================= epilogue: one query row per thread =================
+    // ================= epilogue: one query row per thread (softmax: per thread and column half) =================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = SOFTMAX ? ((warp - 2) >> 2) : 0;  // which 128 columns of every 256-column tile
+    constexpr int COLS = BN / Epi<SOFTMAX>::HALVES;     // columns per thread and tile
     const int row_local = q * 32 + lane;
     const int row = m0 + row_local;
     const float sck = p.sc * p.out_scale;  // exponent scale in units of the (possibly pre-scaled) TMEM scores
-    float run_m = -INFINITY, run_s = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    float run_m = -INFINITY;
+    // argmax: number of bit-equal maxima and the sum of their V rows; softmax: (a0, a1) and (a2, s) as packed pairs
+    float cnt = 0.f, t0s = 0.f, t1s = 0.f, t2s = 0.f;
+    unsigned long long acc01 = 0ull, acc2s = 0ull;
     int run_i = 0;
     const float4* __restrict__ Vg = p.V + (size_t)bphi * p.NB;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
       tc::mbar_wait(&tfull[buf], acc_phase);
+      if (SOFTMAX) tc::mbar_wait(&vfull[buf], acc_phase);
       tc::tc_fence_after();
-      const int colbase = (t0 + t) * BN;
+      const int colbase = (t0 + t) * BN + half * COLS;
+      const float4* Vs = v_ring + buf * BN + half * COLS;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < COLS / 32; ++c) {
         const int cb = colbase + c * 32;
         if (cb >= p.NB) break;  // warp-uniform
         uint32_t r[32];
         __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, r);
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * COLS + c * 32, r);
         tc::tmem_ld_wait();
         const int nvalid = min(32, p.NB - cb);
         float cm = -INFINITY;
@@ -310,26 +416,44 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             if (i < nvalid) cm = fmaxf(cm, __uint_as_float(r[i]));
         }
         if (!SOFTMAX) {
-          if (cm > run_m) {  // rare once the running maximum has settled
-            run_m = cm;
+          if (cm >= run_m) {  // rare once the running maximum has settled
+            if (cm > run_m) run_m = cm, cnt = 0.f, t0s = t1s = t2s = 0.f;
 #pragma unroll
-            for (int i = 31; i >= 0; --i)
-              if (i < nvalid && __uint_as_float(r[i]) == cm) run_i = cb + i;  // lowest index wins
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid && __uint_as_float(r[i]) == cm) {
+                if (cnt == 0.f) run_i = cb + i;  // lowest index attaining the maximum
+                const float4 v = __ldg(Vg + cb + i);
+                cnt += 1.f, t0s += v.x, t1s += v.y, t2s += v.z;
+              }
           }
         } else {
           if (cm > run_m) {
-            const float sc_old = (run_m == -INFINITY) ? 0.f : exp2f((run_m - cm) * sck);
-            run_s *= sc_old, a0 *= sc_old, a1 *= sc_old, a2 *= sc_old;
+            const float sc_old = (run_m == -INFINITY) ? 0.f : ex2_approx((run_m - cm) * sck);
+            const unsigned long long sc2 = pack2(sc_old, sc_old);
+            unsigned long long z = 0ull;
+            fma2(z, acc01, sc2), acc01 = z, z = 0ull;
+            fma2(z, acc2s, sc2), acc2s = z;
             run_m = cm;
           }
+          // weights e = 2^((f - m) * log2(e) / T); V rows come from shared memory as (L, a | b, 1): two packed FMAs
+          // accumulate (a0, a1) and (a2, sum of weights)
+          if (nvalid == 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i < nvalid) {
-              const float e = exp2f((__uint_as_float(r[i]) - run_m) * sck);
-              const float4 v = __ldg(Vg + cb + i);  // same address across the warp: one broadcast load
-              run_s += e;
-              a0 = fmaf(e, v.x, a0), a1 = fmaf(e, v.y, a1), a2 = fmaf(e, v.z, a2);
+            for (int i = 0; i < 32; ++i) {
+              const float e = ex2_approx((__uint_as_float(r[i]) - run_m) * sck);
+              const ulonglong2 vv = *reinterpret_cast<const ulonglong2*>(Vs + c * 32 + i);
+              const unsigned long long e2 = pack2(e, e);
+              fma2(acc01, e2, vv.x), fma2(acc2s, e2, vv.y);
             }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) {
+                const float e = ex2_approx((__uint_as_float(r[i]) - run_m) * sck);
+                const ulonglong2 vv = *reinterpret_cast<const ulonglong2*>(Vs + c * 32 + i);
+                const unsigned long long e2 = pack2(e, e);
+                fma2(acc01, e2, vv.x), fma2(acc2s, e2, vv.y);
+              }
           }
         }
       }
@@ -340,12 +464,19 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           tc::mbar_arrive(&tempty[buf]);
         else
           tc::mbar_arrive_leader(&tempty[buf]);
+        if (SOFTMAX) tc::mbar_arrive(&vempty[buf]);
       }
     }
     if (row < p.NA) {
       SplitOut o;
-      o.m = run_m * p.out_scale, o.s = run_s, o.a0 = a0, o.a1 = a1, o.a2 = a2, o.idx = run_i, o.pad0 = o.pad1 = 0.f;
-      p.part[((size_t)blockIdx.z * p.B + b) * p.NA + row] = o;
+      o.m = run_m * p.out_scale, o.idx = run_i, o.pad0 = o.pad1 = 0.f;
+      if (SOFTMAX) {
+        const float2 x01 = unpack2(acc01), x2s = unpack2(acc2s);
+        o.s = x2s.y, o.a0 = x01.x, o.a1 = x01.y, o.a2 = x2s.x;
+      } else {
+        o.s = cnt, o.a0 = t0s, o.a1 = t1s, o.a2 = t2s;
+      }
+      p.part[((size_t)(blockIdx.z * Epi<SOFTMAX>::HALVES + half) * p.B + b) * p.NA + row] = o;
     }
   }
 
@@ -361,6 +492,316 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
 }
 
+// ---- screened T -> 0 path: one fp16 pass + exact re-scoring of the candidates ----------------------------------------
+// At T <= 2e-10 only the row maximum matters (one-hot softmax), and a single hi.hi pass locates it up to the
+// rigorous error eps_i of row i (screen_planes_kernel): every column j with f_screen(i, j) >= max_j f_screen - 2 eps_i is a
+// CANDIDATE, all others are provably not the maximum.  The screening kernel keeps up to SCREEN_K candidates per (row,
+// column-range split) while it streams the tiles -- one third of the MMA work and half of the operand bytes of the
+// 3-pass kernel; corr_rescore_kernel then evaluates the candidates exactly in fp32 on the CUDA cores (a few per row) and
+// produces (sim, argmax, mean V of bit-equal maxima).  A list that overflows marks its (row, split) for brute force.
+constexpr int SCREEN_K = 16;
+
+template <int CL>
+struct ScreenCfg {
+  static constexpr int STAGES = CL == 2 ? 6 : 4;
+  static constexpr int A_BYTES = BM * 128, B_BYTES = (BN / CL) * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 49152 / 32768
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+constexpr int SCREEN_THREADS = 192;
+
+struct ScreenParams {
+  int NA, NB, B, Bphi, C;
+  int tiles_per_split;
+  const float* nd_a;   // [B*NA]   ||dropped part|| of every query row
+  const float* nh_a;   // [B*NA]   ||hi part||
+  const unsigned int* nd_b_max;  // float bits: max over reference rows of ||dropped part||
+  const unsigned int* nh_b_max;  //             max over reference rows of ||hi part||
+  float* pm;     // [parts][B*NA]            screening maximum of the part (true-score units)
+  int* pcnt;     // [parts][B*NA]            number of candidates, or -1: overflow (brute-force the part's columns)
+  int* pidx;     // [parts][B*NA][SCREEN_K]  candidate columns
+};
+
+// 2 * eps_i in true-score units (see screen_planes_kernel); 64 * 2^-24 covers the truncating TMEM accumulation
+__device__ __forceinline__ float screen_threshold(float nd_a, float nh_a, float nd_b, float nh_b) {
+  return 2.f * (nd_a * (nh_b + nd_b) + nh_a * nd_b + 4e-6f) * 1.001f;
+}
+
+template <int CL>
+__global__ void __launch_bounds__(SCREEN_THREADS, 1)
+    corr_screen_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmBh, const ScreenParams p) {
+  using C = ScreenCfg<CL>;
+  constexpr int KB = 64;
+  constexpr uint32_t IDESC = tc::umma_idesc(0u, BM * CL, BN);
+  constexpr int STAGES = C::STAGES, A_BYTES = C::A_BYTES, STAGE_BYTES = C::STAGE_BYTES;
+  const int crank = (CL == 2) ? (int)tc::cluster_ctarank() : 0;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int bphi = (p.Bphi == 1) ? 0 : b;
+  const int m0 = blockIdx.x * BM;
+  const int ntiles_all = (p.NB + BN - 1) / BN;
+  const int t0 = blockIdx.z * p.tiles_per_split;
+  const int ntiles = max(min(t0 + p.tiles_per_split, ntiles_all) - t0, 0);
+  const int nkb = p.C / KB;
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmAh);
+    tc::tma_prefetch_desc(&tmBh);
+    for (int i = 0; i < STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 4 * CL);
+    tc::fence_barrier_init();
+  }
+  if (CL == 2) tc::cluster_sync_all();
+  if (warp == 1) {
+    if (CL == 2) {
+      tc::tmem_alloc_pair(tmem_slot, 512);
+      tc::tmem_relinquish_pair();
+    } else {
+      tc::tmem_alloc(tmem_slot, 512);
+      tc::tmem_relinquish();
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (CL == 2) tc::cluster_sync_all();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      const int col0 = bphi * p.NB + (t0 + t) * BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        if (tc::elect_one()) {
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          if (CL == 1) {
+            tc::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+            tc::tma_load_2d(st, &tmAh, &full[stage], kb * KB, b * p.NA + m0);
+            tc::tma_load_2d(st + A_BYTES, &tmBh, &full[stage], kb * KB, col0);
+          } else {
+            if (crank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+            tc::tma_load_2d_pair(st, &tmAh, &full[stage], kb * KB, b * p.NA + m0);
+            tc::tma_load_2d_pair(st + A_BYTES, &tmBh, &full[stage], kb * KB, col0 + crank * (BN / 2));
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (CL == 1 || crank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        tc::mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t dA = tc::umma_desc_k128(sa), dB = tc::umma_desc_k128(sa + A_BYTES);
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+              if (CL == 1)
+                tc::umma_ss<false>(d, dA + adv, dB + adv, IDESC, (kb | kk) ? 1u : 0u);
+              else
+                tc::umma_ss_pair<false>(d, dA + adv, dB + adv, IDESC, (kb | kk) ? 1u : 0u);
+            }
+            if (CL == 1) {
+              tc::umma_commit(&empty[stage]);
+              if (kb == nkb - 1) tc::umma_commit(&tfull[buf]);
+            } else {
+              tc::umma_commit_pair_mc(&empty[stage], 3);
+              if (kb == nkb - 1) tc::umma_commit_pair_mc(&tfull[buf], 3);
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================= epilogue: one query row per thread =================
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const size_t grow = (size_t)b * p.NA + min(row, p.NA - 1);
+    // candidate threshold in TMEM units (scores there are true scores * 2^28)
+    const float thr = screen_threshold(__ldg(p.nd_a + grow), __ldg(p.nh_a + grow), __uint_as_float(__ldg(p.nd_b_max)),
+                                       __uint_as_float(__ldg(p.nh_b_max))) * 268435456.0f;
+    float run_m = -INFINITY;
+    float cf[SCREEN_K];
+    int ci[SCREEN_K];
+    int cnt = 0;
+    bool overflow = false;
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      tc::mbar_wait(&tfull[buf], (t >> 1) & 1);
+      tc::tc_fence_after();
+      const int colbase = (t0 + t) * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int cb = colbase + c * 32;
+        if (cb >= p.NB) break;
+        uint32_t r[32];
+        __syncwarp();
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, r);
+        tc::tmem_ld_wait();
+        const int nvalid = min(32, p.NB - cb);
+        float cm = -INFINITY;
+        if (nvalid == 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < nvalid) cm = fmaxf(cm, __uint_as_float(r[i]));
+        }
+        run_m = fmaxf(run_m, cm);
+        const float lim = run_m - thr;
+        if (cm >= lim && !overflow) {  // this chunk holds candidates (rare once the running maximum has settled)
+          float tmp[32];  // indexed dynamically below: lives in local memory, written only on this rare path
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tmp[i] = __uint_as_float(r[i]);
+#pragma unroll 1
+          for (int i = 0; i < nvalid; ++i) {
+            const float v = tmp[i];
+            if (v >= lim) {
+              if (cnt == SCREEN_K) {  // drop the entries the risen maximum has disqualified
+                int k = 0;
+                for (int j = 0; j < SCREEN_K; ++j)
+                  if (cf[j] >= lim) cf[k] = cf[j], ci[k] = ci[j], ++k;
+                cnt = k;
+              }
+              if (cnt == SCREEN_K) {
+                overflow = true;
+                break;
+              }
+              cf[cnt] = v, ci[cnt] = cb + i, ++cnt;
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CL == 1)
+          tc::mbar_arrive(&tempty[buf]);
+        else
+          tc::mbar_arrive_leader(&tempty[buf]);
+      }
+    }
+    if (row < p.NA) {
+      const size_t o = ((size_t)blockIdx.z * p.B + b) * p.NA + row;
+      p.pm[o] = run_m * 3.725290298461914e-09f;
+      int k = 0;
+      if (!overflow) {
+        const float lim = run_m - thr;
+        for (int j = 0; j < cnt; ++j)
+          if (cf[j] >= lim) p.pidx[o * SCREEN_K + k++] = ci[j];
+      }
+      p.pcnt[o] = overflow ? -1 : k;
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (CL == 2) tc::cluster_sync_all();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    if (CL == 2)
+      tc::tmem_dealloc_pair(tmem_base, 512);
+    else
+      tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Exact re-scoring: one warp per query row.  fp32 dot products of the ORIGINAL fp32 operands (lane l owns dimensions
+// 4l..4l+3 and 128+4l..128+4l+3, eight FMAs, then a butterfly sum that leaves the same bits in every lane), running
+// (max, lowest index, number of bit-equal maxima, sum of their V rows) exactly like the 3-pass kernel's epilogue.
+__global__ void __launch_bounds__(256) corr_rescore_kernel(const float* __restrict__ theta, const float* __restrict__ phi,
+                                                           const float4* __restrict__ V, const ScreenParams p, int nparts,
+                                                           float4* __restrict__ y, float* __restrict__ sim, int* __restrict__ argmax,
+                                                           const CorrPeers peers) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int rows = p.B * p.NA;
+  if (r >= rows) return;
+  const int b = r / p.NA;
+  const int bphi = (p.Bphi == 1) ? 0 : b;
+  const float* ph = phi + (size_t)bphi * p.NB * 256;
+  const float4* Vg = V + (size_t)bphi * p.NB;
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(theta + (size_t)r * 256) + lane);
+  const float4 a1 = __ldg(reinterpret_cast<const float4*>(theta + (size_t)r * 256) + 32 + lane);
+  auto score = [&](int col) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(ph + (size_t)col * 256) + lane);
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(ph + (size_t)col * 256) + 32 + lane);
+    float s0 = a0.x * b0.x, s1 = a1.x * b1.x;
+    s0 = fmaf(a0.y, b0.y, s0), s1 = fmaf(a1.y, b1.y, s1);
+    s0 = fmaf(a0.z, b0.z, s0), s1 = fmaf(a1.z, b1.z, s1);
+    s0 = fmaf(a0.w, b0.w, s0), s1 = fmaf(a1.w, b1.w, s1);
+    float sacc = s0 + s1;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
+    return sacc;
+  };
+  float pmax = -INFINITY;
+  for (int s = 0; s < nparts; ++s) pmax = fmaxf(pmax, __ldg(p.pm + (size_t)s * rows + r));
+  const float thr = screen_threshold(__ldg(p.nd_a + r), __ldg(p.nh_a + r), __uint_as_float(__ldg(p.nd_b_max)), __uint_as_float(__ldg(p.nh_b_max)));
+  float m = -INFINITY, cnt = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
+  int idx = 0x7fffffff;
+  auto visit = [&](int col) {
+    const float f = score(col);
+    if (f >= m) {
+      const float4 v = __ldg(Vg + col);
+      if (f > m) m = f, cnt = 0.f, t0 = t1 = t2 = 0.f, idx = col;
+      idx = min(idx, col), cnt += 1.f, t0 += v.x, t1 += v.y, t2 += v.z;
+    }
+  };
+  const int ntiles_all = (p.NB + BN - 1) / BN;
+  for (int s = 0; s < nparts; ++s) {
+    const size_t o = (size_t)s * rows + r;
+    if (__ldg(p.pm + o) < pmax - thr) continue;  // nothing in this part can be the maximum
+    const int n = __ldg(p.pcnt + o);
+    if (n >= 0) {
+      for (int j = 0; j < n; ++j) visit(__ldg(p.pidx + o * SCREEN_K + j));
+    } else {  // overflowed list: every column of the part's range
+      const int c0 = s * p.tiles_per_split * BN, c1 = min(min((s + 1) * p.tiles_per_split, ntiles_all) * BN, p.NB);
+      for (int col = c0; col < c1; ++col) visit(col);
+    }
+  }
+  if (lane == 0) {
+    float4 v;
+    if (cnt == 1.f) {
+      v = __ldg(Vg + idx);
+    } else {
+      const float inv = 1.f / cnt;
+      v = make_float4(t0 * inv, t1 * inv, t2 * inv, 0.f);
+    }
+    y[r] = make_float4(v.x, v.y, v.z, 0.f);
+    sim[r] = m;
+    if (argmax) argmax[r] = idx;
+    for (int g = 0; g < peers.n; ++g) {
+      reinterpret_cast<float4*>(peers.y4[g])[peers.row0 + r] = make_float4(v.x, v.y, v.z, 0.f);
+      peers.sim[g][peers.row0 + r] = m;
+    }
+  }
+}
+
 // ---- merge the column-range splits ----------------------------------------------------------------------
 template <bool SOFTMAX>
 __global__ void __launch_bounds__(256) corr_merge_kernel(const SplitOut* __restrict__ part, int nsplit, int rows, int NA,
@@ -373,12 +814,21 @@ __global__ void __launch_bounds__(256) corr_merge_kernel(const SplitOut* __restr
   const float4* Vg = V + (size_t)((Bphi == 1) ? 0 : b) * NB;
   if (!SOFTMAX) {
     float m = -INFINITY;
-    int idx = 0;
+    for (int s = 0; s < nsplit; ++s) m = fmaxf(m, part[(size_t)s * rows + r].m);
+    // mean of the V rows of all bit-equal maxima (one row, exactly, when the maximum is unique)
+    int idx = 0x7fffffff;
+    float cnt = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
     for (int s = 0; s < nsplit; ++s) {
       const SplitOut o = part[(size_t)s * rows + r];
-      if (o.m > m || (o.m == m && o.idx < idx)) m = o.m, idx = o.idx;
+      if (o.m == m && o.s > 0.f) cnt += o.s, a0 += o.a0, a1 += o.a1, a2 += o.a2, idx = min(idx, o.idx);
     }
-    const float4 v = __ldg(Vg + idx);
+    float4 v;
+    if (cnt == 1.f) {
+      v = __ldg(Vg + idx);
+    } else {
+      const float inv = 1.f / cnt;
+      v = make_float4(a0 * inv, a1 * inv, a2 * inv, 0.f);
+    }
     y[r] = make_float4(v.x, v.y, v.z, 0.f);
     sim[r] = m;
     if (argmax) argmax[r] = idx;
@@ -410,7 +860,7 @@ int ws_get(CorrWorkspace* ws, int i, size_t bytes, void** out) {
   if (ws->cap[i] < bytes) {  // growth outside dvc_set_exemplar's reservation: a stand-alone call with a new shape
     if (ws->buf[i]) cudaFree(ws->buf[i]);
     ws->buf[i] = nullptr, ws->cap[i] = 0;
-    if (i == 2 || i == 3) ws->phi_src = nullptr, ws->phi_version = -1;
+    if (i == 2 || i == 3 || i == 5) ws->phi_src = nullptr, ws->phi_version = -1;
     if (cudaMalloc(&ws->buf[i], bytes) != cudaSuccess) return -1;
     ws->cap[i] = bytes;
   }
@@ -428,7 +878,7 @@ int launch_main_cl(const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtenso
       return -1;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid, cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<CL>::SMEM_BYTES, cfg.stream = s;
+  cfg.gridDim = grid, cfg.blockDim = dim3(Epi<SOFTMAX>::NTHREADS), cfg.dynamicSmemBytes = Cfg<CL>::SMEM_BYTES, cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
@@ -455,25 +905,45 @@ bool first_use_on_device(unsigned long long* mask) {
   return true;
 }
 
+static size_t screen_norm_bytes(int B, int Bphi, int NA, int NB) { return ((size_t)2 * B * NA + (size_t)2 * Bphi * NB + 8) * 4; }
+static size_t screen_cand_bytes(int nparts, int B, int NA) { return (size_t)nparts * B * NA * (8 + 4 * SCREEN_K); }
+
 int corr_ws_reserve(CorrWorkspace* ws, int B, int Bphi, int NA, int NB) {
   void* d;
   const size_t ea = (size_t)B * NA * 256 * 4, ephi = (size_t)Bphi * NB * 256 * 4;  // tf32 words: the widest format
-  const size_t part = (size_t)16 * B * NA * sizeof(SplitOut);                       // at most 16 column splits
-  if (ws_get(ws, 0, ea, &d) || ws_get(ws, 1, ea, &d) || ws_get(ws, 2, ephi, &d) || ws_get(ws, 3, ephi, &d) || ws_get(ws, 4, part, &d))
+  const size_t part = (size_t)16 * 2 * B * NA * sizeof(SplitOut);                   // at most 16 column splits x 2 column halves
+  if (ws_get(ws, 0, ea, &d) || ws_get(ws, 1, ea, &d) || ws_get(ws, 2, ephi, &d) || ws_get(ws, 3, ephi, &d) || ws_get(ws, 4, part, &d) ||
+      ws_get(ws, 5, screen_norm_bytes(B, Bphi, NA, NB), &d) || ws_get(ws, 6, screen_cand_bytes(16, B, NA), &d))
     return -1;
   return 0;
 }
 
 void corr_ws_free(CorrWorkspace* ws) {
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; i < CorrWorkspace::NBUF; ++i) {
     if (ws->buf[i]) cudaFree(ws->buf[i]);
     ws->buf[i] = nullptr, ws->cap[i] = 0;
   }
   ws->phi_src = nullptr, ws->phi_version = -1;
 }
 
-int launch_corr_tc(const CorrParams& p, int math, int cluster, CorrWorkspace* ws, long long phi_version, cudaStream_t s,
-                   std::string* err) {
+template <int CL>
+static int launch_screen_cl(const CUtensorMap& mA, const CUtensorMap& mB, const ScreenParams& sp, dim3 grid, cudaStream_t s) {
+  static unsigned long long attr_mask = 0;
+  if (first_use_on_device(&attr_mask)) {
+    if (cudaFuncSetAttribute(corr_screen_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScreenCfg<CL>::SMEM_BYTES) != cudaSuccess)
+      return -1;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = dim3(SCREEN_THREADS), cfg.dynamicSmemBytes = ScreenCfg<CL>::SMEM_BYTES, cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, corr_screen_kernel<CL>, mA, mB, sp) == cudaSuccess ? 0 : -2;
+}
+
+int launch_corr_tc(const CorrParams& p, int math, int cluster, int screen, CorrWorkspace* ws, long long phi_version,
+                   cudaStream_t s, std::string* err) {
   auto fail = [&](const char* m) {
     if (err) *err = m;
     return -1;
@@ -507,7 +977,44 @@ int launch_corr_tc(const CorrParams& p, int math, int cluster, CorrWorkspace* ws
   }
   const int tps = (ntiles + nsplit - 1) / nsplit;
   nsplit = (ntiles + tps - 1) / tps;
-  if (ws_get(ws, 4, (size_t)nsplit * p.B * p.NA * sizeof(SplitOut), &part)) return fail("workspace allocation failed");
+  const bool softmax = !(p.temperature <= 2e-10f);
+  if (screen && fmt == 2 && !softmax) {
+    // ---- screened T -> 0 path: hi planes + error norms, one fp16 pass, exact re-scoring of the candidates ----
+    const int rows = p.B * p.NA, rphi = p.Bphi * p.NB;
+    void *norms, *cand;
+    if (ws_get(ws, 5, screen_norm_bytes(p.B, p.Bphi, p.NA, p.NB), &norms) || ws_get(ws, 6, screen_cand_bytes(nsplit, p.B, p.NA), &cand))
+      return fail("workspace allocation failed");
+    float* nd_a = (float*)norms;
+    float* nh_a = nd_a + rows;
+    float* nd_b = nh_a + rows;
+    float* nh_b = nd_b + rphi;
+    unsigned int* cells = (unsigned int*)(nh_b + rphi);  // [0,1]: query side (unused maxima), [2,3]: reference side
+    const bool phi_cached = phi_version >= 0 && ws->phi_src == p.phi && ws->phi_version == phi_version && ws->phi_fmt == 3 &&
+                            ws->phi_elems == ephi;
+    if (cudaMemsetAsync(cells, 0, (phi_cached ? 2 : 4) * sizeof(unsigned int), s) != cudaSuccess) return fail("cudaMemsetAsync failed");
+    screen_planes_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>(p.theta, (__half*)Ah, nd_a, nh_a, cells + 0, cells + 1, rows);
+    if (!phi_cached) screen_planes_kernel<<<(rphi * 32 + 255) / 256, 256, 0, s>>>(p.phi, (__half*)Bh, nd_b, nh_b, cells + 2, cells + 3, rphi);
+    launch_counter_add(phi_cached ? 1 : 2);
+    ws->phi_src = phi_version >= 0 ? p.phi : nullptr, ws->phi_version = phi_version, ws->phi_fmt = 3, ws->phi_elems = ephi;
+    CUtensorMap mA, mB;
+    if (encode_tmap_2d(&mA, Ah, (uint64_t)rows, p.C, BM, 64, 2) || encode_tmap_2d(&mB, Bh, (uint64_t)rphi, p.C, BN / cl, 64, 2))
+      return fail("cuTensorMapEncodeTiled failed");
+    ScreenParams sp;
+    sp.NA = p.NA, sp.NB = p.NB, sp.B = p.B, sp.Bphi = p.Bphi, sp.C = p.C, sp.tiles_per_split = tps;
+    sp.nd_a = nd_a, sp.nh_a = nh_a, sp.nd_b_max = cells + 2, sp.nh_b_max = cells + 3;
+    sp.pm = (float*)cand;
+    sp.pcnt = (int*)(sp.pm + (size_t)nsplit * rows);
+    sp.pidx = sp.pcnt + (size_t)nsplit * rows;
+    dim3 grid(row_blocks, p.B, nsplit);
+    const int rc = cl == 2 ? launch_screen_cl<2>(mA, mB, sp, grid, s) : launch_screen_cl<1>(mA, mB, sp, grid, s);
+    if (rc) return fail(rc == -1 ? "cudaFuncSetAttribute(max dynamic smem) failed" : "cudaLaunchKernelEx failed");
+    corr_rescore_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>(p.theta, p.phi, reinterpret_cast<const float4*>(p.V), sp, nsplit,
+                                                                reinterpret_cast<float4*>(p.y), p.sim, p.argmax, p.peers);
+    launch_counter_add(2);
+    return 0;
+  }
+  const int nparts = nsplit * (softmax ? Epi<true>::HALVES : 1);  // partial rows the merge kernel combines
+  if (ws_get(ws, 4, (size_t)nparts * p.B * p.NA * sizeof(SplitOut), &part)) return fail("workspace allocation failed");
 
   const int grid1 = 148 * 8;
   // the reference side's planes survive from launch to launch while (pointer, version, format, size) are unchanged
@@ -540,7 +1047,6 @@ int launch_corr_tc(const CorrParams& p, int math, int cluster, CorrWorkspace* ws
   tp.V = reinterpret_cast<const float4*>(p.V);
   tp.part = reinterpret_cast<SplitOut*>(part);
   dim3 grid(row_blocks, p.B, nsplit);
-  const bool softmax = !(p.temperature <= 2e-10f);
   int rc;
   if (fmt == 0)
     rc = softmax ? launch_main<0, true>(mAh, mAl, mBh, mBl, tp, grid, cl, s) : launch_main<0, false>(mAh, mAl, mBh, mBl, tp, grid, cl, s);
@@ -552,10 +1058,10 @@ int launch_corr_tc(const CorrParams& p, int math, int cluster, CorrWorkspace* ws
   launch_counter_add(1);
   const int rows = p.B * p.NA;
   if (softmax)
-    corr_merge_kernel<true><<<(rows + 255) / 256, 256, 0, s>>>(tp.part, nsplit, rows, p.NA, p.NB, p.Bphi, tp.sc, tp.V,
+    corr_merge_kernel<true><<<(rows + 255) / 256, 256, 0, s>>>(tp.part, nparts, rows, p.NA, p.NB, p.Bphi, tp.sc, tp.V,
                                                                 reinterpret_cast<float4*>(p.y), p.sim, p.argmax, p.peers);
   else
-    corr_merge_kernel<false><<<(rows + 255) / 256, 256, 0, s>>>(tp.part, nsplit, rows, p.NA, p.NB, p.Bphi, tp.sc, tp.V,
+    corr_merge_kernel<false><<<(rows + 255) / 256, 256, 0, s>>>(tp.part, nparts, rows, p.NA, p.NB, p.Bphi, tp.sc, tp.V,
                                                                  reinterpret_cast<float4*>(p.y), p.sim, p.argmax, p.peers);
   launch_counter_add(1);
   return 0;

@@ -128,6 +128,7 @@ struct dvc_ctx {
   ScaleCell* cell_next = nullptr;
   int cell_left = 0;
   int corr_cluster = 2;   // correlation: 2 = CTA pairs (tcgen05.mma.cta_group::2), 1 = single CTAs
+  int corr_screen = 1;    // T <= 2e-10, FP16X3: one screening pass + exact re-scoring of the candidates (0: exact 3-pass kernel)
   CorrWorkspace corr_ws;  // operand planes + split partials of the tensor-core correlation (pre-sized by dvc_set_exemplar)
   long long ex_version = 0;  // bumped whenever ex_phi's contents change (the correlation caches the exemplar's planes)
   int tc_force_bn = 0;    // tests: channel tile (64 / 128 / 256) forced on every tensor-core convolution it divides
@@ -870,7 +871,7 @@ static int run_corr(dvc_ctx* c, const CorrParams& p, cudaStream_t s, long long p
     launch_corr_simt(p, s);
   } else {
     std::string err;
-    if (launch_corr_tc(p, c->corr_math, c->corr_cluster, &c->corr_ws, phi_version, s, &err) != 0)
+    if (launch_corr_tc(p, c->corr_math, c->corr_cluster, c->corr_screen, &c->corr_ws, phi_version, s, &err) != 0)
       return fail(c, DVC_ERR_CUDA, "corr_tc: " + err);
   }
   DVC_TRY(check_launch(c, "corr"));
@@ -1123,6 +1124,7 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!strcmp(name, "two_level")) { c->two_level = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_kc")) { c->tc_kc = value < 1 ? 1 : value; return DVC_OK; }
   if (!strcmp(name, "corr_cluster")) { c->corr_cluster = value == 1 ? 1 : 2; return DVC_OK; }
+  if (!strcmp(name, "corr_screen")) { c->corr_screen = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_tail")) { c->tc_tail = value < 0 ? 0 : value; return DVC_OK; }  // > 1: pretend pair-slot count (tests)
   if (!strcmp(name, "tc_f16")) { c->tc_f16 = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_splits")) { c->tc_splits = value < 0 ? 0 : (value > 8 ? 8 : value); return DVC_OK; }
@@ -1422,8 +1424,9 @@ extern "C" int dvc_corr_softmax_warp(dvc_ctx* c, const float* theta_hat, const f
   // channel-major [b][C][N] (the reference's view, NonlocalNet.py:468,473) -> position-major rows
   launch_transpose_cn(theta_hat, (float*)th, B, C, NA, s);
   launch_transpose_cn(phi_hat, (float*)ph, Bphi, C, NB, s);
-  CUDA_TRY(c, cudaMemsetAsync(V4, 0, (size_t)Bphi * NB * 16, s));
-  CUDA_TRY(c, cudaMemcpy2DAsync(V4, 16, V, 12, 12, (size_t)Bphi * NB, cudaMemcpyDeviceToDevice, s));
+  // rows (L, a, b, 1): the 4th lane is the constant the softmax epilogue sums the weights with
+  launch_pack_v4(V, (float*)V4, (size_t)Bphi * NB, s);
+  DVC_TRY(check_launch(c, "pack_v4"));
   CorrParams p{};
   p.theta = (float*)th, p.phi = (float*)ph, p.V = (float*)V4, p.B = B, p.Bphi = Bphi, p.NA = NA, p.NB = NB, p.C = C;
   p.temperature = temperature, p.y = (float*)y4, p.sim = sim, p.argmax = argmax;
@@ -1771,6 +1774,9 @@ extern "C" int dvc_exemplar_import(dvc_ctx* c, const float* buf, int64_t n, int 
   }
   CUDA_TRY(c, cudaMemcpyAsync(c->ex_phi, buf, (size_t)N * 256 * 4, cudaMemcpyDeviceToDevice, s));
   CUDA_TRY(c, cudaMemcpyAsync(c->ex_V, buf + N * 256, (size_t)N * 16, cudaMemcpyDeviceToDevice, s));
+  // whatever produced the pack, the 4th lane of every V row must be 1 (corr_tc.cu's softmax epilogue)
+  launch_pack_v4(nullptr, c->ex_V, (size_t)N, s);
+  DVC_TRY(check_launch(c, "pack_v4"));
   c->ex_H = H, c->ex_W = W, c->ex_valid = true, c->ex_version++;
   if (corr_ws_reserve(&c->corr_ws, 1, 1, (int)N, (int)N) != 0) return fail(c, DVC_ERR_CUDA, "exemplar_import: correlation workspace allocation failed");
   return DVC_OK;

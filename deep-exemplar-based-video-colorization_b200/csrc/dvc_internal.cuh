@@ -177,8 +177,10 @@ void launch_maxpool2_h16(const void* h16, const void* l16, const ScaleCell* cell
                          void* dh16, void* dl16, ScaleCell* cell_out, int dP, int B, cudaStream_t s);
 // max |x| over n floats -> cell->amax_bits (cell zeroed by the caller's arena)
 void launch_amax(const float* x, size_t n, ScaleCell* cell, cudaStream_t s);
-// NCHW [B][3][H][W] -> V [B][H/4*W/4][4] (4th lane zero): F.avg_pool2d(.,4), NonlocalNet.py:491-493
+// NCHW [B][3][H][W] -> V [B][H/4*W/4][4] (4th lane ONE, see corr_tc.cu): F.avg_pool2d(.,4), NonlocalNet.py:491-493
 void launch_avgpool4_lab(const float* src, float* V, int B, int H, int W, cudaStream_t s);
+// rows [n][3] -> [n][4] = (x, y, z, 1); src == nullptr: only set the 4th lane of dst's rows to 1
+void launch_pack_v4(const float* src3, float* dst4, size_t n, cudaStream_t s);
 // y rows [B][N][4], sim rows [B][N] at h x w -> nearest x4 NCHW (NonlocalNet.py:499-500)
 void launch_rows_to_nchw_up4(const float* yrows, const float* simrows, float* y, float* sim, int B, int h, int w,
                              cudaStream_t s);
@@ -205,7 +207,7 @@ struct CorrPeers {
 struct CorrParams {
   const float* theta;  // [B][NA][C]  (position-major, channels contiguous)
   const float* phi;    // [Bphi][NB][C]
-  const float* V;      // [Bphi][NB][4]
+  const float* V;      // [Bphi][NB][4] = (L, a, b, 1)
   int B, Bphi, NA, NB, C;
   float temperature;
   float* y;     // [B][NA][4]

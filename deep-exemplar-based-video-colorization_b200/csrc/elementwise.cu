@@ -438,7 +438,17 @@ __global__ void __launch_bounds__(256) avgpool4_lab_kernel(const float* __restri
         for (int dx = 0; dx < 4; ++dx) s += __ldg(sp + dy * W + dx);
       o[c] = s * (1.0f / 16.0f);
     }
-    *reinterpret_cast<float4*>(V + ((size_t)b * h * w + n) * 4) = make_float4(o[0], o[1], o[2], 0.f);
+    // 4th lane = 1: the softmax epilogue of the correlation accumulates (b, sum of weights) with one packed FMA
+    *reinterpret_cast<float4*>(V + ((size_t)b * h * w + n) * 4) = make_float4(o[0], o[1], o[2], 1.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_v4_kernel(const float* __restrict__ src3, float* __restrict__ dst4, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (src3)
+      reinterpret_cast<float4*>(dst4)[i] = make_float4(__ldg(src3 + 3 * i), __ldg(src3 + 3 * i + 1), __ldg(src3 + 3 * i + 2), 1.f);
+    else
+      dst4[4 * i + 3] = 1.f;
   }
 }
 
@@ -667,6 +677,11 @@ void launch_amax(const float* x, size_t n, ScaleCell* cell, cudaStream_t s) {
 void launch_avgpool4_lab(const float* src, float* V, int B, int H, int W, cudaStream_t s) {
   dim3 grid(grid_for((long)(H / 4) * (W / 4), 256), B);
   avgpool4_lab_kernel<<<grid, 256, 0, s>>>(src, V, H, W);
+  launch_counter_add(1);
+}
+
+void launch_pack_v4(const float* src3, float* dst4, size_t n, cudaStream_t s) {
+  pack_v4_kernel<<<grid_for((long)n, 256), 256, 0, s>>>(src3, dst4, n);
   launch_counter_add(1);
 }
 

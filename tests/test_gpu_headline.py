@@ -120,13 +120,14 @@ def corr_oracle_25920():
     return dict(th=th, ph=ph, V=V, T=T, sim=torch.cat(sims), idx=torch.cat(idxs), gap=torch.cat(gaps), y=torch.cat(ys))
 
 
-@pytest.mark.parametrize("mode", ["fp16x3", "fp16x3-single", "tf32x3", "bf16x3", "fp32"])
+@pytest.mark.parametrize("mode", ["fp16x3", "fp16x3-single", "fp16x3-noscreen", "tf32x3", "bf16x3", "fp32"])
 def test_corr_kernel_vs_oracle_25920(ctx, corr_oracle_25920, mode):
     """The 204 row blocks x 5 column splits of the bench's correlation launch, against the chunked fp64 oracle."""
     import dvc
 
     o = corr_oracle_25920
-    name = mode.replace("-single", "")
+    name = mode.replace("-single", "").replace("-noscreen", "")
+    ctx.debug_flag("corr_screen", 0 if "noscreen" in mode else 1)
     ctx.set_math(conv=dvc.MATH_TF32X3, corr={"fp32": dvc.MATH_FP32, "tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3,
                                               "fp16x3": dvc.MATH_FP16X3}[name])
     ctx.debug_flag("corr_cluster", 1 if mode.endswith("-single") else 2)
@@ -147,4 +148,5 @@ def test_corr_kernel_vs_oracle_25920(ctx, corr_oracle_25920, mode):
         assert e_y < (2e-2 if name == "bf16x3" else 2e-3)
     finally:
         ctx.debug_flag("corr_cluster", 2)
+        ctx.debug_flag("corr_screen", 1)
         ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)

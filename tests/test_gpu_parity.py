@@ -96,18 +96,22 @@ def test_vgg19_all_keys_and_no_preprocess(ctx, conv_math, sds):
 
 
 # ------------------------------------------------------------------------------------------ K7
-@pytest.fixture(params=["fp32", "tf32x3", "bf16x3", "fp16x3", "tf32x3-single", "fp16x3-single"])
+@pytest.fixture(params=["fp32", "tf32x3", "bf16x3", "fp16x3", "tf32x3-single", "fp16x3-single", "fp16x3-noscreen",
+                        "fp16x3-noscreen-single"])
 def corr_math(request, ctx):
     """Run the correlation tests on the CUDA-core kernel and on the tcgen05 operand-split modes, as CTA pairs
-    (cta_group::2, the default) and as single CTAs."""
+    (cta_group::2, the default) and as single CTAs.  fp16x3 at T -> 0 takes the screened path by default (one fp16 pass
+    + exact fp32 re-scoring of the candidates); "-noscreen" pins the exact 3-pass kernel."""
     import dvc
 
-    name = request.param.replace("-single", "")
+    name = request.param.replace("-single", "").replace("-noscreen", "")
     mode = {"fp32": dvc.MATH_FP32, "tf32x3": dvc.MATH_TF32X3, "bf16x3": dvc.MATH_BF16X3, "fp16x3": dvc.MATH_FP16X3}[name]
     ctx.set_math(conv=dvc.MATH_TF32X3, corr=mode)
     ctx.debug_flag("corr_cluster", 1 if request.param.endswith("-single") else 2)
+    ctx.debug_flag("corr_screen", 0 if "noscreen" in request.param else 1)
     yield name
     ctx.debug_flag("corr_cluster", 2)
+    ctx.debug_flag("corr_screen", 1)
     ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
 
 
@@ -131,6 +135,58 @@ def test_corr_kernel_vs_oracle(ctx, corr_math, NA, NB, T):
     else:
         # softmax weights see the score error as exp(df / T)
         assert (y.cpu().double() - yo).abs().max() < (2e-2 if corr_math == "bf16x3" else 2e-3)
+
+
+def test_corr_duplicated_exemplar_columns_average(ctx, corr_math):
+    """Bit-equal maxima (duplicated phi columns: letterbox bars, flat exemplar regions): the reference's
+    softmax(f / 1e-10) (NonlocalNet.py:486-497) averages the V rows of all of them -- so must the T -> 0 path."""
+    gen = torch.Generator().manual_seed(9)
+    NA, NB = 300, 700
+    ph = torch.nn.functional.normalize(torch.randn(1, 256, NB, generator=gen), dim=1)
+    dup = [3, 150, 151, 400, 699]            # five copies of column 3 spread over several 32-column chunks / tiles
+    ph[:, :, dup] = ph[:, :, 3:4]
+    ph[:, :, [20, 21]] = ph[:, :, 20:21]     # and a pair
+    th = torch.nn.functional.normalize(torch.randn(1, 256, NA, generator=gen), dim=1)
+    th[:, :, :40] = torch.nn.functional.normalize(ph[:, :, 3:4] + 0.05 * th[:, :, :40], dim=1)   # rows that pick the 5 copies
+    th[:, :, 40:60] = torch.nn.functional.normalize(ph[:, :, 20:21] + 0.05 * th[:, :, 40:60], dim=1)
+    V = torch.randn(1, NB, 3, generator=gen) * 30
+    y, sim, am = ctx.corr_softmax_warp(th.cuda(), ph.cuda(), V.cuda(), 1e-10, want_argmax=True)
+    yo, so, io = O.corr_softmax_warp(th.double(), ph.double(), V.double(), 1e-10, return_argmax=True)
+    y = y.cpu().double()
+    assert (y[0, :40] - V[0, dup].double().mean(0)).abs().max() < 1e-4
+    assert (y[0, 40:60] - V[0, [20, 21]].double().mean(0)).abs().max() < 1e-4
+    assert (am.cpu()[0, :40] == 3).all() and (am.cpu()[0, 40:60] == 20).all()  # lowest index of the tie
+    tol = 8e-6 if corr_math == "bf16x3" else 2e-6
+    gap = O.top2_gap(th.double(), ph.double())[0]
+    ok = (gap == 0) | (gap > 4 * tol)     # exact ties (averaged by the fp64 oracle too) or a clear winner
+    assert (y[0][ok] - yo[0][ok]).abs().max() < 1e-3
+    assert (sim.cpu().double() - so).abs().max() < tol
+
+
+def test_corr_many_near_ties_overflow_the_candidate_lists(ctx, corr_math):
+    """60 exemplar columns within 1e-6 of each other (plus 40 exact copies): far more candidates than a screening list
+    holds, so the affected rows take the brute-force re-scoring path; results must not change."""
+    gen = torch.Generator().manual_seed(10)
+    NA, NB = 200, 900
+    ph = torch.nn.functional.normalize(torch.randn(1, 256, NB, generator=gen), dim=1)
+    base = ph[:, :, 7:8].clone()
+    near = list(range(300, 360))
+    ph[:, :, near] = torch.nn.functional.normalize(base + 1e-6 * torch.randn(1, 256, 60, generator=gen), dim=1)
+    same = list(range(500, 540))
+    ph[:, :, same] = ph[:, :, 333:334]
+    th = torch.nn.functional.normalize(torch.randn(1, 256, NA, generator=gen), dim=1)
+    th[:, :, :50] = torch.nn.functional.normalize(base + 0.05 * th[:, :, :50], dim=1)
+    V = torch.randn(1, NB, 3, generator=gen) * 30
+    y, sim, am = ctx.corr_softmax_warp(th.cuda(), ph.cuda(), V.cuda(), 1e-10, want_argmax=True)
+    f = th[0].double().t() @ ph[0].double()
+    m64, i64 = f.max(1)
+    tol = 8e-6 if corr_math == "bf16x3" else 2e-6
+    assert (sim.cpu().double()[0] - m64).abs().max() < tol
+    # every reported argmax attains the fp64 maximum up to the score tolerance (the near ties are legal alternatives)
+    assert (f.gather(1, am.cpu()[0].long().view(-1, 1))[:, 0] - m64).abs().max() < 2 * tol
+    gap = O.top2_gap(th.double(), ph.double())[0]
+    clear = gap > 4 * tol
+    assert (am.cpu()[0][clear].long() == i64[clear]).all()
 
 
 def test_corr_kernel_shared_exemplar_batch(ctx, corr_math):
