@@ -1740,6 +1740,95 @@ extern "C" int dvc_rgb8_to_lab(dvc_ctx* c, const unsigned char* dev_rgb, int B, 
   return check_launch(c, "rgb8_to_lab");
 }
 
+// ---- Fast Global Smoother ("WLS filter", test.py:105-112) ---------------------------------------------------------
+extern "C" int dvc_fgs_filter(dvc_ctx* c, const unsigned char* dev_guide, const float* dev_src, int planes, int H, int W, float lambda,
+                              float sigma_color, float lambda_attenuation, int num_iter, float* dev_dst, void* stream) {
+  if (!c || !dev_guide || !dev_src || !dev_dst || planes < 1 || H < 2 || W < 2) return c ? fail(c, DVC_ERR_ARG, "fgs_filter: bad argument") : DVC_ERR_ARG;
+  if (!(lambda >= 0.f) || !(sigma_color > 0.f) || num_iter < 1 || !(lambda_attenuation > 0.f)) return fail(c, DVC_ERR_ARG, "fgs_filter: bad parameter");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const size_t hw = (size_t)H * W;
+  void *lut, *Ch, *Cv, *D;
+  DVC_TRY(get_raw(c, "fgs.lut", 256 * 4, &lut, s));
+  DVC_TRY(get_raw(c, "fgs.Ch", hw * 4, &Ch, s));
+  DVC_TRY(get_raw(c, "fgs.Cv", hw * 4, &Cv, s));
+  DVC_TRY(get_raw(c, "fgs.D", (size_t)planes * hw * 4, &D, s));
+  // weights_LUT[d] = -exp(-d / sigma_color), d = |difference of neighbouring guide pixels|: evaluated in double and
+  // rounded once to the fp32 work type (the oracle does the same, so the two agree bit for bit)
+  float h_lut[256];
+  for (int d = 0; d < 256; ++d) h_lut[d] = (float)(-exp(-(double)d / (double)sigma_color));
+  CUDA_TRY(c, cudaMemcpyAsync(lut, h_lut, sizeof(h_lut), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(c, cudaStreamSynchronize(s));  // h_lut lives on this stack frame
+  launch_fgs_weights(dev_guide, (const float*)lut, (float*)Ch, (float*)Cv, H, W, s);
+  DVC_TRY(check_launch(c, "fgs_weights"));
+  if (dev_dst != dev_src) CUDA_TRY(c, cudaMemcpyAsync(dev_dst, dev_src, (size_t)planes * hw * 4, cudaMemcpyDeviceToDevice, s));
+  float lam = lambda;
+  for (int n = 0; n < num_iter; ++n) {
+    launch_fgs_horizontal(dev_dst, (const float*)Ch, (float*)D, planes, H, W, lam, s);
+    launch_fgs_vertical(dev_dst, (const float*)Cv, (float*)D, planes, H, W, lam, s);
+    lam *= lambda_attenuation;
+  }
+  return check_launch(c, "fgs");
+}
+
+extern "C" int dvc_l_to_guide8(dvc_ctx* c, const float* dev_l, int H, int W, unsigned char* dev_guide, void* stream) {
+  if (!c || !dev_l || !dev_guide || H < 1 || W < 1) return c ? fail(c, DVC_ERR_ARG, "l_to_guide8: bad argument") : DVC_ERR_ARG;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  launch_l_to_guide8(dev_l, dev_guide, (size_t)H * W, (cudaStream_t)stream);
+  return check_launch(c, "l_to_guide8");
+}
+
+// ---- CenterPad's anti-aliased resize + crop / pad (util_distortion.py:217-258) ---------------------------------------
+static void gaussian_taps(double sigma, std::vector<double>* w, int* radius) {  // scipy.ndimage._gaussian_kernel1d, truncate = 4
+  const int r = (int)(4.0 * sigma + 0.5);
+  w->assign(2 * r + 1, 0.0);
+  const double s2 = sigma * sigma;
+  double sum = 0.0;
+  for (int x = -r; x <= r; ++x) (*w)[x + r] = exp(-0.5 / s2 * (double)(x * x)), sum += (*w)[x + r];
+  for (double& v : *w) v /= sum;
+  *radius = r;
+}
+
+extern "C" int dvc_resize_antialias_crop_rgb8(dvc_ctx* c, const unsigned char* dev_src, int Hs, int Ws, int Hr, int Wr, int oy, int ox,
+                                              unsigned char* dev_dst, int Ho, int Wo, void* stream) {
+  if (!c || !dev_src || !dev_dst || Hs < 1 || Ws < 1 || Hr < 1 || Wr < 1 || Ho < 1 || Wo < 1)
+    return c ? fail(c, DVC_ERR_ARG, "resize_antialias_crop: bad argument") : DVC_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)Hs * Ws * 3;
+  void *f0, *f1, *taps;
+  DVC_TRY(get_raw(c, "rs.f0", n * 8, &f0, s));
+  DVC_TRY(get_raw(c, "rs.f1", n * 8, &f1, s));
+  DVC_TRY(get_raw(c, "rs.taps", 8192 * 8, &taps, s));
+  // skimage.transform.resize: sigma = max(0, (in / out - 1) / 2) per axis, applied axis 0 first (scipy.ndimage.gaussian_filter)
+  const double sy = fmax(0.0, ((double)Hs / Hr - 1.0) / 2.0), sx = fmax(0.0, ((double)Ws / Wr - 1.0) / 2.0);
+  std::vector<double> wy, wx;
+  int ry = 0, rx = 0;
+  if (sy > 1e-15) gaussian_taps(sy, &wy, &ry);
+  if (sx > 1e-15) gaussian_taps(sx, &wx, &rx);
+  if (wy.size() + wx.size() > 8192) return fail(c, DVC_ERR_SHAPE, "resize_antialias_crop: down-scaling factor too large");
+  if (!wy.empty()) CUDA_TRY(c, cudaMemcpyAsync(taps, wy.data(), wy.size() * 8, cudaMemcpyHostToDevice, s));
+  if (!wx.empty()) CUDA_TRY(c, cudaMemcpyAsync((double*)taps + wy.size(), wx.data(), wx.size() * 8, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(c, cudaStreamSynchronize(s));  // the tap vectors live on this stack frame
+  // image as float64 [Hs][Ws][3]; a zero-radius "filter" (one tap of weight 1) converts uint8 -> float64 when an axis needs none
+  const double one = 1.0;
+  double* cur = (double*)f0;
+  double* nxt = (double*)f1;
+  if (wy.empty()) {
+    CUDA_TRY(c, cudaMemcpyAsync((double*)taps + 8191, &one, 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    launch_gauss_axis_u8(dev_src, cur, (double*)taps + 8191, 0, 1, Hs, Ws * 3, s);
+  } else {
+    launch_gauss_axis_u8(dev_src, cur, (double*)taps, ry, 1, Hs, Ws * 3, s);
+  }
+  if (!wx.empty()) {
+    launch_gauss_axis_f64(cur, nxt, (double*)taps + wy.size(), rx, (size_t)Hs, Ws, 3, s);
+    std::swap(cur, nxt);
+  }
+  launch_zoom_crop(cur, Hs, Ws, Hr, Wr, oy, ox, dev_dst, Ho, Wo, s);
+  return check_launch(c, "resize_antialias_crop");
+}
+
 // ---- exemplar operands for the NCCL broadcast -----------------------------------------------------
 extern "C" int64_t dvc_exemplar_pack_size(const dvc_ctx*, int H, int W) {
   const int64_t N = (int64_t)(H / 4) * (W / 4);

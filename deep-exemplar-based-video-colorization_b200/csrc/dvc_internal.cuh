@@ -228,6 +228,18 @@ void launch_rgb8_to_lab(const unsigned char* rgb, float* lab, int B, int H, int 
 void launch_lab_to_rgb8(const float* l, const float* ab, unsigned char* rgb, int B, int H, int W, const double* rgb_from_xyz,
                         cudaStream_t s);
 
+// Fast Global Smoother (test.py:105-112) and the CenterPad resize (util_distortion.py:217-258): prepost.cu
+void launch_fgs_weights(const unsigned char* guide, const float* lut, float* Ch, float* Cv, int H, int W, cudaStream_t s);
+void launch_fgs_horizontal(float* cur, const float* Ch, float* D, int planes, int H, int W, float lam, cudaStream_t s);
+void launch_fgs_vertical(float* cur, const float* Cv, float* D, int planes, int H, int W, float lam, cudaStream_t s);
+void launch_l_to_guide8(const float* l, unsigned char* g, size_t n, cudaStream_t s);
+void launch_gauss_axis_u8(const unsigned char* src, double* dst, const double* w, int radius, size_t n_outer, int len, int inner,
+                          cudaStream_t s);
+void launch_gauss_axis_f64(const double* src, double* dst, const double* w, int radius, size_t n_outer, int len, int inner,
+                           cudaStream_t s);
+void launch_zoom_crop(const double* src, int Hs, int Ws, int Hr, int Wr, int oy, int ox, unsigned char* dst, int Ho, int Wo,
+                      cudaStream_t s);
+
 int64_t launch_counter_add(int64_t n);  // global launch counter (introspection)
 
 }  // namespace dvc

@@ -23,6 +23,7 @@ EXPORTED = [
     "dvc_exemplar_export", "dvc_exemplar_import", "dvc_launch_count", "dvc_profile_corr", "dvc_corr_mean_ms",
     "dvc_debug_set_flag", "dvc_debug_get_buffer", "dvc_debug_conv2d", "dvc_profile_conv", "dvc_conv_profile",
     "dvc_resize_half", "dvc_upsample2_scaled", "dvc_lab_to_rgb8", "dvc_rgb8_to_lab",
+    "dvc_fgs_filter", "dvc_l_to_guide8", "dvc_resize_antialias_crop_rgb8",
     "dvc_peer_buffer_create", "dvc_peer_buffer_open", "dvc_peer_buffer_close", "dvc_peer_buffer_destroy",
     "dvc_corr_set_peer_outputs",
 ]
@@ -79,6 +80,10 @@ def load_library():
         lib.dvc_upsample2_scaled.argtypes = [c_void, c_void, c_int, c_int, c_int, c_float, c_void, c_void]
         lib.dvc_lab_to_rgb8.argtypes = [c_void, c_void, c_void, c_int, c_int, c_int, c_void, c_void]
         lib.dvc_rgb8_to_lab.argtypes = [c_void, c_void, c_int, c_int, c_int, c_void, c_void]
+        lib.dvc_fgs_filter.argtypes = [c_void, c_void, c_void, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_void, c_void]
+        lib.dvc_l_to_guide8.argtypes = [c_void, c_void, c_int, c_int, c_void, c_void]
+        lib.dvc_resize_antialias_crop_rgb8.argtypes = [c_void, c_void, c_int, c_int, c_int, c_int, c_int, c_int, c_void, c_int, c_int,
+                                                       c_void]
         lib.dvc_peer_buffer_create.argtypes = [c_void, c_i64, P(c_void), ctypes.c_char_p]
         lib.dvc_peer_buffer_open.argtypes = [c_void, ctypes.c_char_p, P(c_void)]
         lib.dvc_peer_buffer_close.argtypes = [c_void, c_void]
@@ -307,6 +312,44 @@ class Context:
         out = torch.empty(B, 3, H, W, device=rgb.device, dtype=torch.float32)
         self._check(self.lib.dvc_rgb8_to_lab(self.h, ctypes.c_void_p(rgb.data_ptr()), B, H, W, _ptr(out), _stream(rgb.device)),
                     "dvc_rgb8_to_lab")
+        return out
+
+    def fgs_filter(self, guide, src, lam=500.0, sigma_color=4.0, lambda_attenuation=0.25, num_iter=3):
+        """cv2.ximgproc.createFastGlobalSmootherFilter(guide, lam, sigma_color).filter(plane) for every plane of the
+        CUDA float32 tensor src [P,H,W] with the CUDA uint8 guide [H,W] (test.py:105-112; defaults of test.py:32-33)."""
+        src = _dev_f32(src, "fgs_filter src")
+        if not (isinstance(guide, torch.Tensor) and guide.is_cuda and guide.dtype == torch.uint8 and guide.dim() == 2):
+            raise DvcError("fgs_filter: the guide must be a CUDA uint8 [H,W] tensor")
+        P, H, W = src.shape
+        if tuple(guide.shape) != (H, W):
+            raise DvcError("fgs_filter: guide and planes differ in size")
+        guide = guide.contiguous()
+        out = torch.empty_like(src)
+        self._check(self.lib.dvc_fgs_filter(self.h, ctypes.c_void_p(guide.data_ptr()), _ptr(src), P, H, W, float(lam), float(sigma_color),
+                                            float(lambda_attenuation), int(num_iter), _ptr(out), _stream(src.device)), "dvc_fgs_filter")
+        return out
+
+    def l_to_guide8(self, l):
+        """uint8(uncenter_l(L) * 255 / 100) (test.py:106) for a CUDA float32 [H,W] centred-luminance plane."""
+        l = _dev_f32(l, "l_to_guide8 input")
+        H, W = l.shape[-2:]
+        out = torch.empty(H, W, device=l.device, dtype=torch.uint8)
+        self._check(self.lib.dvc_l_to_guide8(self.h, _ptr(l), H, W, ctypes.c_void_p(out.data_ptr()), _stream(l.device)), "dvc_l_to_guide8")
+        return out
+
+    def centerpad_rgb8(self, rgb, size):
+        """CenterPad(size) + CenterCrop(size) of test.py:44-46 for a CUDA uint8 [H,W,3] image -> uint8 [size[0],size[1],3]."""
+        from dvc.prepost import centerpad_geometry
+
+        if not (isinstance(rgb, torch.Tensor) and rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.dim() == 3 and rgb.shape[2] == 3):
+            raise DvcError("centerpad_rgb8: expected a CUDA uint8 tensor [H,W,3]")
+        rgb = rgb.contiguous()
+        Hs, Ws, _ = rgb.shape
+        Hr, Wr, oy, ox = centerpad_geometry(Hs, Ws, size)
+        out = torch.empty(size[0], size[1], 3, device=rgb.device, dtype=torch.uint8)
+        self._check(self.lib.dvc_resize_antialias_crop_rgb8(self.h, ctypes.c_void_p(rgb.data_ptr()), Hs, Ws, Hr, Wr, oy, ox,
+                                                            ctypes.c_void_p(out.data_ptr()), size[0], size[1], _stream(rgb.device)),
+                    "dvc_resize_antialias_crop_rgb8")
         return out
 
     # ---- query-row-sharded correlation: peer-mapped result buffers (CUDA IPC) ----------------------------

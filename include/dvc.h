@@ -144,6 +144,25 @@ int dvc_lab_to_rgb8(dvc_ctx* ctx, const float* dev_l, const float* dev_ab, int B
  * 0.008856 cube-root threshold), cast to float32, then L - 50.  dev_rgb [B,H,W,3] uint8 -> dev_lab [B,3,H,W]. */
 int dvc_rgb8_to_lab(dvc_ctx* ctx, const unsigned char* dev_rgb, int B, int H, int W, float* dev_lab, void* stream);
 
+/* The "WLS filter" of test.py:105-112: cv2.ximgproc.createFastGlobalSmootherFilter(guide, lambda, sigma_color,
+ * lambda_attenuation = 0.25, num_iter = 3).filter(plane) for `planes` fp32 planes [planes,H,W] sharing one single-channel uint8
+ * guide [H,W] (Min et al., Fast Global Image Smoothing Based on Weighted Least Squares, TIP 2014: per iteration a horizontal
+ * and a vertical sweep of tridiagonal solves (I + lambda_n L) u = f, weights exp(-|dg| / sigma_color), lambda_{n+1} =
+ * lambda_n * lambda_attenuation).  dev_dst may equal dev_src.  test.py uses lambda = 500, sigma_color = 4. */
+int dvc_fgs_filter(dvc_ctx* ctx, const unsigned char* dev_guide, const float* dev_src, int planes, int H, int W, float lambda,
+                   float sigma_color, float lambda_attenuation, int num_iter, float* dev_dst, void* stream);
+/* The guide of test.py:106: uint8(uncenter_l(L) * 255 / 100) from the centred luminance plane dev_l [H,W]. */
+int dvc_l_to_guide8(dvc_ctx* ctx, const float* dev_l, int H, int W, unsigned char* dev_guide, void* stream);
+
+/* The resize inside CenterPad (utils/util_distortion.py:217-258) and the crop / pad around it:
+ * skimage.transform.resize(I, (Hr, Wr), mode="reflect", preserve_range=True, clip=False, anti_aliasing=True) of the uint8
+ * image dev_src [Hs,Ws,3] -- float64 Gaussian pre-filter with sigma = max(0, (in/out - 1)/2) per axis (scipy.ndimage
+ * gaussian_filter, mode "mirror", truncate 4) then bilinear scipy.ndimage.zoom(order=1, mode="mirror", grid_mode=True) --
+ * truncated to uint8; dev_dst [Ho,Wo,3] receives resized[y + oy, x + ox] where that exists and 0 elsewhere (CenterPad's
+ * centred crop and torchvision CenterCrop's zero pad; the geometry is computed by the caller, dvc/prepost.py). */
+int dvc_resize_antialias_crop_rgb8(dvc_ctx* ctx, const unsigned char* dev_src, int Hs, int Ws, int Hr, int Wr, int oy, int ox,
+                                   unsigned char* dev_dst, int Ho, int Wo, void* stream);
+
 /* ---- multi-GPU: exemplar operands travel once per clip ----------------------- */
 
 /* ---- single-frame scaling: query-row-sharded correlation with a fused all-gather (BASELINE config 4) --

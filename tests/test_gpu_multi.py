@@ -27,7 +27,11 @@ def _worker(rank, world, port, N, NB, T, out_dir):
     full_y, full_sim = ctx.corr_softmax_warp(th, ph, V, T)
     sharded = RowShardedCorrelation(ctx, N)
     y, sim = sharded(th, ph, V, T)
-    ok = bool(torch.equal(y, full_y) and torch.equal(sim, full_sim))
+    y_again, sim_again = sharded(th, ph, V, T)  # second call: the other result set of the double buffer
+    if T < 1e-9:  # one-hot rows: bit for bit
+        ok = bool(torch.equal(y, full_y) and torch.equal(sim, full_sim) and torch.equal(y_again, y))
+    else:  # softmax: a shard may pick another column-split count = another fp32 summation order of the same terms
+        ok = bool((y - full_y).abs().max() < 1e-4 and torch.equal(sim, full_sim) and torch.equal(y_again, y))
     sharded.close()
     open(os.path.join(out_dir, f"rank{rank}.txt"), "w").write("ok" if ok else "mismatch")
     dist.barrier()

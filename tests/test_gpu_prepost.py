@@ -1,5 +1,6 @@
 """GPU: pre / post-processing kernels around the nets against the CPU oracle
 (the reference does these with torch.nn.functional.interpolate at test.py:58,71,100-102)."""
+import numpy as np
 import pytest
 import torch
 
@@ -85,3 +86,40 @@ def test_colour_round_trip_on_device(ctx):
     lab = ctx.rgb8_to_lab(rgb.cuda())
     back = ctx.lab_to_rgb8(lab[:, 0:1].contiguous(), lab[:, 1:3].contiguous()).cpu()
     assert int((back.int() - rgb.int()).abs().max()) <= 1
+
+
+# ------------------------------------------------------------------------------------------ §8f rows 2-3
+def test_fgs_filter_vs_oracle(ctx):
+    """test.py:105-112 at the reference's own "large" size (432 x 768), lambda = 500, sigma_color = 4: every fp32 operation
+    of the kernel is the oracle's, so the two agree bit for bit (oracle/prepost_oracle.py; parity with OpenCV unpinned)."""
+    from oracle import prepost_oracle as P
+
+    rng = np.random.default_rng(3)
+    for H, W in ((432, 768), (37, 50)):
+        l = make_lab(90 + H, 1, H, W)[0, 0].numpy()
+        guide = P.l_to_guide8(l)
+        g_dev = ctx.l_to_guide8(torch.from_numpy(l).cuda())
+        assert np.array_equal(g_dev.cpu().numpy(), guide)
+        src = (rng.standard_normal((2, H, W)) * 30).astype(np.float32)
+        out = ctx.fgs_filter(g_dev, torch.from_numpy(src).cuda()).cpu().numpy()
+        ref = P.fgs_filter(guide, src, 500.0, 4.0)
+        assert np.isfinite(out).all()
+        assert np.abs(out - ref).max() <= 1e-6 * np.abs(ref).max(), np.abs(out - ref).max()
+        assert abs(out.sum() - src.sum()) < 1e-3 * np.abs(src).sum()
+
+
+@pytest.mark.parametrize("hs,ws,size", [(540, 960, (432, 768)), (480, 640, (432, 768)), (300, 900, (216, 384)), (216, 384, (216, 384)),
+                                        (100, 120, (216, 384))])
+def test_centerpad_resize_vs_scipy(ctx, hs, ws, size):
+    """CenterPad + CenterCrop (test.py:44-46) on the device vs the scipy.ndimage arithmetic skimage.transform.resize uses."""
+    from oracle import prepost_oracle as P
+
+    rng = np.random.default_rng(hs + ws)
+    img = (rng.random((hs // 4 + 1, ws // 4 + 1, 3)) * 255).astype(np.uint8)
+    img = np.kron(img, np.ones((4, 4, 1), np.uint8))[:hs, :ws]  # blocky content + noise: edges and flats
+    img = np.clip(img.astype(np.int32) + rng.integers(-9, 10, img.shape), 0, 255).astype(np.uint8)
+    ref = P.centerpad_transform(img, size, P.skimage_resize)
+    out = ctx.centerpad_rgb8(torch.from_numpy(img).cuda(), size).cpu().numpy()
+    diff = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    # float64 on both sides, same operation order; a value within 1e-13 of an integer could still truncate differently
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-5, (diff.max(), (diff > 0).mean())
