@@ -1,0 +1,28 @@
+#!/bin/bash
+# One GPU-box session: every step under its own timeout, every log under gpurun_out/ (merged back by gpurun).
+# Usage (on the GPU box): bash tools/gpu_session.sh <tag> [steps...]   steps: test bench probe diag cfg5 launches ncu
+TAG=${1:-s}; shift
+STEPS=${@:-test bench probe diag cfg5 launches}
+O=gpurun_out; mkdir -p $O
+for S in $STEPS; do
+  T0=$(date +%s)
+  case $S in
+    test)     timeout 1500 python -m pytest tests -m gpu -q --maxfail=40 -s -p no:cacheprovider > $O/${TAG}_test.log 2>&1 ;;
+    testfast) timeout 900 python -m pytest tests -m gpu -q --maxfail=40 -s -p no:cacheprovider -k "not test_layer and not 25920 and not fused_frame_vs_golden and not colorvidnet_module and not warpnet_module" > $O/${TAG}_testfast.log 2>&1 ;;
+    bench)    timeout 600 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err ;;
+    probe)    timeout 120 tools/probes/umma_rowshift_probe > $O/${TAG}_probe.log 2>&1 ;;
+    diag)     timeout 300 python tools/diag_corr_candidates.py > $O/${TAG}_diag.log 2>&1 ;;
+    cfg5)     timeout 600 python tools/config5_corr_microbench.py --out $O/config5_r2.jsonl > $O/${TAG}_cfg5.log 2>&1 ;;
+    cfg4)     timeout 600 bash tools/run_config4.sh > $O/${TAG}_cfg4.log 2>&1 ;;
+    extra)    timeout 600 python tools/extra_configs.py > $O/${TAG}_extra.log 2>&1 ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $O/${TAG}_launches.csv \
+                python bench.py --steps 4 --warmup 3 --cpu-sample 0 --sustain-s 0 --clip-frames 0 > $O/${TAG}_launches.out 2>&1 ;;
+    ncu)      timeout 1200 bash tools/ncu_captures.sh $TAG > $O/${TAG}_ncu.log 2>&1 ;;
+    multi)    timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -s -p no:cacheprovider > $O/${TAG}_multi.log 2>&1 ;;
+    *) echo "unknown step $S" ;;
+  esac
+  echo "step $S rc=$? $(( $(date +%s) - T0 ))s" >> $O/${TAG}_steps.log
+done
+tail -n 12 $O/${TAG}_steps.log
+for f in $O/${TAG}_test.log $O/${TAG}_testfast.log; do [ -f $f ] && tail -n 6 $f; done
+exit 0
