@@ -214,6 +214,8 @@ def main():
                     help="K bytes per pipeline stage of the conv engine (64 = twice the stages, measured slower)")
     ap.add_argument("--tc-f16", type=int, default=int(os.environ.get("DVC_TC_F16", "1")),
                     help="1: convolutions with bounded inputs run 3xFP16 on scaled planes; 0: 3xTF32 everywhere")
+    ap.add_argument("--corr-screen", type=int, default=int(os.environ.get("DVC_CORR_SCREEN", "1")), choices=[0, 1],
+                    help="1 = T->0 correlation as one fp16 screening pass + exact fp32 re-scoring of the candidates; 0 = exact 3-pass kernel")
     ap.add_argument("--corr-cluster", type=int, default=int(os.environ.get("DVC_CORR_CLUSTER", "2")), choices=[1, 2],
                     help="2 = CTA pairs (tcgen05.mma.cta_group::2) in the correlation kernel, 1 = single CTAs")
     ap.add_argument("--tc-tail", type=int, default=int(os.environ.get("DVC_TC_TAIL", "0")),
@@ -259,6 +261,7 @@ def main():
     ctx.debug_flag("tc_f16", args.tc_f16)
     ctx.debug_flag("tc_tail", args.tc_tail)
     ctx.debug_flag("corr_cluster", args.corr_cluster)
+    ctx.debug_flag("corr_screen", args.corr_screen)
 
     K, Wm = args.steps, args.warmup
     # every rank owns its own contiguous segment of synthetic frames (distinct content per rank and per step)
@@ -453,11 +456,17 @@ def main():
                              "counted, so frac is bounded by 1/3 (3xFP16) or 1/6 (3xTF32) of the dense 16-bit peak" % KP,
                      "other_variants": conv_detail},
         # the north-star kernel (BASELINE metric: correlation tensor-pipe fraction)
-        "roofline_corr": {"kernel": f"corr_tc_kernel ({args.corr_math}) incl. operand split + merge", "bound": "tensor",
+        "roofline_corr": {"kernel": (f"corr_screen_kernel + corr_rescore_kernel ({args.corr_math}, T<=2e-10: one fp16 pass locates every row's "
+                                     "candidates within a rigorous error bound, exact fp32 re-scoring) incl. operand preparation"
+                                     if (args.corr_screen and args.corr_math == "fp16x3") else
+                                     f"corr_tc_kernel ({args.corr_math}) incl. operand split + merge"),
+                          "bound": "tensor", "mma_passes": 1 if (args.corr_screen and args.corr_math == "fp16x3") else 3,
                           "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                           "traffic": ncu_traffic("corr_tc_kernel"), "peak_source": peak_src, "launch_ms": corr_ms,
-                          "note": "algorithmic 2*N*N*(256+3) FLOP per launch; 3 MMA passes per product are not counted, so the ceiling is "
-                                  "1/3 (fp16x3 / bf16x3) or 1/6 (tf32x3) of the dense 16-bit peak"},
+                          "note": "algorithmic 2*N*N*(256+3) FLOP per launch (the reference's matmul + softmax + matmul) over the CUDA-event "
+                                  "time of the whole launch sequence; the exact kernel spends 3 MMA passes per product (ceiling 1/3 of the "
+                                  "dense 16-bit peak, 1/6 for tf32x3), the screened T->0 path one pass (ceiling 1; the shared-memory port "
+                                  "allows ~128 B/clk = one pass at full rate)"},
         "serial_ms_per_frame": ms_serial,
         "rank_checksum": {"ok": rank_check_ok, "ranks": world,
                           "what": "bit pattern of ab for one common seeded frame, all_gather'ed and compared across ranks"},

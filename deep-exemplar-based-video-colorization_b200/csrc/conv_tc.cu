@@ -54,6 +54,28 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + 8 * BN * 4;  // + barriers + statistics [4][2][BN]
 };
 
+// Row-shared taps (RS): the three horizontal taps of a 3x3 row (two of a 2x2 phase-convolution row) read pixel rows
+// that differ by `dil` positions of the flat padded index, i.e. the SAME shared-memory tile shifted by dil rows.  One
+// activation tile of AR = 136 rows (>= 128 + 2 * dil) is loaded per (tap row, k-block) and the tcgen05 descriptors of the
+// taps start dil * 128 bytes apart: a third of the activation bytes through TMA and L2 (the weights still arrive per tap,
+// in a ring of their own).  What this buys: the shared-memory port -- 3 MMA passes re-read both operands -- is what
+// bounds the 128- and 64-channel tiles; per k-step a CTA of a pair writes 8 KB of activations + BN/2 * 64 B of weights by
+// TMA and reads 12 KB + 3 * BN/2 * 64 B by MMA in 3 * BN/2 tensor cycles (BN = 128: 156 B/clk against a 128 B/clk port);
+// with shared rows the activation writes drop to 2.8 KB (129 B/clk), BN = 256 goes from 104 to 90.
+template <int BN, int CL>
+struct CfgRS {
+  static constexpr int AR = 136;
+  static constexpr int A_TILE = AR * 128;              // one plane: 17 KB (a multiple of the 1024-byte swizzle atom)
+  static constexpr int A_STAGE = 2 * A_TILE;           // hi + lo
+  static constexpr int B_TILE = (BN / CL) * 128;
+  static constexpr int B_STAGE = 2 * B_TILE;
+  static constexpr int A_STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int B_STAGES = (BN == 256) ? (CL == 2 ? 4 : 2) : (BN == 128 ? (CL == 2 ? 6 : 3) : (CL == 2 ? 9 : 6));
+  static constexpr int RING_BYTES = A_STAGES * A_STAGE + B_STAGES * B_STAGE;
+  static constexpr int NBUF = 512 / BN;
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 512 + 8 * BN * 4;
+};
+
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -69,25 +91,29 @@ __device__ __forceinline__ float tf32_rna(float x) {
 // F16: operands are fp16 hi/lo planes of x * 2^e (e static per tensor / layer, chosen from a proven bound so that
 // nothing overflows): the same 2 x 11 significant bits as the tf32 split at twice the MMA rate, half the operand
 // bytes and half as many truncating accumulations per unit of K; the epilogue multiplies by 2^-(e_x + e_w) (exact).
-template <int BN, int CL, int KBY, bool F16>
+template <int BN, int CL, int KBY, bool F16, bool RS = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                    const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const ConvTcParams p) {
   using C = Cfg<BN, KBY, CL>;
+  using R = CfgRS<BN, CL>;
+  static_assert(!RS || KBY == 128, "row-shared taps use 128-byte K blocks");
   constexpr int A_BYTES = C::A_BYTES;
+  constexpr int RING = RS ? R::RING_BYTES : C::STAGES * C::STAGE_BYTES;
+  constexpr int NFULL = RS ? (R::A_STAGES + R::B_STAGES) : C::STAGES;  // "full" barriers (then as many "empty" ones)
   constexpr int KE = F16 ? KBY / 2 : KBY / 4;  // K elements per stage
   constexpr uint32_t IDESC = tc::umma_idesc(F16 ? 0u : 2u, BM * CL, BN);
   constexpr int CPT = BN / 2;  // output channels per epilogue thread (two warps share a TMEM lane quarter)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + C::STAGES;
-  uint64_t* tfull = bars + 2 * C::STAGES;                  // [NBUF]
-  uint64_t* tempty = bars + 2 * C::STAGES + C::NBUF;       // [NBUF]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 2 * C::NBUF);
-  float* s_stat = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 512);  // [4 lane quarters][2][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING);
+  uint64_t* full = bars;          // RS: [A_STAGES] activation tiles, then [B_STAGES] weight tiles
+  uint64_t* empty = bars + NFULL;
+  uint64_t* tfull = bars + 2 * NFULL;                  // [NBUF]
+  uint64_t* tempty = bars + 2 * NFULL + C::NBUF;       // [NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NFULL + 2 * C::NBUF);
+  float* s_stat = reinterpret_cast<float*>(smem + RING + 512);  // [4 lane quarters][2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.mtn ? p.mtn : (p.Mtot + BM - 1) / BM;
@@ -116,7 +142,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc::tma_prefetch_desc(&tmXl);
     tc::tma_prefetch_desc(&tmWh);
     tc::tma_prefetch_desc(&tmWl);
-    for (int i = 0; i < C::STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
+    for (int i = 0; i < NFULL; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
     for (int i = 0; i < C::NBUF; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 8 * CL);  // pair: both epilogues
     tc::fence_barrier_init();
   }
@@ -143,7 +169,57 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     // ================= TMA producer =================
     // The whole warp runs the loop convergently (so that addresses / coordinates are provably warp-uniform and live
     // in uniform registers); one elected lane issues the instructions.
-    {
+    if constexpr (RS) {
+      // k runs over (tap row ty, k-block kb, tap column tx) with tx fastest: the activation tile of (ty, kb) serves
+      // its ntx taps; weights come per tap.  (No split-K in this mode: p.splits == 1.)
+      const int ntx = p.rs_ntx, ngroups = nk / ntx;
+      uint8_t* ringB = smem + R::A_STAGES * R::A_STAGE;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int work = item0; work < total_work; work += item_stride) {
+        const int mg = work / n_tiles, nt = work - mg * n_tiles;
+        const int m0 = (p.mt0 + mg * CL + crank) * BM, n0 = nt * BN;
+        for (int g = 0; g < ngroups; ++g) {
+          const int ty = g / kbs, kb = g - ty * kbs;
+          tc::mbar_wait(&empty[as], aph ^ 1);
+          if (tc::elect_one()) {
+            uint8_t* st = smem + as * R::A_STAGE;
+            const int row = m0 + p.tap_off[ty * ntx];
+            if (CL == 1) {
+              tc::mbar_arrive_expect_tx(&full[as], R::A_STAGE);
+              tc::tma_load_2d(st, &tmXh, &full[as], kb * KE, row);
+              tc::tma_load_2d(st + R::A_TILE, &tmXl, &full[as], kb * KE, row);
+            } else {
+              if (crank == 0) tc::mbar_arrive_expect_tx(&full[as], 2 * R::A_STAGE);
+              tc::tma_load_2d_pair(st, &tmXh, &full[as], kb * KE, row);
+              tc::tma_load_2d_pair(st + R::A_TILE, &tmXl, &full[as], kb * KE, row);
+            }
+          }
+          __syncwarp();
+          if (++as == R::A_STAGES) as = 0, aph ^= 1;
+          for (int tx = 0; tx < ntx; ++tx) {
+            const int tap = ty * ntx + tx;
+            uint64_t* fb = &full[R::A_STAGES + bs];
+            tc::mbar_wait(&empty[R::A_STAGES + bs], bph ^ 1);
+            if (tc::elect_one()) {
+              uint8_t* st = ringB + bs * R::B_STAGE;
+              if (CL == 1) {
+                tc::mbar_arrive_expect_tx(fb, R::B_STAGE);
+                tc::tma_load_2d(st, &tmWh, fb, kb * KE, tap * p.CoutPad + n0);
+                tc::tma_load_2d(st + R::B_TILE, &tmWl, fb, kb * KE, tap * p.CoutPad + n0);
+              } else {
+                if (crank == 0) tc::mbar_arrive_expect_tx(fb, 2 * R::B_STAGE);
+                const int hrow = crank * (BN / 2);
+                tc::tma_load_2d_pair(st, &tmWh, fb, kb * KE, tap * p.CoutPad + n0 + hrow);
+                tc::tma_load_2d_pair(st + R::B_TILE, &tmWl, fb, kb * KE, tap * p.CoutPad + n0 + hrow);
+              }
+            }
+            __syncwarp();
+            if (++bs == R::B_STAGES) bs = 0, bph ^= 1;
+          }
+        }
+      }
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       for (int work = item0; work < total_work; work += item_stride) {
@@ -179,7 +255,67 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
   } else if (warp == 1 && (CL == 1 || crank == 0)) {
     // ================= MMA issuer (warp-convergent loop, one elected lane issues; pair: the leader CTA only) ====
-    {
+    if constexpr (RS) {
+      const int ntx = p.rs_ntx;
+      const uint32_t ringB = tc::smem_u32(smem + R::A_STAGES * R::A_STAGE);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0, chunk_id = 0;
+      for (int work = item0; work < total_work; work += item_stride) {
+        for (int ch = 0; ch < nchunks; ++ch, ++chunk_id) {
+          const int buf = chunk_id % C::NBUF;
+          tc::mbar_wait(&tempty[buf], ((chunk_id / C::NBUF) & 1) ^ 1);
+          tc::tc_fence_after();
+          const uint32_t d = tmem_base + buf * BN;
+          const int k_end = min((ch + 1) * kc, nk);
+          for (int k = ch * kc; k < k_end; ++k) {
+            const int g = k / ntx, tx = k - g * ntx, ty = g / kbs;
+            if (tx == 0) tc::mbar_wait(&full[as], aph);  // the activation tile of this (tap row, k-block)
+            tc::mbar_wait(&full[R::A_STAGES + bs], bph);
+            tc::tc_fence_after();
+            // the tap's rows start (tap_off[tap] - tap_off[first tap of the row]) rows into the shared tile
+            const int shift = p.tap_off[ty * ntx + tx] - p.tap_off[ty * ntx];
+            const uint32_t sa = tc::smem_u32(smem + as * R::A_STAGE) + (uint32_t)shift * 128u;
+            const uint32_t sb = ringB + bs * R::B_STAGE;
+            const uint64_t bo = p.rs_base_offset ? ((uint64_t)(shift & 7) << 49) : 0ull;
+            const uint64_t dXh = tc::umma_desc_k128(sa) | bo, dXl = tc::umma_desc_k128(sa + R::A_TILE) | bo;
+            const uint64_t dWh = tc::umma_desc_k128(sb), dWl = tc::umma_desc_k128(sb + R::B_TILE);
+            if (tc::elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                if (CL == 1) {
+                  tc::umma_ss<!F16>(d, dXl + adv, dWh + adv, IDESC, (k > ch * kc || kk) ? 1u : 0u);
+                  tc::umma_ss<!F16>(d, dXh + adv, dWl + adv, IDESC, 1u);
+                } else {
+                  tc::umma_ss_pair<!F16>(d, dXl + adv, dWh + adv, IDESC, (k > ch * kc || kk) ? 1u : 0u);
+                  tc::umma_ss_pair<!F16>(d, dXh + adv, dWl + adv, IDESC, 1u);
+                }
+              }
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                if (CL == 1)
+                  tc::umma_ss<!F16>(d, dXh + adv, dWh + adv, IDESC, 1u);
+                else
+                  tc::umma_ss_pair<!F16>(d, dXh + adv, dWh + adv, IDESC, 1u);
+              }
+              if (CL == 1) {
+                tc::umma_commit(&empty[R::A_STAGES + bs]);
+                if (tx == ntx - 1) tc::umma_commit(&empty[as]);
+                if (k == k_end - 1) tc::umma_commit(&tfull[buf]);
+              } else {
+                tc::umma_commit_pair_mc(&empty[R::A_STAGES + bs], 3);
+                if (tx == ntx - 1) tc::umma_commit_pair_mc(&empty[as], 3);
+                if (k == k_end - 1) tc::umma_commit_pair_mc(&tfull[buf], 3);
+              }
+            }
+            __syncwarp();
+            if (++bs == R::B_STAGES) bs = 0, bph ^= 1;
+            if (tx == ntx - 1 && ++as == R::A_STAGES) as = 0, aph ^= 1;
+          }
+        }
+      }
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk_id = 0;  // global chunk counter: TMEM buffer = chunk_id % NBUF
@@ -509,13 +645,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   }
 }
 
-template <int BN, int CL, int KBY, bool F16>
+template <int BN, int CL, int KBY, bool F16, bool RS = false>
 int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap& mWh, const CUtensorMap& mWl,
               const ConvTcParams& p, int num_sms, cudaStream_t s) {
+  constexpr int SMEM = RS ? CfgRS<BN, CL>::SMEM_BYTES : Cfg<BN, KBY, CL>::SMEM_BYTES;
   static unsigned long long attr_mask = 0;  // the attribute is per device
   if (first_use_on_device(&attr_mask)) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<BN, CL, KBY, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, KBY, CL>::SMEM_BYTES) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc_kernel<BN, CL, KBY, F16, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
       return -1;
   }
   const int m_tiles = p.mtn ? p.mtn : (p.Mtot + BM - 1) / BM;
@@ -523,12 +659,12 @@ int launch_bn(const CUtensorMap& mXh, const CUtensorMap& mXl, const CUtensorMap&
   const int max_groups = num_sms / CL;
   const int grid = CL * (items < max_groups ? items : max_groups);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<BN, KBY, CL>::SMEM_BYTES, cfg.stream = s;
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = SMEM, cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
   cfg.attrs = at, cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, KBY, F16>, mXh, mXl, mWh, mWl, p) == cudaSuccess ? 0 : -2;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CL, KBY, F16, RS>, mXh, mXl, mWh, mWl, p) == cudaSuccess ? 0 : -2;
 }
 
 }  // namespace
@@ -598,18 +734,32 @@ int launch_conv_tc(const ConvTcParams& p, const void* x_hi, const void* x_lo, co
     }
     q.splits = best;
   }
+  // row-shared taps: taps of one kernel row read the same activation tile shifted by a few rows (see CfgRS)
+  bool rs = false;
+  if (p.rowshare && KBY == 128 && q.splits == 1 && (p.taps == 9 || p.taps == 4)) {
+    const int ntx = p.taps == 9 ? 3 : 2;
+    rs = true;
+    for (int t = 0; t < p.taps; ++t) {
+      const int sh = p.tap_off[t] - p.tap_off[(t / ntx) * ntx];
+      if (sh < 0 || sh > CfgRS<64, 1>::AR - BM) rs = false;
+    }
+    q.rs_ntx = ntx, q.rs_base_offset = p.rowshare == 2 ? 1 : 0;
+  }
   CUtensorMap mXh, mXl, mWh, mWl;
-  if (encode_tmap_2d(&mXh, x_hi, (uint64_t)p.Mtot, p.Cin, BM, KBY / eb, eb, KBY) ||
-      encode_tmap_2d(&mXl, x_lo, (uint64_t)p.Mtot, p.Cin, BM, KBY / eb, eb, KBY) ||
+  const int abox = rs ? CfgRS<64, 1>::AR : BM;
+  if (encode_tmap_2d(&mXh, x_hi, (uint64_t)p.Mtot, p.Cin, abox, KBY / eb, eb, KBY) ||
+      encode_tmap_2d(&mXl, x_lo, (uint64_t)p.Mtot, p.Cin, abox, KBY / eb, eb, KBY) ||
       encode_tmap_2d(&mWh, w_hi, (uint64_t)p.taps * p.CoutPad, p.Cin, BN / CL, KBY / eb, eb, KBY) ||
       encode_tmap_2d(&mWl, w_lo, (uint64_t)p.taps * p.CoutPad, p.Cin, BN / CL, KBY / eb, eb, KBY))
     return fail("cuTensorMapEncodeTiled failed");
   int rc;
-#define DVC_LAUNCH(BNv, CLv)                                                              \
-  rc = f16 ? ((KBY == 128) ? launch_bn<BNv, CLv, 128, true>(mXh, mXl, mWh, mWl, q, num_sms, s)   \
-                           : launch_bn<BNv, CLv, 64, true>(mXh, mXl, mWh, mWl, q, num_sms, s))   \
-           : ((KBY == 128) ? launch_bn<BNv, CLv, 128, false>(mXh, mXl, mWh, mWl, q, num_sms, s)  \
-                           : launch_bn<BNv, CLv, 64, false>(mXh, mXl, mWh, mWl, q, num_sms, s))
+#define DVC_LAUNCH(BNv, CLv)                                                                        \
+  rc = rs ? (f16 ? launch_bn<BNv, CLv, 128, true, true>(mXh, mXl, mWh, mWl, q, num_sms, s)            \
+                 : launch_bn<BNv, CLv, 128, false, true>(mXh, mXl, mWh, mWl, q, num_sms, s))          \
+          : (f16 ? ((KBY == 128) ? launch_bn<BNv, CLv, 128, true>(mXh, mXl, mWh, mWl, q, num_sms, s)  \
+                                 : launch_bn<BNv, CLv, 64, true>(mXh, mXl, mWh, mWl, q, num_sms, s))  \
+                 : ((KBY == 128) ? launch_bn<BNv, CLv, 128, false>(mXh, mXl, mWh, mWl, q, num_sms, s) \
+                                 : launch_bn<BNv, CLv, 64, false>(mXh, mXl, mWh, mWl, q, num_sms, s)))
   if (CL == 2) {
     if (BN == 256) { DVC_LAUNCH(256, 2); } else if (BN == 128) { DVC_LAUNCH(128, 2); } else { DVC_LAUNCH(64, 2); }
   } else {

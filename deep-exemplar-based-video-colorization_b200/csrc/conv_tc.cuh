@@ -43,6 +43,9 @@ struct ConvTcParams {
   int kbytes;     // bytes of K per pipeline stage: 64 (SWIZZLE_64B, twice the stages) or 128 (SWIZZLE_128B)
   int cluster;    // 2: run as 2-CTA clusters with TMA-multicast weight tiles; 1: single CTAs
   int kc;         // k-blocks (32 input channels each) summed in TMEM before promotion to fp32 registers
+  int rowshare;   // 1 / 2: the taps of one kernel row share one activation tile in shared memory (conv_tc.cu: CfgRS); 2 also
+                  // sets the descriptors' base-offset field to the row shift; 0: one activation tile per tap
+  int rs_ntx, rs_base_offset;  // filled by the launcher
 };
 
 int conv_tc_pick_bn(int cout);  // channel tile (64 / 128 / 256) used for `cout` output channels

@@ -131,6 +131,7 @@ struct dvc_ctx {
   int corr_screen = 1;    // T <= 2e-10, FP16X3: one screening pass + exact re-scoring of the candidates (0: exact 3-pass kernel)
   CorrWorkspace corr_ws;  // operand planes + split partials of the tensor-core correlation (pre-sized by dvc_set_exemplar)
   long long ex_version = 0;  // bumped whenever ex_phi's contents change (the correlation caches the exemplar's planes)
+  int tc_rowshare = 0;    // tensor-core convolutions: taps of a kernel row share one activation tile (conv_tc.cu: CfgRS)
   int tc_force_bn = 0;    // tests: channel tile (64 / 128 / 256) forced on every tensor-core convolution it divides
   int tc_tail = 0;        // tensor-core convolutions: 1 = 128-channel tiles for the partial last round of 256-channel
                           // launches (-1.3 % on one stream, +1.6 % in the two-stream clip pipeline: off by default)
@@ -583,6 +584,7 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     t.add = p.add, t.add_lo = o.add ? o.add->lo : nullptr, t.aHp = p.aHp, t.aWp = p.aWp, t.aP = p.aP, t.aC = p.aC;
     t.act = o.act, t.slope = o.slope, t.stats = o.stats, t.kc = c->tc_kc, t.cluster = c->tc_cluster, t.kbytes = c->tc_kbytes;
     t.tail = c->tc_tail;
+    t.rowshare = c->tc_rowshare;
     t.force_bn = (c->tc_force_bn && !o.fin_w && w->cout_pad_tc % c->tc_force_bn == 0) ? c->tc_force_bn : 0;
     t.splits = c->tc_splits, t.ws = nullptr, t.flags = nullptr, t.epoch = 0;
     if (c->tc_splits != 1 && (c->tc_splits > 1 || t.Mtot <= 128 * 8 * c->num_sms)) {  // split-K hand-over workspace + flags of this phase's arena (L2-resident, reused by every layer)
@@ -1130,6 +1132,7 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!strcmp(name, "tc_splits")) { c->tc_splits = value < 0 ? 0 : (value > 8 ? 8 : value); return DVC_OK; }
   if (!strcmp(name, "tc_kbytes")) { c->tc_kbytes = value == 64 ? 64 : 128; return DVC_OK; }
   if (!strcmp(name, "tc_cluster")) { c->tc_cluster = value == 2 ? 2 : 1; return DVC_OK; }
+  if (!strcmp(name, "tc_rowshare")) { c->tc_rowshare = value < 0 ? 0 : (value > 2 ? 2 : value); return DVC_OK; }
   if (!strcmp(name, "tc_force_bn")) {
     if (value != 0 && value != 64 && value != 128 && value != 256) return fail(c, DVC_ERR_ARG, "tc_force_bn must be 0, 64, 128 or 256");
     c->tc_force_bn = value;
