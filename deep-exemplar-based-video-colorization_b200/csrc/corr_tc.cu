@@ -499,16 +499,21 @@ __global__ void __launch_bounds__(Epi<SOFTMAX>::NTHREADS, 1)
 // column-range split) while it streams the tiles -- one third of the MMA work and half of the operand bytes of the
 // 3-pass kernel; corr_rescore_kernel then evaluates the candidates exactly in fp32 on the CUDA cores (a few per row) and
 // produces (sim, argmax, mean V of bit-equal maxima).  A list that overflows marks its (row, split) for brute force.
-constexpr int SCREEN_K = 16;
+constexpr int SCREEN_K = 12;        // candidates kept per (row, column-range split, column half)
+constexpr int SCREEN_EPI_WARPS = 8;  // two per TMEM lane quarter, each owning 128 of a tile's 256 columns
+constexpr int SCREEN_HALVES = SCREEN_EPI_WARPS / 4;
 
 template <int CL>
 struct ScreenCfg {
   static constexpr int STAGES = CL == 2 ? 6 : 4;
   static constexpr int A_BYTES = BM * 128, B_BYTES = (BN / CL) * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 49152 / 32768
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  // candidate lists of the epilogue threads: [SCREEN_K][epilogue threads] (value, column) -- slot k of thread t lives at
+  // [k][t], so dynamic slot indices never conflict on a bank and never touch local memory
+  static constexpr int LIST_BYTES = SCREEN_K * SCREEN_EPI_WARPS * 32 * 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + LIST_BYTES;
 };
-constexpr int SCREEN_THREADS = 192;
+constexpr int SCREEN_THREADS = 64 + 32 * SCREEN_EPI_WARPS;
 
 struct ScreenParams {
   int NA, NB, B, Bphi, C;
@@ -544,6 +549,8 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1)
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* s_cf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [SCREEN_K][epilogue threads] values
+  int* s_ci = reinterpret_cast<int*>(s_cf + SCREEN_K * SCREEN_EPI_WARPS * 32);  // ... and their columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -558,7 +565,7 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1)
     tc::tma_prefetch_desc(&tmAh);
     tc::tma_prefetch_desc(&tmBh);
     for (int i = 0; i < STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
-    for (int i = 0; i < 2; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 4 * CL);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], SCREEN_EPI_WARPS * CL);
     tc::fence_barrier_init();
   }
   if (CL == 2) tc::cluster_sync_all();
@@ -637,64 +644,66 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1)
       }
     }
   } else {
-    // ================= epilogue: one query row per thread =================
-    const int q = warp & 3;
+    // ================= epilogue: one query row x one column half per thread =================
+    // Per 32-column chunk the common path is one tcgen05.ld and 16 three-input maxima.  A chunk whose maximum comes within
+    // the threshold of the row's running maximum (a "record" or a near-tie: ~ln(#chunks) times per row, but for SOME lane
+    // of a warp in about every second chunk) appends its qualifying columns to the thread's list with 32 predicated
+    // shared-memory stores -- no local memory, no data-dependent loop.
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    constexpr int COLS = BN / SCREEN_HALVES;
+    constexpr int LT = SCREEN_EPI_WARPS * 32;  // list stride
+    const int et = threadIdx.x - 64;           // epilogue thread index
     const int row = m0 + q * 32 + lane;
     const size_t grow = (size_t)b * p.NA + min(row, p.NA - 1);
     // candidate threshold in TMEM units (scores there are true scores * 2^28)
     const float thr = screen_threshold(__ldg(p.nd_a + grow), __ldg(p.nh_a + grow), __uint_as_float(__ldg(p.nd_b_max)),
                                        __uint_as_float(__ldg(p.nh_b_max))) * 268435456.0f;
     float run_m = -INFINITY;
-    float cf[SCREEN_K];
-    int ci[SCREEN_K];
-    int cnt = 0;
+    int cnt = 0;  // entries appended (only the first SCREEN_K are stored: cnt > SCREEN_K = overflow)
     bool overflow = false;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       tc::mbar_wait(&tfull[buf], (t >> 1) & 1);
       tc::tc_fence_after();
-      const int colbase = (t0 + t) * BN;
+      const int colbase = (t0 + t) * BN + half * COLS;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < COLS / 32; ++c) {
         const int cb = colbase + c * 32;
         if (cb >= p.NB) break;
         uint32_t r[32];
         __syncwarp();
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + c * 32, r);
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * COLS + c * 32, r);
         tc::tmem_ld_wait();
         const int nvalid = min(32, p.NB - cb);
-        float cm = -INFINITY;
-        if (nvalid == 32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(r[i]));
-        } else {
+        if (nvalid < 32) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < nvalid) cm = fmaxf(cm, __uint_as_float(r[i]));
+            if (i >= nvalid) r[i] = __float_as_uint(-INFINITY);
         }
+        float cm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(r[i]));
         run_m = fmaxf(run_m, cm);
         const float lim = run_m - thr;
-        if (cm >= lim && !overflow) {  // this chunk holds candidates (rare once the running maximum has settled)
-          float tmp[32];  // indexed dynamically below: lives in local memory, written only on this rare path
+        if (cm >= lim) {
+          if (cnt > SCREEN_K / 2 && cnt <= SCREEN_K) {  // drop the entries the risen maximum has disqualified
+            int k = 0;
+            for (int j = 0; j < cnt; ++j) {
+              const float v = s_cf[j * LT + et];
+              const int ci = s_ci[j * LT + et];
+              if (v >= lim) s_cf[k * LT + et] = v, s_ci[k * LT + et] = ci, ++k;
+            }
+            cnt = k;
+          }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) tmp[i] = __uint_as_float(r[i]);
-#pragma unroll 1
-          for (int i = 0; i < nvalid; ++i) {
-            const float v = tmp[i];
+          for (int i = 0; i < 32; ++i) {
+            const float v = __uint_as_float(r[i]);
             if (v >= lim) {
-              if (cnt == SCREEN_K) {  // drop the entries the risen maximum has disqualified
-                int k = 0;
-                for (int j = 0; j < SCREEN_K; ++j)
-                  if (cf[j] >= lim) cf[k] = cf[j], ci[k] = ci[j], ++k;
-                cnt = k;
-              }
-              if (cnt == SCREEN_K) {
-                overflow = true;
-                break;
-              }
-              cf[cnt] = v, ci[cnt] = cb + i, ++cnt;
+              if (cnt < SCREEN_K) s_cf[cnt * LT + et] = v, s_ci[cnt * LT + et] = cb + i;
+              ++cnt;
             }
           }
+          if (cnt > SCREEN_K) overflow = true, cnt = SCREEN_K + 1;
         }
       }
       tc::tc_fence_before();
@@ -707,13 +716,13 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1)
       }
     }
     if (row < p.NA) {
-      const size_t o = ((size_t)blockIdx.z * p.B + b) * p.NA + row;
+      const size_t o = ((size_t)(blockIdx.z * SCREEN_HALVES + half) * p.B + b) * p.NA + row;
       p.pm[o] = run_m * 3.725290298461914e-09f;
       int k = 0;
       if (!overflow) {
         const float lim = run_m - thr;
         for (int j = 0; j < cnt; ++j)
-          if (cf[j] >= lim) p.pidx[o * SCREEN_K + k++] = ci[j];
+          if (s_cf[j * LT + et] >= lim) p.pidx[o * SCREEN_K + k++] = s_ci[j * LT + et];
       }
       p.pcnt[o] = overflow ? -1 : k;
     }
@@ -779,9 +788,13 @@ __global__ void __launch_bounds__(256) corr_rescore_kernel(const float* __restri
     const int n = __ldg(p.pcnt + o);
     if (n >= 0) {
       for (int j = 0; j < n; ++j) visit(__ldg(p.pidx + o * SCREEN_K + j));
-    } else {  // overflowed list: every column of the part's range
-      const int c0 = s * p.tiles_per_split * BN, c1 = min(min((s + 1) * p.tiles_per_split, ntiles_all) * BN, p.NB);
-      for (int col = c0; col < c1; ++col) visit(col);
+    } else {  // overflowed list: every column of the part's range (part = column-range split x column half of each tile)
+      const int sp = s / SCREEN_HALVES, hf = s - sp * SCREEN_HALVES, hc = BN / SCREEN_HALVES;
+      const int tl0 = sp * p.tiles_per_split, tl1 = min((sp + 1) * p.tiles_per_split, ntiles_all);
+      for (int tl = tl0; tl < tl1; ++tl) {
+        const int c0 = tl * BN + hf * hc, c1 = min(c0 + hc, p.NB);
+        for (int col = c0; col < c1; ++col) visit(col);
+      }
     }
   }
   if (lane == 0) {
@@ -913,7 +926,7 @@ int corr_ws_reserve(CorrWorkspace* ws, int B, int Bphi, int NA, int NB) {
   const size_t ea = (size_t)B * NA * 256 * 4, ephi = (size_t)Bphi * NB * 256 * 4;  // tf32 words: the widest format
   const size_t part = (size_t)16 * 2 * B * NA * sizeof(SplitOut);                   // at most 16 column splits x 2 column halves
   if (ws_get(ws, 0, ea, &d) || ws_get(ws, 1, ea, &d) || ws_get(ws, 2, ephi, &d) || ws_get(ws, 3, ephi, &d) || ws_get(ws, 4, part, &d) ||
-      ws_get(ws, 5, screen_norm_bytes(B, Bphi, NA, NB), &d) || ws_get(ws, 6, screen_cand_bytes(16, B, NA), &d))
+      ws_get(ws, 5, screen_norm_bytes(B, Bphi, NA, NB), &d) || ws_get(ws, 6, screen_cand_bytes(16 * SCREEN_HALVES, B, NA), &d))
     return -1;
   return 0;
 }
@@ -982,7 +995,8 @@ int launch_corr_tc(const CorrParams& p, int math, int cluster, int screen, CorrW
     // ---- screened T -> 0 path: hi planes + error norms, one fp16 pass, exact re-scoring of the candidates ----
     const int rows = p.B * p.NA, rphi = p.Bphi * p.NB;
     void *norms, *cand;
-    if (ws_get(ws, 5, screen_norm_bytes(p.B, p.Bphi, p.NA, p.NB), &norms) || ws_get(ws, 6, screen_cand_bytes(nsplit, p.B, p.NA), &cand))
+    const int sparts = nsplit * SCREEN_HALVES;
+    if (ws_get(ws, 5, screen_norm_bytes(p.B, p.Bphi, p.NA, p.NB), &norms) || ws_get(ws, 6, screen_cand_bytes(sparts, p.B, p.NA), &cand))
       return fail("workspace allocation failed");
     float* nd_a = (float*)norms;
     float* nh_a = nd_a + rows;
@@ -1003,12 +1017,12 @@ int launch_corr_tc(const CorrParams& p, int math, int cluster, int screen, CorrW
     sp.NA = p.NA, sp.NB = p.NB, sp.B = p.B, sp.Bphi = p.Bphi, sp.C = p.C, sp.tiles_per_split = tps;
     sp.nd_a = nd_a, sp.nh_a = nh_a, sp.nd_b_max = cells + 2, sp.nh_b_max = cells + 3;
     sp.pm = (float*)cand;
-    sp.pcnt = (int*)(sp.pm + (size_t)nsplit * rows);
-    sp.pidx = sp.pcnt + (size_t)nsplit * rows;
+    sp.pcnt = (int*)(sp.pm + (size_t)sparts * rows);
+    sp.pidx = sp.pcnt + (size_t)sparts * rows;
     dim3 grid(row_blocks, p.B, nsplit);
     const int rc = cl == 2 ? launch_screen_cl<2>(mA, mB, sp, grid, s) : launch_screen_cl<1>(mA, mB, sp, grid, s);
     if (rc) return fail(rc == -1 ? "cudaFuncSetAttribute(max dynamic smem) failed" : "cudaLaunchKernelEx failed");
-    corr_rescore_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>(p.theta, p.phi, reinterpret_cast<const float4*>(p.V), sp, nsplit,
+    corr_rescore_kernel<<<(rows * 32 + 255) / 256, 256, 0, s>>>(p.theta, p.phi, reinterpret_cast<const float4*>(p.V), sp, sparts,
                                                                 reinterpret_cast<float4*>(p.y), p.sim, p.argmax, p.peers);
     launch_counter_add(2);
     return 0;

@@ -157,11 +157,14 @@ __global__ void __launch_bounds__(256) gauss_axis_kernel(const TIn* __restrict__
     const int pos = (int)(t % len);
     const size_t outer = t / len;
     const TIn* base = src + outer * (size_t)len * inner + in_i;
-    // scipy's correlate1d for symmetric weights: centre tap first, then the pairs (left + right) * w from the OUTSIDE in
-    double acc = (double)base[(size_t)pos * inner] * w[radius];
+    // scipy's correlate1d for symmetric weights: centre tap first, then the pairs (left + right) * w from the OUTSIDE in.
+    // Separately rounded multiplies and adds (no FMA contraction): with sigma = 0.125 (a 1.25x down-scale) the taps are
+    // (1.3e-14, 1, 1.3e-14), the filtered values sit within 1e-12 of integers and the final truncation to uint8 sees
+    // the last bit -- scipy's C code is compiled without FMA.
+    double acc = __dmul_rn((double)base[(size_t)pos * inner], w[radius]);
     for (int k = radius; k >= 1; --k) {
       const double l = (double)base[(size_t)mirror_idx(pos - k, len) * inner], r = (double)base[(size_t)mirror_idx(pos + k, len) * inner];
-      acc += (l + r) * w[radius + k];
+      acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(l, r), w[radius + k]));
     }
     dst[idx] = acc;
   }
@@ -181,20 +184,21 @@ __global__ void __launch_bounds__(256) zoom_crop_kernel(const double* __restrict
     unsigned char out = 0;
     if (yr >= 0 && yr < Hr && xr >= 0 && xr < Wr) {
       // grid_mode: pixel centres align, in = (out + 0.5) * (in_len / out_len) - 0.5
-      const double cy = ((double)yr + 0.5) * ((double)Hs / (double)Hr) - 0.5;
-      const double cx = ((double)xr + 0.5) * ((double)Ws / (double)Wr) - 0.5;
+      // (separately rounded operations throughout: see gauss_axis_kernel)
+      const double cy = __dsub_rn(__dmul_rn(__dadd_rn((double)yr, 0.5), __ddiv_rn((double)Hs, (double)Hr)), 0.5);
+      const double cx = __dsub_rn(__dmul_rn(__dadd_rn((double)xr, 0.5), __ddiv_rn((double)Ws, (double)Wr)), 0.5);
       const double fy = floor(cy), fx = floor(cx);
-      const double ty = cy - fy, tx = cx - fx;
+      const double ty = __dsub_rn(cy, fy), tx = __dsub_rn(cx, fx);
       const int y0 = mirror_idx((int)fy, Hs), y1 = mirror_idx((int)fy + 1, Hs);
       const int x0 = mirror_idx((int)fx, Ws), x1 = mirror_idx((int)fx + 1, Ws);
       const double v00 = src[((size_t)y0 * Ws + x0) * 3 + ch], v01 = src[((size_t)y0 * Ws + x1) * 3 + ch];
       const double v10 = src[((size_t)y1 * Ws + x0) * 3 + ch], v11 = src[((size_t)y1 * Ws + x1) * 3 + ch];
       // scipy (ni_interpolation.c) sums the 2 x 2 neighbourhood, row-major, each term ((value * wy) * wx)
-      const double wy0 = 1.0 - ty, wx0 = 1.0 - tx;
-      double v = (v00 * wy0) * wx0;
-      v += (v01 * wy0) * tx;
-      v += (v10 * ty) * wx0;
-      v += (v11 * ty) * tx;
+      const double wy0 = __dsub_rn(1.0, ty), wx0 = __dsub_rn(1.0, tx);
+      double v = __dmul_rn(__dmul_rn(v00, wy0), wx0);
+      v = __dadd_rn(v, __dmul_rn(__dmul_rn(v01, wy0), tx));
+      v = __dadd_rn(v, __dmul_rn(__dmul_rn(v10, ty), wx0));
+      v = __dadd_rn(v, __dmul_rn(__dmul_rn(v11, ty), tx));
       out = (unsigned char)fmin(fmax(trunc(v), 0.0), 255.0);
     }
     dst[idx] = out;

@@ -8,7 +8,8 @@ sizes) is compared with the oracle at small M, and then again at the bench's own
 of the persistent grid; 108 tiles of the 512-channel layers).
 
 Tolerances: max|y - y64| <= 4e-6 * max|y64| (fp32-class accumulation over K = 9 * Cin <= 4608 products: the
-reference's own fp32 F.conv2d is printed beside it); InstanceNorm sums: 2e-6 relative to the sum of |values|.
+reference's own fp32 F.conv2d is printed beside it); InstanceNorm sums (of the stored fp32 values, against fp64 sums of
+the fp64 values): 1e-5 relative to the sum of |values|.
 """
 import numpy as np
 import pytest
@@ -114,7 +115,7 @@ def run_layer(ctx, sds, net, name, cin, cout, H, W, B=1, seed=0, out_planes=Fals
         s64 = torch.stack((y64.sum((2, 3)), (y64 * y64).sum((2, 3))), -1)
         a64 = torch.stack((y64.abs().sum((2, 3)), (y64 * y64).sum((2, 3))), -1)
         serr = ((st - s64).abs() / a64.clamp_min(1e-30)).max().item()
-        assert serr < 2e-6, ("InstanceNorm sums", name, serr)
+        assert serr < 1e-5, ("InstanceNorm sums", name, serr)
     return err, floor
 
 
@@ -153,7 +154,8 @@ BENCH = [
     ("eighth_512_108tiles", VGG, "conv4_2", 512, 512, 60, 108, dict(act=1, nonneg=True), 256),
     ("eighth_512_dil2_stats", COLOR, "conv5_3", 512, 512, 60, 108, dict(act=1, dil=2, nonneg=True, want_stats=True), 256),
     ("half_128", VGG, "conv2_2", 128, 128, 240, 432, dict(act=1, nonneg=True), 128),
-    ("quarter_upconv_256", COLOR, "conv8_1.1", 512, 256, 60, 108, dict(act=1, upconv=True, with_add=True), 256),
+    # the four phases of conv8_1 each see 54 pixel tiles of the 1/8-resolution input: the launcher narrows to 128 channels
+    ("quarter_upconv_256", COLOR, "conv8_1.1", 512, 256, 60, 108, dict(act=1, upconv=True, with_add=True), 128),
 ]
 
 

@@ -156,7 +156,8 @@ def test_corr_duplicated_exemplar_columns_average(ctx, corr_math):
     assert (y[0, :40] - V[0, dup].double().mean(0)).abs().max() < 1e-4
     assert (y[0, 40:60] - V[0, [20, 21]].double().mean(0)).abs().max() < 1e-4
     assert (am.cpu()[0, :40] == 3).all() and (am.cpu()[0, 40:60] == 20).all()  # lowest index of the tie
-    tol = 8e-6 if corr_math == "bf16x3" else 2e-6
+    # the matched rows score ~1.0 (a query that IS an exemplar column): the operand splits' relative error shows in full
+    tol = {"bf16x3": 8e-6, "tf32x3": 4e-6}.get(corr_math, 2e-6)
     gap = O.top2_gap(th.double(), ph.double())[0]
     ok = (gap == 0) | (gap > 4 * tol)     # exact ties (averaged by the fp64 oracle too) or a clear winner
     assert (y[0][ok] - yo[0][ok]).abs().max() < 1e-3
@@ -180,7 +181,7 @@ def test_corr_many_near_ties_overflow_the_candidate_lists(ctx, corr_math):
     y, sim, am = ctx.corr_softmax_warp(th.cuda(), ph.cuda(), V.cuda(), 1e-10, want_argmax=True)
     f = th[0].double().t() @ ph[0].double()
     m64, i64 = f.max(1)
-    tol = 8e-6 if corr_math == "bf16x3" else 2e-6
+    tol = {"bf16x3": 8e-6, "tf32x3": 4e-6}.get(corr_math, 2e-6)  # scores ~1.0 here, see the duplicated-columns test
     assert (sim.cpu().double()[0] - m64).abs().max() < tol
     # every reported argmax attains the fp64 maximum up to the score tolerance (the near ties are legal alternatives)
     assert (f.gather(1, am.cpu()[0].long().view(-1, 1))[:, 0] - m64).abs().max() < 2 * tol
