@@ -222,6 +222,8 @@ def main():
                     help="1: partial last rounds of 256-channel conv launches run on 128-channel tiles; 0: off")
     ap.add_argument("--tc-splits", type=int, default=int(os.environ.get("DVC_TC_SPLITS", "1")),
                     help="split-K of the conv engine: 1 off (default), 0 automatic")
+    ap.add_argument("--tc-rowshare", type=int, default=int(os.environ.get("DVC_TC_ROWSHARE", "0")), choices=[0, 1],
+                    help="1: the taps of a 3x3 kernel row share one activation tile in shared memory (conv_tc.cu: CfgRS)")
     ap.add_argument("--tc-cluster", type=int, default=int(os.environ.get("DVC_TC_CLUSTER", "2")), choices=[1, 2],
                     help="2 = CTA pairs (tcgen05.mma.cta_group::2) in the conv engine, 1 = single CTAs")
     ap.add_argument("--cpu-sample", type=int, default=4, help="frames timed for cpu_baseline (0 = skip)")
@@ -260,6 +262,7 @@ def main():
     ctx.debug_flag("tc_splits", args.tc_splits)
     ctx.debug_flag("tc_f16", args.tc_f16)
     ctx.debug_flag("tc_tail", args.tc_tail)
+    ctx.debug_flag("tc_rowshare", args.tc_rowshare)
     ctx.debug_flag("corr_cluster", args.corr_cluster)
     ctx.debug_flag("corr_screen", args.corr_screen)
 

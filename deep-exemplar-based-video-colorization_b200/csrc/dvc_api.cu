@@ -130,6 +130,8 @@ struct dvc_ctx {
   int corr_cluster = 2;   // correlation: 2 = CTA pairs (tcgen05.mma.cta_group::2), 1 = single CTAs
   int corr_screen = 1;    // T <= 2e-10, FP16X3: one screening pass + exact re-scoring of the candidates (0: exact 3-pass kernel)
   CorrWorkspace corr_ws;  // operand planes + split partials of the tensor-core correlation (pre-sized by dvc_set_exemplar)
+  CorrWorkspace corr_ws2;  // the same for the second phase-A stream of the clip driver (clip_astreams = 2)
+  int clip_astreams = 1;   // clip driver: 1 = frame t+1's phase A overlaps frame t's ColorVidNet; 2 = frames t+1 AND t+2
   long long ex_version = 0;  // bumped whenever ex_phi's contents change (the correlation caches the exemplar's planes)
   int tc_rowshare = 0;    // tensor-core convolutions: taps of a kernel row share one activation tile (conv_tc.cu: CfgRS)
   int tc_force_bn = 0;    // tests: channel tile (64 / 128 / 256) forced on every tensor-core convolution it divides
@@ -145,10 +147,12 @@ struct dvc_ctx {
   double* stats = nullptr;
   size_t stats_cap = 0, stats_used = 0, stats_lo = 0, stats_hi = 0;
   int cur_arena = 0;          // 0: frame-independent phase, 1: ColorVidNet (may run concurrently on two streams)
-  int tc_epoch[2] = {0, 0};   // split-K hand-over epochs, one flag buffer per arena
+  int tc_epoch[3] = {0, 0, 0};   // split-K hand-over epochs, one flag buffer per arena
   int tc_splits = 1;          // split-K: 1 = off (default: measured no gain once two streams overlap), 0 = automatic, >1 = forced
   // clip driver: frame t+1's VGG/WarpNet/correlation overlaps frame t's ColorVidNet on two internal streams
   cudaStream_t sA = nullptr, sC = nullptr, sU = nullptr, sD = nullptr;  // phase A, phase C, uploads, downloads
+  cudaStream_t sA2 = nullptr;  // phase A of the odd frames when clip_astreams = 2
+  cudaEvent_t evJoinA2 = nullptr;
   cudaEvent_t evA[4] = {nullptr, nullptr, nullptr, nullptr}, evC[4] = {nullptr, nullptr, nullptr, nullptr}, evFork = nullptr,
               evJoinA = nullptr, evJoinC = nullptr, evJoinD = nullptr;
   cudaEvent_t evU[4] = {nullptr, nullptr, nullptr, nullptr}, evD[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -248,9 +252,9 @@ static int stats_begin(dvc_ctx* c, cudaStream_t s, int arena = 0) {
     CUDA_TRY(c, cudaMalloc((void**)&c->stats, need * sizeof(double)));
     c->stats_cap = need;
   }
-  c->cur_arena = arena ? 1 : 0;
-  c->stats_lo = arena ? need / 2 : 0;
-  c->stats_hi = arena ? need : need / 2;
+  c->cur_arena = arena < 0 ? 0 : (arena > 2 ? 2 : arena);  // 0: phase A, 1: ColorVidNet, 2: phase A on the second stream
+  c->stats_lo = (size_t)c->cur_arena * (need / 4);
+  c->stats_hi = c->stats_lo + need / 4;
   c->stats_used = c->stats_lo;
   c->cell_left = 0;
   return DVC_OK;
@@ -591,8 +595,8 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
       const size_t mt = ((size_t)t.Mtot + 127) / 128 + 1;
       void *wsb, *flb;
       const int sigw[5] = {0, 0, 0, 0, 0};
-      DVC_TRY(get_buf(c, c->cur_arena ? "tc.ws1" : "tc.ws0", mt * 128 * (size_t)w->cout_pad_tc * sizeof(float), &wsb, sigw, false, s));
-      DVC_TRY(get_buf(c, c->cur_arena ? "tc.flags1" : "tc.flags0", (size_t)1 << 20, &flb, sigw, true, s));
+      DVC_TRY(get_buf(c, "tc.ws" + std::to_string(c->cur_arena), mt * 128 * (size_t)w->cout_pad_tc * sizeof(float), &wsb, sigw, false, s));
+      DVC_TRY(get_buf(c, "tc.flags" + std::to_string(c->cur_arena), (size_t)1 << 20, &flb, sigw, true, s));
       if (mt * (size_t)(w->cout_pad_tc / 64) < ((size_t)1 << 18)) {
         t.ws = (float*)wsb, t.flags = (int*)flb, t.epoch = ++c->tc_epoch[c->cur_arena];
       }
@@ -862,7 +866,7 @@ static int warp_side(dvc_ctx* c, const std::string& tag, const Act n[4], const c
 // ------------------------------------------------------------------------------------------------
 // correlation dispatch
 // ------------------------------------------------------------------------------------------------
-static int run_corr(dvc_ctx* c, const CorrParams& p, cudaStream_t s, long long phi_version = -1) {
+static int run_corr(dvc_ctx* c, const CorrParams& p, cudaStream_t s, long long phi_version = -1, CorrWorkspace* ws = nullptr) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->prof_corr) {
     CUDA_TRY(c, cudaEventCreate(&e0));
@@ -873,7 +877,7 @@ static int run_corr(dvc_ctx* c, const CorrParams& p, cudaStream_t s, long long p
     launch_corr_simt(p, s);
   } else {
     std::string err;
-    if (launch_corr_tc(p, c->corr_math, c->corr_cluster, c->corr_screen, &c->corr_ws, phi_version, s, &err) != 0)
+    if (launch_corr_tc(p, c->corr_math, c->corr_cluster, c->corr_screen, ws ? ws : &c->corr_ws, phi_version, s, &err) != 0)
       return fail(c, DVC_ERR_CUDA, "corr_tc: " + err);
   }
   DVC_TRY(check_launch(c, "corr"));
@@ -1087,6 +1091,9 @@ extern "C" int dvc_destroy(dvc_ctx* c) {
   }
   if (c->stats) cudaFree(c->stats);
   if (c->sA) cudaStreamDestroy(c->sA);
+  if (c->sA2) cudaStreamDestroy(c->sA2);
+  if (c->evJoinA2) cudaEventDestroy(c->evJoinA2);
+  corr_ws_free(&c->corr_ws2);
   if (c->sC) cudaStreamDestroy(c->sC);
   for (int i = 0; i < 4; ++i) {
     if (c->evA[i]) cudaEventDestroy(c->evA[i]);
@@ -1127,6 +1134,7 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!strcmp(name, "tc_kc")) { c->tc_kc = value < 1 ? 1 : value; return DVC_OK; }
   if (!strcmp(name, "corr_cluster")) { c->corr_cluster = value == 1 ? 1 : 2; return DVC_OK; }
   if (!strcmp(name, "corr_screen")) { c->corr_screen = value != 0; return DVC_OK; }
+  if (!strcmp(name, "clip_astreams")) { c->clip_astreams = value == 2 ? 2 : 1; return DVC_OK; }
   if (!strcmp(name, "tc_tail")) { c->tc_tail = value < 0 ? 0 : value; return DVC_OK; }  // > 1: pretend pair-slot count (tests)
   if (!strcmp(name, "tc_f16")) { c->tc_f16 = value != 0; return DVC_OK; }
   if (!strcmp(name, "tc_splits")) { c->tc_splits = value < 0 ? 0 : (value > 8 ? 8 : value); return DVC_OK; }
@@ -1548,8 +1556,8 @@ extern "C" int dvc_set_exemplar(dvc_ctx* c, const float* IB_lab, int H, int W, v
 
 // Phase A (independent of the previous frame): VGG19 -> feature_normalize -> WarpNet A side -> correlation.
 static int frames_phaseA(dvc_ctx* c, const std::string& tag, const float* IA_l, int B, int H, int W, float temperature,
-                         float* yrows, float* simrows, cudaStream_t s) {
-  DVC_TRY(stats_begin(c, s, 0));
+                         float* yrows, float* simrows, cudaStream_t s, int arena = 0, CorrWorkspace* ws = nullptr) {
+  DVC_TRY(stats_begin(c, s, arena));
   const int h = H / 4, w = W / 4, N = h * w;
   Act x0;
   DVC_TRY(get_act(c, tag + ".x0", B, H, W, 8, 1, &x0, s));
@@ -1565,7 +1573,7 @@ static int frames_phaseA(dvc_ctx* c, const std::string& tag, const float* IA_l, 
   CorrParams p{};
   p.theta = (float*)theta, p.phi = c->ex_phi, p.V = c->ex_V, p.B = B, p.Bphi = 1, p.NA = N, p.NB = N, p.C = 256;
   p.temperature = temperature, p.y = yrows, p.sim = simrows, p.argmax = nullptr;
-  return run_corr(c, p, s, c->ex_version);
+  return run_corr(c, p, s, c->ex_version, ws);
 }
 
 // Phase C (the recurrent part): ColorVidNet on [L, warped ab, similarity, previous Lab] (FrameColor.py:63-65).
@@ -1607,6 +1615,8 @@ extern "C" int dvc_colorize_frames(dvc_ctx* c, const float* IA_l, const float* I
 static int clip_streams(dvc_ctx* c) {
   if (c->sA) return DVC_OK;
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->sA, cudaStreamNonBlocking));
+  CUDA_TRY(c, cudaStreamCreateWithFlags(&c->sA2, cudaStreamNonBlocking));
+  CUDA_TRY(c, cudaEventCreateWithFlags(&c->evJoinA2, cudaEventDisableTiming));
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->sC, cudaStreamNonBlocking));
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->sU, cudaStreamNonBlocking));
   CUDA_TRY(c, cudaStreamCreateWithFlags(&c->sD, cudaStreamNonBlocking));
@@ -1641,8 +1651,11 @@ extern "C" int dvc_colorize_clip(dvc_ctx* c, const float* L_in, int F, int H, in
   DVC_TRY(get_raw(c, "clip.L", 4 * hw * 4, &dL, s));   // 4 slots
   DVC_TRY(get_raw(c, "clip.last", 3 * hw * 4, &dlast, s));
   DVC_TRY(get_raw(c, "clip.ab", 2 * 2 * hw * 4, &dab, s));  // 2 slots
-  DVC_TRY(get_raw(c, "clip.yrows", (size_t)2 * N * 16, &yrows, s));
-  DVC_TRY(get_raw(c, "clip.simrows", (size_t)2 * N * 4, &simrows, s));
+  DVC_TRY(get_raw(c, "clip.yrows", (size_t)4 * N * 16, &yrows, s));  // 4 slots: phase A may run up to 3 frames ahead
+  DVC_TRY(get_raw(c, "clip.simrows", (size_t)4 * N * 4, &simrows, s));
+  const bool two_a = c->clip_astreams == 2;
+  // the second phase-A stream has its own correlation workspace (sized like the first at dvc_set_exemplar time)
+  if (two_a && corr_ws_reserve(&c->corr_ws2, 1, 1, N, N) != 0) return fail(c, DVC_ERR_CUDA, "colorize_clip: correlation workspace allocation failed");
   if (first_last)
     CUDA_TRY(c, cudaMemcpyAsync(dlast, first_last, 3 * hw * 4, cudaMemcpyDefault, s));
   else
@@ -1652,6 +1665,7 @@ extern "C" int dvc_colorize_clip(dvc_ctx* c, const float* L_in, int F, int H, in
   auto enqueue = [&]() -> int {
     CUDA_TRY(c, cudaEventRecord(c->evFork, s));
     CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evFork, 0));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->sA2, c->evFork, 0));
     CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evFork, 0));
     CUDA_TRY(c, cudaStreamWaitEvent(c->sU, c->evFork, 0));
     CUDA_TRY(c, cudaStreamWaitEvent(c->sD, c->evFork, 0));
@@ -1659,17 +1673,20 @@ extern "C" int dvc_colorize_clip(dvc_ctx* c, const float* L_in, int F, int H, in
       const int slot = t & 1;
       float* Lt = (float*)dL + (size_t)(t & 3) * hw;
       float* abt = (float*)dab + (size_t)slot * 2 * hw;
-      float* yr = (float*)yrows + (size_t)slot * N * 4;
-      float* sr = (float*)simrows + (size_t)slot * N;
+      float* yr = (float*)yrows + (size_t)(t & 3) * N * 4;
+      float* sr = (float*)simrows + (size_t)(t & 3) * N;
+      const bool odd = two_a && (t & 1);
+      cudaStream_t sAt = odd ? c->sA2 : c->sA;
       // ---- upload stream: the L slot was last read by frame t-4's ColorVidNet / make_last ----
       if (t >= 4) CUDA_TRY(c, cudaStreamWaitEvent(c->sU, c->evC[(t - 4) & 3], 0));
       CUDA_TRY(c, cudaMemcpyAsync(Lt, L_in + (size_t)t * hw, hw * 4, cudaMemcpyDefault, c->sU));
       CUDA_TRY(c, cudaEventRecord(c->evU[t & 3], c->sU));
-      // ---- stream A: frame-independent phase; the warp-row slot reuse waits for frame t-2's ColorVidNet ----
-      CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evU[t & 3], 0));
-      if (t >= 2) CUDA_TRY(c, cudaStreamWaitEvent(c->sA, c->evC[(t - 2) & 3], 0));
-      DVC_TRY(frames_phaseA(c, "clipA", Lt, 1, H, W, temperature, yr, sr, c->sA));
-      CUDA_TRY(c, cudaEventRecord(c->evA[t & 3], c->sA));
+      // ---- stream A (two of them, alternating, when clip_astreams = 2): the frame-independent phase; the reuse of the
+      // warp-row slot waits for frame t-4's ColorVidNet ----
+      CUDA_TRY(c, cudaStreamWaitEvent(sAt, c->evU[t & 3], 0));
+      if (t >= 4) CUDA_TRY(c, cudaStreamWaitEvent(sAt, c->evC[(t - 4) & 3], 0));
+      DVC_TRY(frames_phaseA(c, odd ? "clipA2" : "clipA", Lt, 1, H, W, temperature, yr, sr, sAt, odd ? 2 : 0, odd ? &c->corr_ws2 : nullptr));
+      CUDA_TRY(c, cudaEventRecord(c->evA[t & 3], sAt));
       // ---- stream C: the recurrent phase ----
       CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evA[t & 3], 0));
       if (t >= 2) CUDA_TRY(c, cudaStreamWaitEvent(c->sC, c->evD[(t - 2) & 3], 0));  // the ab slot has been downloaded
@@ -1689,13 +1706,15 @@ extern "C" int dvc_colorize_clip(dvc_ctx* c, const float* L_in, int F, int H, in
   // join: the caller's stream waits for the four internal streams, then the host waits for the caller's stream
   bool join_ok = true;
   join_ok &= cudaEventRecord(c->evJoinA, c->sA) == cudaSuccess && cudaStreamWaitEvent(s, c->evJoinA, 0) == cudaSuccess;
+  join_ok &= cudaEventRecord(c->evJoinA2, c->sA2) == cudaSuccess && cudaStreamWaitEvent(s, c->evJoinA2, 0) == cudaSuccess;
   join_ok &= cudaEventRecord(c->evJoinC, c->sC) == cudaSuccess && cudaStreamWaitEvent(s, c->evJoinC, 0) == cudaSuccess;
   join_ok &= cudaEventRecord(c->evJoinD, c->sD) == cudaSuccess && cudaStreamWaitEvent(s, c->evJoinD, 0) == cudaSuccess;
   join_ok &= cudaEventRecord(c->evFork, c->sU) == cudaSuccess && cudaStreamWaitEvent(s, c->evFork, 0) == cudaSuccess;
   const cudaError_t se = cudaStreamSynchronize(s);
   if (rc != DVC_OK) {
     if (!join_ok || se != cudaSuccess) {  // could not even drain the streams: make sure nothing is in flight
-      cudaStreamSynchronize(c->sA), cudaStreamSynchronize(c->sC), cudaStreamSynchronize(c->sU), cudaStreamSynchronize(c->sD);
+      cudaStreamSynchronize(c->sA), cudaStreamSynchronize(c->sA2), cudaStreamSynchronize(c->sC), cudaStreamSynchronize(c->sU),
+          cudaStreamSynchronize(c->sD);
     }
     c->err = first_err;
     return rc;

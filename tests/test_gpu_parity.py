@@ -317,6 +317,12 @@ def test_fused_clip_recurrence(ctx, conv_math):
     frames, IB, ref = torch.from_numpy(g["frames_lab"]), torch.from_numpy(g["IB_lab"]), g["ab32"]
     ctx.set_exemplar(IB)
     out = ctx.colorize_clip(frames[:, 0:1].contiguous().pin_memory())
+    ctx.debug_flag("clip_astreams", 2)  # frames t+1 and t+2 in flight on two phase-A streams: same bits
+    try:
+        out2 = ctx.colorize_clip(frames[:, 0:1].contiguous().pin_memory())
+    finally:
+        ctx.debug_flag("clip_astreams", 1)
+    assert torch.equal(out, out2)
     last = torch.zeros(1, 3, 32, 48, device="cuda")
     for t in range(frames.shape[0]):
         L = frames[t:t + 1, 0:1].cuda()
