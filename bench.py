@@ -224,6 +224,8 @@ def main():
                     help="split-K of the conv engine: 1 off (default), 0 automatic")
     ap.add_argument("--tc-rowshare", type=int, default=int(os.environ.get("DVC_TC_ROWSHARE", "0")), choices=[0, 1],
                     help="1: the taps of a 3x3 kernel row share one activation tile in shared memory (conv_tc.cu: CfgRS)")
+    ap.add_argument("--clip-astreams", type=int, default=int(os.environ.get("DVC_CLIP_ASTREAMS", "1")), choices=[1, 2],
+                    help="2: the frame-independent phase of frames t+1 and t+2 overlaps frame t's ColorVidNet (two streams)")
     ap.add_argument("--tc-cluster", type=int, default=int(os.environ.get("DVC_TC_CLUSTER", "2")), choices=[1, 2],
                     help="2 = CTA pairs (tcgen05.mma.cta_group::2) in the conv engine, 1 = single CTAs")
     ap.add_argument("--cpu-sample", type=int, default=4, help="frames timed for cpu_baseline (0 = skip)")
@@ -263,6 +265,7 @@ def main():
     ctx.debug_flag("tc_f16", args.tc_f16)
     ctx.debug_flag("tc_tail", args.tc_tail)
     ctx.debug_flag("tc_rowshare", args.tc_rowshare)
+    ctx.debug_flag("clip_astreams", args.clip_astreams)
     ctx.debug_flag("corr_cluster", args.corr_cluster)
     ctx.debug_flag("corr_screen", args.corr_screen)
 

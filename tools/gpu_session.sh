@@ -21,6 +21,8 @@ for S in $STEPS; do
     rs)       DVC_TEST_ROWSHARE=1,2 timeout 600 python -m pytest tests/test_gpu_rowshare.py -m gpu -q --maxfail=400 -s -p no:cacheprovider > $O/${TAG}_rs.log 2>&1 ;;
     layers)   timeout 300 python tools/conv_layer_bench.py --out $O/conv_layers_r2.jsonl > $O/${TAG}_layers.log 2>&1 ;;
     benchrs)  timeout 600 python bench.py --steps 20 --warmup 5 --tc-rowshare 1 --cpu-sample 0 --clip-frames 0 > $O/${TAG}_benchrs.json 2> $O/${TAG}_benchrs.err ;;
+    bench3)   timeout 600 python bench.py --steps 20 --warmup 5 --clip-astreams 2 --cpu-sample 0 --clip-frames 0 > $O/${TAG}_bench3.json 2> $O/${TAG}_bench3.err ;;
+    bench3rs) timeout 600 python bench.py --steps 20 --warmup 5 --clip-astreams 2 --tc-rowshare 1 --cpu-sample 0 --clip-frames 0 > $O/${TAG}_bench3rs.json 2> $O/${TAG}_bench3rs.err ;;
     multi)    timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -s -p no:cacheprovider > $O/${TAG}_multi.log 2>&1 ;;
     *) echo "unknown step $S" ;;
   esac
