@@ -503,15 +503,20 @@ constexpr int SCREEN_K = 12;        // candidates kept per (row, column-range sp
 constexpr int SCREEN_EPI_WARPS = 8;  // two per TMEM lane quarter, each owning 128 of a tile's 256 columns
 constexpr int SCREEN_HALVES = SCREEN_EPI_WARPS / 4;
 
+// The query tile (128 rows x 256 channels of fp16 = 64 KB) stays RESIDENT in shared memory for the CTA's whole sweep over
+// the reference positions; only the reference tiles stream through the ring.  The kernel is bound by the L2 -> SM fabric
+// (ncu: l1tex__m_xbar2l1tex_read_bytes at 4.6 TB/s with both operands streamed; the exact 3-pass kernel pulls 6.6 TB/s, the
+// most any kernel of this library gets out of the L2), so halving the bytes per tile is what shortens it.
 template <int CL>
 struct ScreenCfg {
-  static constexpr int STAGES = CL == 2 ? 6 : 4;
+  static constexpr int STAGES = CL == 2 ? 8 : 4;
   static constexpr int A_BYTES = BM * 128, B_BYTES = (BN / CL) * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 49152 / 32768
+  static constexpr int A_RES_BYTES = 4 * A_BYTES;        // all four k-blocks of the query tile (C = 256)
+  static constexpr int STAGE_BYTES = B_BYTES;            // 16384 / 32768
   // candidate lists of the epilogue threads: [SCREEN_K][epilogue threads] (value, column) -- slot k of thread t lives at
   // [k][t], so dynamic slot indices never conflict on a bank and never touch local memory
   static constexpr int LIST_BYTES = SCREEN_K * SCREEN_EPI_WARPS * 32 * 8;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + LIST_BYTES;
+  static constexpr int SMEM_BYTES = A_RES_BYTES + STAGES * STAGE_BYTES + 1024 + 256 + LIST_BYTES;
 };
 constexpr int SCREEN_THREADS = 64 + 32 * SCREEN_EPI_WARPS;
 
@@ -538,18 +543,20 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1)
   using C = ScreenCfg<CL>;
   constexpr int KB = 64;
   constexpr uint32_t IDESC = tc::umma_idesc(0u, BM * CL, BN);
-  constexpr int STAGES = C::STAGES, A_BYTES = C::A_BYTES, STAGE_BYTES = C::STAGE_BYTES;
+  constexpr int STAGES = C::STAGES, A_BYTES = C::A_BYTES, STAGE_BYTES = C::STAGE_BYTES, A_RES = C::A_RES_BYTES;
   const int crank = (CL == 2) ? (int)tc::cluster_ctarank() : 0;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* ring = smem + A_RES;  // the resident query tile comes first, then the ring of reference tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* s_cf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [SCREEN_K][epilogue threads] values
+  uint64_t* afull = bars + 2 * STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+  float* s_cf = reinterpret_cast<float*>(ring + STAGES * STAGE_BYTES + 256);  // [SCREEN_K][epilogue threads] values
   int* s_ci = reinterpret_cast<int*>(s_cf + SCREEN_K * SCREEN_EPI_WARPS * 32);  // ... and their columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -566,6 +573,7 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1)
     tc::tma_prefetch_desc(&tmBh);
     for (int i = 0; i < STAGES; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
     for (int i = 0; i < 2; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], SCREEN_EPI_WARPS * CL);
+    tc::mbar_init(afull, 1);
     tc::fence_barrier_init();
   }
   if (CL == 2) tc::cluster_sync_all();
@@ -587,20 +595,28 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1)
   if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
+    if (ntiles > 0 && tc::elect_one()) {  // the query tile: loaded once, resident for the whole sweep
+      if (CL == 1) {
+        tc::mbar_arrive_expect_tx(afull, A_RES);
+        for (int kb = 0; kb < nkb; ++kb) tc::tma_load_2d(smem + kb * A_BYTES, &tmAh, afull, kb * KB, b * p.NA + m0);
+      } else {
+        if (crank == 0) tc::mbar_arrive_expect_tx(afull, 2 * A_RES);
+        for (int kb = 0; kb < nkb; ++kb) tc::tma_load_2d_pair(smem + kb * A_BYTES, &tmAh, afull, kb * KB, b * p.NA + m0);
+      }
+    }
+    __syncwarp();
     for (int t = 0; t < ntiles; ++t) {
       const int col0 = bphi * p.NB + (t0 + t) * BN;
       for (int kb = 0; kb < nkb; ++kb) {
         tc::mbar_wait(&empty[stage], phase ^ 1);
         if (tc::elect_one()) {
-          uint8_t* st = smem + stage * STAGE_BYTES;
+          uint8_t* st = ring + stage * STAGE_BYTES;
           if (CL == 1) {
             tc::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-            tc::tma_load_2d(st, &tmAh, &full[stage], kb * KB, b * p.NA + m0);
-            tc::tma_load_2d(st + A_BYTES, &tmBh, &full[stage], kb * KB, col0);
+            tc::tma_load_2d(st, &tmBh, &full[stage], kb * KB, col0);
           } else {
             if (crank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
-            tc::tma_load_2d_pair(st, &tmAh, &full[stage], kb * KB, b * p.NA + m0);
-            tc::tma_load_2d_pair(st + A_BYTES, &tmBh, &full[stage], kb * KB, col0 + crank * (BN / 2));
+            tc::tma_load_2d_pair(st, &tmBh, &full[stage], kb * KB, col0 + crank * (BN / 2));
           }
         }
         __syncwarp();
@@ -613,14 +629,15 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1)
       uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
+        if (t == 0) tc::mbar_wait(afull, 0);
         tc::mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t d = tmem_base + buf * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           tc::mbar_wait(&full[stage], phase);
           tc::tc_fence_after();
-          const uint32_t sa = tc::smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t dA = tc::umma_desc_k128(sa), dB = tc::umma_desc_k128(sa + A_BYTES);
+          const uint64_t dA = tc::umma_desc_k128(tc::smem_u32(smem + kb * A_BYTES));
+          const uint64_t dB = tc::umma_desc_k128(tc::smem_u32(ring + stage * STAGE_BYTES));
           if (tc::elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {

@@ -10,9 +10,9 @@ cap() {  # name, kernel regex, launch-skip, launch-count, extra env
   rm -f /tmp/ncu_$name.ncu-rep
 }
 # exemplar prologue = 41 tensor-core conv launches; frame kernels come after.  Pick launches of the first frame.
-cap conv256 'conv_tc_kernel<256' 24 8 DVC_X=1
-cap conv128 'conv_tc_kernel<128' 14 4 DVC_X=1
-cap conv64  'conv_tc_kernel<64'  8 3 DVC_X=1
+cap conv256 'conv_tc_kernel<\(int\)256' 24 8 DVC_X=1
+cap conv128 'conv_tc_kernel<\(int\)128' 14 4 DVC_X=1
+cap conv64  'conv_tc_kernel<\(int\)64' 8 3 DVC_X=1
 cap xform   'xform_kernel'       20 4 DVC_X=1
 cap screen  'corr_screen_kernel' 0 1 DVC_X=1
 cap rescore 'corr_rescore_kernel' 0 1 DVC_X=1

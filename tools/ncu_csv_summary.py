@@ -1,0 +1,47 @@
+"""Key metrics of `ncu --page raw --csv` exports (one row per captured launch) as a markdown table.
+python tools/ncu_csv_summary.py file.csv [out.md]"""
+import csv
+import sys
+
+WANT = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_tensor.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__m_xbar2l1tex_read_bytes.sum",
+    "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+    "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_sleeping_per_warp_active.pct",
+    "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+    "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_membar_per_warp_active.pct",
+    "smsp__warp_issue_stalled_tex_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
+]
+
+
+def main(path, out=None):
+    rows = list(csv.reader(open(path, newline="")))
+    rows = [r for r in rows if len(r) > 10]
+    if len(rows) < 3:
+        print("no launches in", path)
+        return
+    hdr, units, launches = rows[0], rows[1], rows[2:]
+    ki = hdr.index("Kernel Name") if "Kernel Name" in hdr else None
+    lines = []
+    head = "| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(launches))) + " |"
+    lines += [f"kernel: `{launches[0][ki][:110] if ki is not None else '?'}`", "", head, "|---|---|" + "---:|" * len(launches)]
+    for w in WANT:
+        for j, h in enumerate(hdr):
+            if h == w or h.endswith(w):
+                lines.append(f"| {w} | {units[j]} | " + " | ".join(l[j] for l in launches) + " |")
+                break
+    text = "\n".join(lines) + "\n"
+    if out:
+        open(out, "w").write(text)
+    print(text)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
