@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(Epi<SOFTMAX>::NTHREADS, 1)
 // column-range split) while it streams the tiles -- one third of the MMA work and half of the operand bytes of the
 // 3-pass kernel; corr_rescore_kernel then evaluates the candidates exactly in fp32 on the CUDA cores (a few per row) and
 // produces (sim, argmax, mean V of bit-equal maxima).  A list that overflows marks its (row, split) for brute force.
-constexpr int SCREEN_K = 12;        // candidates kept per (row, column-range split, column half)
+constexpr int SCREEN_K = 16;        // candidates kept per (row, column-range split, column half)
 constexpr int SCREEN_EPI_WARPS = 8;  // two per TMEM lane quarter, each owning 128 of a tile's 256 columns
 constexpr int SCREEN_HALVES = SCREEN_EPI_WARPS / 4;
 
@@ -513,9 +513,9 @@ struct ScreenCfg {
   static constexpr int A_BYTES = BM * 128, B_BYTES = (BN / CL) * 128;
   static constexpr int A_RES_BYTES = 4 * A_BYTES;        // all four k-blocks of the query tile (C = 256)
   static constexpr int STAGE_BYTES = B_BYTES;            // 16384 / 32768
-  // candidate lists of the epilogue threads: [SCREEN_K][epilogue threads] (value, column) -- slot k of thread t lives at
+  // candidate lists of the epilogue threads: [SCREEN_K][epilogue threads] column indices -- slot k of thread t lives at
   // [k][t], so dynamic slot indices never conflict on a bank and never touch local memory
-  static constexpr int LIST_BYTES = SCREEN_K * SCREEN_EPI_WARPS * 32 * 8;
+  static constexpr int LIST_BYTES = SCREEN_K * SCREEN_EPI_WARPS * 32 * 4;
   static constexpr int SMEM_BYTES = A_RES_BYTES + STAGES * STAGE_BYTES + 1024 + 256 + LIST_BYTES;
 };
 constexpr int SCREEN_THREADS = 64 + 32 * SCREEN_EPI_WARPS;
@@ -556,8 +556,7 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1)
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint64_t* afull = bars + 2 * STAGES + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
-  float* s_cf = reinterpret_cast<float*>(ring + STAGES * STAGE_BYTES + 256);  // [SCREEN_K][epilogue threads] values
-  int* s_ci = reinterpret_cast<int*>(s_cf + SCREEN_K * SCREEN_EPI_WARPS * 32);  // ... and their columns
+  int* s_ci = reinterpret_cast<int*>(ring + STAGES * STAGE_BYTES + 256);  // [SCREEN_K][epilogue threads] candidate columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -662,12 +661,17 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1)
     }
   } else {
     // ================= epilogue: one query row x one column half per thread =================
-    // Per 32-column chunk the common path is one tcgen05.ld and 16 three-input maxima.  A chunk whose maximum comes within
-    // the threshold of the row's running maximum (a "record" or a near-tie: ~ln(#chunks) times per row, but for SOME lane
-    // of a warp in about every second chunk) appends its qualifying columns to the thread's list with 32 predicated
-    // shared-memory stores -- no local memory, no data-dependent loop.
+    // Per tile a thread drains its 128 columns with four tcgen05.ld in flight before one wait (a load that is waited for
+    // alone exposes its full latency: the first version, one x32 load per wait, spent 7.5 K cycles per tile on a 2 K-cycle
+    // MMA tile -- as did the exact 3-pass kernel's epilogue, which hid behind its 6 K cycles of MMAs), then 16 three-input
+    // maxima per 32-column chunk.  A chunk whose maximum comes within the threshold of the row's running maximum (a
+    // "record" or a near-tie: ~ln(#chunks) times per row, but for SOME lane of a warp in about every second chunk) builds
+    // a 32-bit mask of its qualifying columns and appends their indices to the thread's list in shared memory
+    // ([slot][thread]: no bank conflicts, no local memory).  Values are not kept: a record that beats the previous maximum
+    // by more than the threshold disqualifies the whole list at once (every entry is <= the previous maximum); otherwise
+    // the old entries stay -- at worst a few extra candidates for the exact re-scoring, never a missing one.
     const int q = warp & 3, half = (warp - 2) >> 2;
-    constexpr int COLS = BN / SCREEN_HALVES;
+    constexpr int COLS = BN / SCREEN_HALVES;   // 128
     constexpr int LT = SCREEN_EPI_WARPS * 32;  // list stride
     const int et = threadIdx.x - 64;           // epilogue thread index
     const int row = m0 + q * 32 + lane;
@@ -677,50 +681,45 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1)
                                        __uint_as_float(__ldg(p.nh_b_max))) * 268435456.0f;
     float run_m = -INFINITY;
     int cnt = 0;  // entries appended (only the first SCREEN_K are stored: cnt > SCREEN_K = overflow)
-    bool overflow = false;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       tc::mbar_wait(&tfull[buf], (t >> 1) & 1);
       tc::tc_fence_after();
       const int colbase = (t0 + t) * BN + half * COLS;
-#pragma unroll 1
-      for (int c = 0; c < COLS / 32; ++c) {
-        const int cb = colbase + c * 32;
-        if (cb >= p.NB) break;
-        uint32_t r[32];
+      if (colbase < p.NB) {  // warp-uniform
+        uint32_t r[COLS / 32][32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * COLS;
         __syncwarp();
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * COLS + c * 32, r);
+#pragma unroll
+        for (int c = 0; c < COLS / 32; ++c) tc::tmem_ld_32x32(taddr + c * 32, r[c]);
         tc::tmem_ld_wait();
-        const int nvalid = min(32, p.NB - cb);
-        if (nvalid < 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i >= nvalid) r[i] = __float_as_uint(-INFINITY);
-        }
-        float cm = -INFINITY;
+        for (int c = 0; c < COLS / 32; ++c) {
+          const int cb = colbase + c * 32;
+          const int nvalid = p.NB - cb;  // columns at or beyond NB hold zero-filled (TMA) operands: mask them
+          if (nvalid < 32) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(r[i]));
-        run_m = fmaxf(run_m, cm);
-        const float lim = run_m - thr;
-        if (cm >= lim) {
-          if (cnt > SCREEN_K / 2 && cnt <= SCREEN_K) {  // drop the entries the risen maximum has disqualified
-            int k = 0;
-            for (int j = 0; j < cnt; ++j) {
-              const float v = s_cf[j * LT + et];
-              const int ci = s_ci[j * LT + et];
-              if (v >= lim) s_cf[k * LT + et] = v, s_ci[k * LT + et] = ci, ++k;
-            }
-            cnt = k;
+            for (int i = 0; i < 32; ++i)
+              if (i >= nvalid) r[c][i] = __float_as_uint(-INFINITY);
           }
+          float cm = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = __uint_as_float(r[i]);
-            if (v >= lim) {
-              if (cnt < SCREEN_K) s_cf[cnt * LT + et] = v, s_ci[cnt * LT + et] = cb + i;
+          for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(r[c][i]));
+          if (cm - thr > run_m) cnt = 0;  // a record that disqualifies every earlier entry (all <= the old maximum)
+          run_m = fmaxf(run_m, cm);
+          const float lim = run_m - thr;
+          if (cm >= lim && cm > -INFINITY) {
+            uint32_t mask = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(r[c][i]) >= lim ? 1u : 0u) << i;
+            while (mask) {
+              const int i = __ffs(mask) - 1;
+              mask &= mask - 1;
+              if (cnt < SCREEN_K) s_ci[cnt * LT + et] = cb + i;
               ++cnt;
             }
+            if (cnt > SCREEN_K) cnt = SCREEN_K + 1;  // overflow (sticky until a disqualifying record clears the list)
           }
-          if (cnt > SCREEN_K) overflow = true, cnt = SCREEN_K + 1;
         }
       }
       tc::tc_fence_before();
@@ -735,13 +734,10 @@ __global__ void __launch_bounds__(SCREEN_THREADS, 1)
     if (row < p.NA) {
       const size_t o = ((size_t)(blockIdx.z * SCREEN_HALVES + half) * p.B + b) * p.NA + row;
       p.pm[o] = run_m * 3.725290298461914e-09f;
-      int k = 0;
-      if (!overflow) {
-        const float lim = run_m - thr;
-        for (int j = 0; j < cnt; ++j)
-          if (s_cf[j * LT + et] >= lim) p.pidx[o * SCREEN_K + k++] = s_ci[j * LT + et];
-      }
-      p.pcnt[o] = overflow ? -1 : k;
+      const bool overflow = cnt > SCREEN_K;
+      if (!overflow)
+        for (int j = 0; j < cnt; ++j) p.pidx[o * SCREEN_K + j] = s_ci[j * LT + et];
+      p.pcnt[o] = overflow ? -1 : cnt;
     }
   }
 

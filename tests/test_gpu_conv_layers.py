@@ -149,14 +149,32 @@ def test_layer_batch2_tiles_straddle_images(ctx, sds, engine):
 
 # ---- the bench's own geometry (480x864 frame: 120x216 quarter-resolution, 60x108 eighth-resolution maps) ----
 BENCH = [
-    ("quarter_256_208tiles", VGG, "conv3_2", 256, 256, 120, 216, dict(act=1, nonneg=True), 256),
-    ("quarter_256_reflect_stats", WARP, "layer.0.conv1", 256, 256, 120, 216, dict(reflect=True, want_stats=True), 256),
+    # 104 pair items on 74 pair slots: the launcher's cost model takes three rounds of 128-channel tiles over two of 256
+    ("quarter_256_208tiles", VGG, "conv3_2", 256, 256, 120, 216, dict(act=1, nonneg=True), 128),
+    ("quarter_256_reflect_stats", WARP, "layer.0.conv1", 256, 256, 120, 216, dict(reflect=True, want_stats=True), 128),
     ("eighth_512_108tiles", VGG, "conv4_2", 512, 512, 60, 108, dict(act=1, nonneg=True), 256),
     ("eighth_512_dil2_stats", COLOR, "conv5_3", 512, 512, 60, 108, dict(act=1, dil=2, nonneg=True, want_stats=True), 256),
     ("half_128", VGG, "conv2_2", 128, 128, 240, 432, dict(act=1, nonneg=True), 128),
     # the four phases of conv8_1 each see 54 pixel tiles of the 1/8-resolution input: the launcher narrows to 128 channels
     ("quarter_upconv_256", COLOR, "conv8_1.1", 512, 256, 60, 108, dict(act=1, upconv=True, with_add=True), 128),
 ]
+
+
+@pytest.mark.parametrize("force_bn", [256, 128])
+@pytest.mark.parametrize("layer", BENCH[:4], ids=[l[0] for l in BENCH[:4]])
+def test_layer_at_bench_geometry_forced_tile(ctx, sds, layer, force_bn):
+    """Both candidate tiles of the launcher's cost model at the bench's geometry (two rounds of 256 / three of 128)."""
+    import dvc
+
+    _, net, name, cin, cout, H, W, kw, _ = layer
+    ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
+    ctx.debug_flag("tc_cluster", 2)
+    ctx.debug_flag("tc_force_bn", force_bn)
+    try:
+        err, floor = run_layer(ctx, sds, net, name, cin, cout, H, W, **kw)
+    finally:
+        ctx.debug_flag("tc_force_bn", 0)
+    assert err <= 4e-6, (layer[0], force_bn, err, floor)
 
 
 @pytest.mark.parametrize("layer", BENCH, ids=[l[0] for l in BENCH])

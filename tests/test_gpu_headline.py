@@ -56,8 +56,8 @@ def test_fused_frame_vs_reference_at_full_size(ctx, engine, name, H, W):
         n256 = ctx.conv_profile(256)[0]
         ctx.conv_profile(0, reset=True)
         ctx.profile_conv(False)
-        if H == 480:
-            assert n256 >= 30, f"only {n256} launches ran on the 256-channel tile: this test must cover the bench's engine"
+        if H == 480:  # the sixteen 1/8-resolution 512-channel layers (the quarter-resolution ones take 128-channel tiles)
+            assert n256 >= 12, f"only {n256} launches ran on the 256-channel tile: this test must cover the bench's engine"
     ss = sim.cpu().numpy()[:, :, ::4, ::4]
     ys = warp.cpu().numpy()[:, :, ::4, ::4].reshape(1, 3, -1)
     e_sim = np.abs(ss - g["sim64"]).max()
