@@ -431,64 +431,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         for (int j = 0; j < CPT; ++j) tot[j] = __ldcg(wsp + (size_t)j * BM);
       }
       const int ch_lo = nchunks * sp / S, ch_hi = nchunks * (sp + 1) / S;
-#ifdef DVC_DRAIN_SINGLE  // A/B builds only (tools/gpu_session.sh: the "alt" library)
-      constexpr bool kGroupedDrain = false;
-#else
-      constexpr bool kGroupedDrain = true;
-#endif
-      if constexpr (CPT <= 64 && kGroupedDrain) {
-        // Narrow tiles: the MMAs of a chunk take 384 (BN = 64) / 768 (BN = 128) cycles, less than the latency of a
-        // tcgen05.ld that is waited for alone, so draining chunk by chunk made these tiles EPILOGUE-LATENCY bound (the
-        // 64-channel tile ran at 55 % of the 256-channel tile's rate; coarser chunks, which halve the number of drains,
-        // bought 7-18 % at the price of accuracy).  Instead the loads of G = NBUF / 2 consecutive chunks (4 / 2) are issued
-        // back to back, waited for once, and added to the totals chunk by chunk in the same order as before -- the same
-        // bits, a fraction of the exposed latency.  The TMEM ring (NBUF accumulators) keeps the MMAs G chunks ahead.
-        constexpr int G = C::NBUF / 2, LPC = CPT / 32;
-        for (int ch = ch_lo; ch < ch_hi; ch += G) {
-          const int g = min(G, ch_hi - ch);
-          uint32_t r[G][LPC][32];
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < G; ++j)
-            if (j < g) {
-              const uint32_t id = chunk_id + j;
-              const int buf = id % C::NBUF;
-              tc::mbar_wait(&tfull[buf], (id / C::NBUF) & 1);
-              tc::tc_fence_after();
-              const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * CPT;
-#pragma unroll
-              for (int l = 0; l < LPC; ++l) tc::tmem_ld_32x32(tsrc + l * 32, r[j][l]);
-            }
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < G; ++j)
-            if (j < g) {
-              if (ch + j == 0) {  // first chunk of the tile (always in split 0)
-#pragma unroll
-                for (int l = 0; l < LPC; ++l)
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) tot[l * 32 + i] = __uint_as_float(r[j][l][i]);
-              } else {
-#pragma unroll
-                for (int l = 0; l < LPC; ++l)
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) tot[l * 32 + i] += __uint_as_float(r[j][l][i]);
-              }
-            }
-          tc::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            for (int j = 0; j < g; ++j) {
-              const int buf = (chunk_id + j) % C::NBUF;
-              if (CL == 1)
-                tc::mbar_arrive(&tempty[buf]);
-              else
-                tc::mbar_arrive_leader(&tempty[buf]);
-            }
-          }
-          chunk_id += g;
-        }
-      } else {
+      // (Tested and not adopted: issuing the TMEM loads of NBUF / 2 consecutive chunks before one wait on the narrow tiles --
+      // 20-40 % SLOWER, 64-channel tile 123 -> 149 us on the full-resolution 64 -> 64 layer: the accumulators are released
+      // later and the register pressure of the 128-channel variant spills.)
+      {
       for (int ch = ch_lo; ch < ch_hi; ++ch, ++chunk_id) {
         const int buf = chunk_id % C::NBUF;
         const uint32_t acc_phase = (chunk_id / C::NBUF) & 1;

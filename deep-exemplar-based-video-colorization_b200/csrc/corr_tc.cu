@@ -398,13 +398,20 @@ __global__ void __launch_bounds__(Epi<SOFTMAX>::NTHREADS, 1)
       const int colbase = (t0 + t) * BN + half * COLS;
       const float4* Vs = v_ring + buf * BN + half * COLS;
 #pragma unroll 1
-      for (int c = 0; c < COLS / 32; ++c) {
-        const int cb = colbase + c * 32;
-        if (cb >= p.NB) break;  // warp-uniform
-        uint32_t r[32];
+      for (int c0 = 0; c0 < COLS / 32; c0 += 2) {
+        if (colbase + c0 * 32 >= p.NB) break;  // warp-uniform
+        // two loads in flight per wait: a tcgen05.ld that is waited for alone exposes its whole latency
+        uint32_t r2[2][32];
         __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * COLS + c * 32, r);
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * COLS + c0 * 32, r2[0]);
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * COLS + c0 * 32 + 32, r2[1]);
         tc::tmem_ld_wait();
+#pragma unroll
+      for (int cj = 0; cj < 2; ++cj) {
+        const int c = c0 + cj;
+        const int cb = colbase + c * 32;
+        if (cb >= p.NB) continue;  // warp-uniform
+        uint32_t (&r)[32] = r2[cj];
         const int nvalid = min(32, p.NB - cb);
         float cm = -INFINITY;
         if (nvalid == 32) {
@@ -456,6 +463,7 @@ __global__ void __launch_bounds__(Epi<SOFTMAX>::NTHREADS, 1)
               }
           }
         }
+      }  // cj
       }
       tc::tc_fence_before();
       __syncwarp();

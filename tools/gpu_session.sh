@@ -23,10 +23,6 @@ for S in $STEPS; do
     benchrs)  timeout 600 python bench.py --steps 20 --warmup 5 --tc-rowshare 1 --cpu-sample 0 --clip-frames 0 > $O/${TAG}_benchrs.json 2> $O/${TAG}_benchrs.err ;;
     bench3)   timeout 600 python bench.py --steps 20 --warmup 5 --clip-astreams 2 --cpu-sample 0 --clip-frames 0 > $O/${TAG}_bench3.json 2> $O/${TAG}_bench3.err ;;
     bench3rs) timeout 600 python bench.py --steps 20 --warmup 5 --clip-astreams 2 --tc-rowshare 1 --cpu-sample 0 --clip-frames 0 > $O/${TAG}_bench3rs.json 2> $O/${TAG}_bench3rs.err ;;
-    layers_alt) cp deep-exemplar-based-video-colorization_b200/lib/libdvc.so /tmp/libdvc_main.so; cp deep-exemplar-based-video-colorization_b200/lib/libdvc_alt.so deep-exemplar-based-video-colorization_b200/lib/libdvc.so;
-              timeout 300 python tools/conv_layer_bench.py > $O/${TAG}_layers_alt.log 2>&1;
-              timeout 300 python bench.py --steps 20 --warmup 5 --cpu-sample 0 --clip-frames 0 --sustain-s 0 > $O/${TAG}_bench_alt.json 2> $O/${TAG}_bench_alt.err;
-              cp /tmp/libdvc_main.so deep-exemplar-based-video-colorization_b200/lib/libdvc.so ;;
     multi)    timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -s -p no:cacheprovider > $O/${TAG}_multi.log 2>&1 ;;
     *) echo "unknown step $S" ;;
   esac
