@@ -75,7 +75,7 @@ class RowShardedCorrelation:
         # my full-size result buffers: y4 [N][4] followed by sim [N], TWO sets used alternately by call parity: a fast
         # peer may already store the rows of call k+1 while this rank still copies the result of call k out of the
         # other set (it cannot reach call k+2 before this rank has passed call k+1's barrier, i.e. finished that copy)
-        self._set_bytes = self.N * 20
+        self._set_bytes = (self.N * 20 + 255) // 256 * 256  # float4 stores: every set starts 16-byte aligned
         self._calls = 0
         self._own, handle = ctx.peer_buffer_create(2 * self._set_bytes)
         handles = [None] * self.world
