@@ -128,6 +128,12 @@ struct dvc_ctx {
   ScaleCell* cell_next = nullptr;
   int cell_left = 0;
   int corr_cluster = 2;   // correlation: 2 = CTA pairs (tcgen05.mma.cta_group::2), 1 = single CTAs
+  // stand-alone correlation entry: the caller promises that the phi_hat / V buffers keep their contents while this is set, so
+  // their transposed / packed / split forms are prepared once per (pointer, size) -- the exemplar side of a clip
+  int corr_phi_static = 0;
+  const void* corr_phi_key = nullptr;
+  const void* corr_V_key = nullptr;
+  long long corr_phi_dims = 0, corr_phi_version = 0;
   int corr_screen = 1;    // T <= 2e-10, FP16X3: one screening pass + exact re-scoring of the candidates (0: exact 3-pass kernel)
   CorrWorkspace corr_ws;  // operand planes + split partials of the tensor-core correlation (pre-sized by dvc_set_exemplar)
   CorrWorkspace corr_ws2;  // the same for the second phase-A stream of the clip driver (clip_astreams = 2)
@@ -1134,6 +1140,11 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!strcmp(name, "tc_kc")) { c->tc_kc = value < 1 ? 1 : value; return DVC_OK; }
   if (!strcmp(name, "corr_cluster")) { c->corr_cluster = value == 1 ? 1 : 2; return DVC_OK; }
   if (!strcmp(name, "corr_screen")) { c->corr_screen = value != 0; return DVC_OK; }
+  if (!strcmp(name, "corr_phi_static")) {
+    c->corr_phi_static = value != 0;
+    c->corr_phi_key = c->corr_V_key = nullptr;  // the next call prepares the exemplar side afresh
+    return DVC_OK;
+  }
   if (!strcmp(name, "clip_astreams")) { c->clip_astreams = value == 2 ? 2 : 1; return DVC_OK; }
   if (!strcmp(name, "tc_tail")) { c->tc_tail = value < 0 ? 0 : value; return DVC_OK; }  // > 1: pretend pair-slot count (tests)
   if (!strcmp(name, "tc_f16")) { c->tc_f16 = value != 0; return DVC_OK; }
@@ -1434,10 +1445,15 @@ extern "C" int dvc_corr_softmax_warp(dvc_ctx* c, const float* theta_hat, const f
   DVC_TRY(get_raw(c, "corr.y4", (size_t)B * NA * 16, &y4, s));
   // channel-major [b][C][N] (the reference's view, NonlocalNet.py:468,473) -> position-major rows
   launch_transpose_cn(theta_hat, (float*)th, B, C, NA, s);
-  launch_transpose_cn(phi_hat, (float*)ph, Bphi, C, NB, s);
-  // rows (L, a, b, 1): the 4th lane is the constant the softmax epilogue sums the weights with
-  launch_pack_v4(V, (float*)V4, (size_t)Bphi * NB, s);
-  DVC_TRY(check_launch(c, "pack_v4"));
+  const long long dims = ((long long)Bphi << 40) ^ ((long long)NB << 8) ^ C;
+  const bool phi_ready = c->corr_phi_static && c->corr_phi_key == phi_hat && c->corr_V_key == V && c->corr_phi_dims == dims;
+  if (!phi_ready) {
+    launch_transpose_cn(phi_hat, (float*)ph, Bphi, C, NB, s);
+    // rows (L, a, b, 1): the 4th lane is the constant the softmax epilogue sums the weights with
+    launch_pack_v4(V, (float*)V4, (size_t)Bphi * NB, s);
+    DVC_TRY(check_launch(c, "pack_v4"));
+    c->corr_phi_key = phi_hat, c->corr_V_key = V, c->corr_phi_dims = dims, c->corr_phi_version++;
+  }
   CorrParams p{};
   p.theta = (float*)th, p.phi = (float*)ph, p.V = (float*)V4, p.B = B, p.Bphi = Bphi, p.NA = NA, p.NB = NB, p.C = C;
   p.temperature = temperature, p.y = (float*)y4, p.sim = sim, p.argmax = argmax;
@@ -1446,7 +1462,8 @@ extern "C" int dvc_corr_softmax_warp(dvc_ctx* c, const float* theta_hat, const f
     if (c->corr_math == DVC_MATH_FP32) return fail(c, DVC_ERR_STATE, "corr: peer outputs need a tensor-core correlation mode");
     p.peers = c->corr_peers;
   }
-  DVC_TRY(run_corr(c, p, s));
+  // a version number lets the correlation keep the exemplar's operand planes too (offset: never collides with ex_version)
+  DVC_TRY(run_corr(c, p, s, c->corr_phi_static ? (1ll << 40) + c->corr_phi_version : -1));
   CUDA_TRY(c, cudaMemcpy2DAsync(y, 12, y4, 16, 12, (size_t)B * NA, cudaMemcpyDeviceToDevice, s));
   return DVC_OK;
 }

@@ -77,6 +77,7 @@ class RowShardedCorrelation:
         # other set (it cannot reach call k+2 before this rank has passed call k+1's barrier, i.e. finished that copy)
         self._set_bytes = (self.N * 20 + 255) // 256 * 256  # float4 stores: every set starts 16-byte aligned
         self._calls = 0
+        self._static = False
         self._own, handle = ctx.peer_buffer_create(2 * self._set_bytes)
         handles = [None] * self.world
         if self.world > 1:
@@ -92,8 +93,11 @@ class RowShardedCorrelation:
             self._y4.append(base)
             self._sim.append(base + self.N * 16)
 
-    def __call__(self, theta_hat, phi_hat, V, temperature):
-        """theta_hat [1,256,N], phi_hat [1,256,NB], V [1,NB,3] (identical on every rank) -> (y [1,N,3], sim [1,N])."""
+    def __call__(self, theta_hat, phi_hat, V, temperature, exemplar_unchanged=False):
+        """theta_hat [1,256,N], phi_hat [1,256,NB], V [1,NB,3] (identical on every rank) -> (y [1,N,3], sim [1,N]).
+
+        exemplar_unchanged=True: phi_hat / V are the same tensors with the same contents as in the previous call (the
+        exemplar of a clip), so their operand planes are not prepared again."""
         if theta_hat.shape[0] != 1 or theta_hat.shape[2] != self.N:
             raise ValueError("RowShardedCorrelation: theta_hat must be [1,C,N]")
         ctx = self.ctx
@@ -101,6 +105,9 @@ class RowShardedCorrelation:
         self._calls += 1
         if self.row1 > self.row0:
             ctx.corr_set_peer_outputs([p + off for p in self._y4], [p + off for p in self._sim], self.row0)
+            if not exemplar_unchanged or not self._static:
+                ctx.debug_flag("corr_phi_static", 1)  # (re)arms the cache: this call prepares the exemplar side
+                self._static = True
             try:
                 ctx.corr_softmax_warp(theta_hat[:, :, self.row0:self.row1].contiguous(), phi_hat, V, temperature)
             finally:
@@ -116,6 +123,9 @@ class RowShardedCorrelation:
     def close(self):
         if self.world > 1:
             dist.barrier(group=self.group)  # nobody may still be writing into a buffer that is about to go away
+        if self._static:
+            self.ctx.debug_flag("corr_phi_static", 0)
+            self._static = False
         for p in self._opened:
             self.ctx.peer_buffer_close(p)
         self._opened = []

@@ -112,6 +112,7 @@ class FakeCtx:
         return 1000 + self.rank, path.encode().ljust(64, b"\0")
     def peer_buffer_open(self, handle): return 1000 + int(handle.rstrip(b"\0").decode()[-5])
     def peer_buffer_close(self, ptr): pass
+    def debug_flag(self, name, value): pass
     def peer_buffer_destroy(self, ptr): pass
     def corr_set_peer_outputs(self, y4=(), sim=(), row0=0): self.routes = (list(y4), list(sim), row0) if y4 else self.routes
     def corr_softmax_warp(self, th, ph, V, T):
