@@ -109,7 +109,7 @@ class ClockSampler:
 
 def ncu_traffic(kernel):
     """DRAM bytes of one launch from the committed ncu --set full capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "ncu_r1_traffic.json")
+    path = os.path.join(ROOT, "profiles", "ncu_r2_traffic.json")
     try:
         return json.load(open(path))[kernel]["bytes"]
     except Exception:
@@ -424,8 +424,7 @@ def main():
 
     peak, peak_src = measured_peak(ms_serial * KP * 1e-3)
     achieved = CORR_FLOP / (corr_ms * 1e-3) / 1e12 if corr_ms > 0 else 0.0
-    n256, ms256, fl256 = conv_by[256]
-    conv_ach = fl256 / (ms256 * 1e-3) / 1e12 if ms256 > 0 else 0.0
+    conv_all_tflops = conv_all[2] / (conv_all[1] * 1e-3) / 1e12 if conv_all[1] > 0 else 0.0
     conv_detail = {str(v): {"launches_per_frame": n / KP, "ms_per_frame": ms / KP,
                             "tflops": (fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0)} for v, (n, ms, fl) in conv_by.items() if n}
     line = {
@@ -448,18 +447,20 @@ def main():
                 "d2h_bytes_per_step": 2 * H * W * 4},
         "gpu_launches": launches,
         "clocks": clocks,
-        # dominant kernel by device time (profiles/launches_r1.md: conv_tc_kernel<256> ~ 50 % of a frame)
-        "roofline": {"kernel": "conv_tc_kernel<BN=256> (flat shifted GEMM, 3 MMA passes per product, all launches of a frame)",
+        # dominant kernel by device time (profiles/launches_r2.md: conv_tc_kernel, all channel tiles, ~78 % of a frame; the
+        # 128-channel tile alone ~50 %: the launcher moved the quarter-resolution 256-channel layers onto it)
+        "roofline": {"kernel": "conv_tc_kernel (flat shifted GEMM on tcgen05, 3 MMA passes per product; all tensor-core convolution "
+                               "launches of a frame, channel tiles 256 / 128 / 64 listed under other_variants)",
                      "bound": "tensor",
-                     "achieved": conv_ach, "peak": peak, "unit": "TFLOP/s", "frac": conv_ach / peak if peak else None,
-                     "traffic": ncu_traffic("conv_tc_kernel<256>"), "peak_source": peak_src,
-                     "traffic_note": "DRAM bytes of ONE profiled launch (a quarter-resolution 256->256 layer), profiles/ncu_r1_conv256.md; "
-                                     "algorithmic bytes of that launch: 27.2 MB fp16 hi/lo input planes + 2.4 MB weights + 27.2 MB "
-                                     "fp32 output = 56.8 MB (the output stays in L2 for the next layer)",
-                     "launches_per_frame": n256 / KP, "ms_per_frame": ms256 / KP,
-                     "note": "sum of algorithmic FLOPs (2 x output pixels x 9 x Cin x Cout) / sum of CUDA-event launch times, "
+                     "achieved": conv_all_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_all_tflops / peak if peak else None,
+                     "traffic": ncu_traffic("conv_tc_kernel<128>"), "peak_source": peak_src,
+                     "traffic_note": "DRAM bytes (read + write) of ONE profiled launch of the 128-channel tile, the largest class by "
+                                     "device time (profiles/ncu_r2_traffic.json names the layer and its algorithmic bytes)",
+                     "launches_per_frame": conv_all[0] / KP, "ms_per_frame": conv_all[1] / KP,
+                     "note": "sum of algorithmic FLOPs (2 x output pixels x taps x Cin x Cout) / sum of CUDA-event launch times, "
                              "single-stream pass of %d frames inside this run; the 3 MMA passes of the operand split are not "
-                             "counted, so frac is bounded by 1/3 (3xFP16) or 1/6 (3xTF32) of the dense 16-bit peak" % KP,
+                             "counted, so frac is bounded by 1/3 of the dense 16-bit peak (cuBLAS itself reaches 66-76 %% of the "
+                             "nominal 2.25 PFLOP/s on this chip: MEASURED_PEAKS.json)" % KP,
                      "other_variants": conv_detail},
         # the north-star kernel (BASELINE metric: correlation tensor-pipe fraction)
         "roofline_corr": {"kernel": (f"corr_screen_kernel + corr_rescore_kernel ({args.corr_math}, T<=2e-10: one fp16 pass locates every row's "

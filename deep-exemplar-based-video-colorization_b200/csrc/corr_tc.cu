@@ -77,12 +77,12 @@ struct Cfg {
   static constexpr int V_RING_BYTES = 2 * BN * 16;  // softmax epilogue: the V rows of the tile in flight, two slots
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + V_RING_BYTES;
 };
-// warp 0 TMA, warp 1 MMA, then the epilogue warps: 4 (one per TMEM lane quarter) for the argmax epilogue, 8 for the
-// softmax epilogue (two per lane quarter, each owning 128 of the tile's 256 columns: twice the threads to hide the
-// exp2 / FMA latency chains behind)
+// warp 0 TMA, warp 1 MMA, then 8 epilogue warps: two per TMEM lane quarter, each owning 128 of the tile's 256 columns --
+// twice the threads to hide the tcgen05.ld / exp2 / FMA latency chains behind (with 4 warps the exact argmax kernel ran at
+// 39 % tensor-pipe activity under ncu, the 8-warp softmax kernel at 71 %)
 template <bool SOFTMAX>
 struct Epi {
-  static constexpr int WARPS = SOFTMAX ? 8 : 4;
+  static constexpr int WARPS = 8;
   static constexpr int HALVES = WARPS / 4;
   static constexpr int NTHREADS = 64 + 32 * WARPS;
 };
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(Epi<SOFTMAX>::NTHREADS, 1)
   } else {
     // ================= epilogue: one query row per thread (softmax: per thread and column half) =================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int half = SOFTMAX ? ((warp - 2) >> 2) : 0;  // which 128 columns of every 256-column tile
+    const int half = (warp - 2) >> 2;  // which 128 columns of every 256-column tile
     constexpr int COLS = BN / Epi<SOFTMAX>::HALVES;     // columns per thread and tile
     const int row_local = q * 32 + lane;
     const int row = m0 + row_local;
@@ -1048,7 +1048,7 @@ int launch_corr_tc(const CorrParams& p, int math, int cluster, int screen, CorrW
     launch_counter_add(2);
     return 0;
   }
-  const int nparts = nsplit * (softmax ? Epi<true>::HALVES : 1);  // partial rows the merge kernel combines
+  const int nparts = nsplit * Epi<true>::HALVES;  // partial rows the merge kernel combines
   if (ws_get(ws, 4, (size_t)nparts * p.B * p.NA * sizeof(SplitOut), &part)) return fail("workspace allocation failed");
 
   const int grid1 = 148 * 8;
