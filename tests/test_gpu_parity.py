@@ -201,6 +201,30 @@ def test_corr_kernel_shared_exemplar_batch(ctx, corr_math):
         assert torch.equal(y[b:b + 1], yb) and torch.equal(sim[b:b + 1], sb)
 
 
+def test_corr_static_exemplar_side(ctx, corr_math):
+    """corr_phi_static: the exemplar side (transpose, V rows, operand planes) of the stand-alone entry is prepared once per
+    (pointer, size) while the flag is set -- same bits as preparing it every call; re-arming the flag picks up new contents."""
+    gen = torch.Generator().manual_seed(12)
+    th = torch.nn.functional.normalize(torch.randn(1, 256, 400, generator=gen), dim=1).cuda()
+    th2 = torch.nn.functional.normalize(torch.randn(1, 256, 400, generator=gen), dim=1).cuda()
+    ph = torch.nn.functional.normalize(torch.randn(1, 256, 600, generator=gen), dim=1).cuda()
+    V = (torch.randn(1, 600, 3, generator=gen) * 30).cuda()
+    for T in (1e-10, 0.01):
+        ref1, ref2 = ctx.corr_softmax_warp(th, ph, V, T), ctx.corr_softmax_warp(th2, ph, V, T)
+        ctx.debug_flag("corr_phi_static", 1)
+        try:
+            a1 = ctx.corr_softmax_warp(th, ph, V, T)    # prepares the exemplar side
+            a2 = ctx.corr_softmax_warp(th2, ph, V, T)   # reuses it
+            assert all(torch.equal(x, y) for x, y in zip(ref1 + ref2, a1 + a2))
+            ph.copy_(torch.nn.functional.normalize(torch.randn(1, 256, 600, generator=gen), dim=1))  # new exemplar, same buffer
+            ctx.debug_flag("corr_phi_static", 1)        # re-arm: the next call prepares it afresh
+            b1 = ctx.corr_softmax_warp(th, ph, V, T)
+        finally:
+            ctx.debug_flag("corr_phi_static", 0)
+        assert all(torch.equal(x, y) for x, y in zip(ctx.corr_softmax_warp(th, ph, V, T), b1))
+        assert not torch.equal(b1[1], a1[1])
+
+
 def test_corr_golden_operands(ctx):
     g = load_golden("small_32x48")
     y, sim, am = ctx.corr_softmax_warp(cu(g["theta_hat32"]), cu(g["phi_hat32"]), cu(g["V32"]), 1e-10, want_argmax=True)
