@@ -127,6 +127,7 @@ struct TcParams {
   int NA, NB, B, Bphi, C;
   int tiles_per_split;
   float sc;  // log2(e) / T
+  const float* row_sc;  // optional per-query-row log2(e) / T_i (overrides sc): the contextual loss normalises every row by its own minimum distance
   float out_scale;  // scores in TMEM are true scores / out_scale (2^-28 for pre-scaled fp16 operands, else 1)
   const float4* V;
   SplitOut* part;  // [nsplit][B*NA]
@@ -382,7 +383,8 @@ __global__ void __launch_bounds__(Epi<SOFTMAX>::NTHREADS, 1)
     constexpr int COLS = BN / Epi<SOFTMAX>::HALVES;     // columns per thread and tile
     const int row_local = q * 32 + lane;
     const int row = m0 + row_local;
-    const float sck = p.sc * p.out_scale;  // exponent scale in units of the (possibly pre-scaled) TMEM scores
+    // exponent scale in units of the (possibly pre-scaled) TMEM scores
+    const float sck = (p.row_sc ? __ldg(p.row_sc + (size_t)b * p.NA + min(m0 + q * 32 + lane, p.NA - 1)) : p.sc) * p.out_scale;
     float run_m = -INFINITY;
     // argmax: number of bit-equal maxima and the sum of their V rows; softmax: (a0, a1) and (a2, s) as packed pairs
     float cnt = 0.f, t0s = 0.f, t1s = 0.f, t2s = 0.f;
@@ -839,11 +841,12 @@ __global__ void __launch_bounds__(256) corr_rescore_kernel(const float* __restri
 // ---- merge the column-range splits ----------------------------------------------------------------------
 template <bool SOFTMAX>
 __global__ void __launch_bounds__(256) corr_merge_kernel(const SplitOut* __restrict__ part, int nsplit, int rows, int NA,
-                                                         int NB, int Bphi, float sc, const float4* __restrict__ V,
-                                                         float4* __restrict__ y, float* __restrict__ sim,
-                                                         int* __restrict__ argmax, const CorrPeers peers) {
+                                                         int NB, int Bphi, float sc_all, const float* __restrict__ row_sc,
+                                                         const float4* __restrict__ V, float4* __restrict__ y, float* __restrict__ sim,
+                                                         int* __restrict__ argmax, float* __restrict__ denom, const CorrPeers peers) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
+  const float sc = row_sc ? row_sc[r] : sc_all;
   const int b = r / NA;
   const float4* Vg = V + (size_t)((Bphi == 1) ? 0 : b) * NB;
   if (!SOFTMAX) {
@@ -882,6 +885,7 @@ __global__ void __launch_bounds__(256) corr_merge_kernel(const SplitOut* __restr
     }
     y[r] = make_float4(a0 / ssum, a1 / ssum, a2 / ssum, 0.f);
     sim[r] = m;
+    if (denom) denom[r] = ssum;  // sum_j exp((f_ij - m_i) / T_i)
     if (argmax) argmax[r] = -1;
     for (int g = 0; g < peers.n; ++g) {
       reinterpret_cast<float4*>(peers.y4[g])[peers.row0 + r] = make_float4(a0 / ssum, a1 / ssum, a2 / ssum, 0.f);
@@ -984,7 +988,7 @@ int launch_corr_tc(const CorrParams& p, int math, int cluster, int screen, CorrW
   };
   const bool tf32 = (math == 1);
   const int fmt = math == 1 ? 0 : (math == 2 ? 1 : 2);  // DVC_MATH_TF32X3 / BF16X3 / FP16X3
-  if (p.C != 256) return fail("C must be 256");
+  if (p.C < 64 || p.C % 64 || p.C > 4096) return fail("C must be a multiple of 64 (<= 4096)");
   const int eb = tf32 ? 4 : 2;
   const size_t ea = (size_t)p.B * p.NA * p.C, ephi = (size_t)p.Bphi * p.NB * p.C;
   void *Ah, *Al, *Bh, *Bl, *part;
@@ -1011,8 +1015,8 @@ int launch_corr_tc(const CorrParams& p, int math, int cluster, int screen, CorrW
   }
   const int tps = (ntiles + nsplit - 1) / nsplit;
   nsplit = (ntiles + tps - 1) / tps;
-  const bool softmax = !(p.temperature <= 2e-10f);
-  if (screen && fmt == 2 && !softmax) {
+  const bool softmax = !(p.temperature <= 2e-10f) || p.row_scale != nullptr;
+  if (screen && fmt == 2 && !softmax && p.C == 256) {  // (the resident query tile of the screening kernel is sized for C = 256)
     // ---- screened T -> 0 path: hi planes + error norms, one fp16 pass, exact re-scoring of the candidates ----
     const int rows = p.B * p.NA, rphi = p.Bphi * p.NB;
     void *norms, *cand;
@@ -1078,6 +1082,7 @@ int launch_corr_tc(const CorrParams& p, int math, int cluster, int screen, CorrW
   TcParams tp;
   tp.NA = p.NA, tp.NB = p.NB, tp.B = p.B, tp.Bphi = p.Bphi, tp.C = p.C, tp.tiles_per_split = tps;
   tp.sc = 1.4426950408889634f / p.temperature;
+  tp.row_sc = p.row_scale;
   tp.out_scale = fmt == 2 ? 3.725290298461914e-09f /* 2^-28 */ : 1.0f;
   tp.V = reinterpret_cast<const float4*>(p.V);
   tp.part = reinterpret_cast<SplitOut*>(part);
@@ -1093,11 +1098,11 @@ int launch_corr_tc(const CorrParams& p, int math, int cluster, int screen, CorrW
   launch_counter_add(1);
   const int rows = p.B * p.NA;
   if (softmax)
-    corr_merge_kernel<true><<<(rows + 255) / 256, 256, 0, s>>>(tp.part, nparts, rows, p.NA, p.NB, p.Bphi, tp.sc, tp.V,
-                                                                reinterpret_cast<float4*>(p.y), p.sim, p.argmax, p.peers);
+    corr_merge_kernel<true><<<(rows + 255) / 256, 256, 0, s>>>(tp.part, nparts, rows, p.NA, p.NB, p.Bphi, tp.sc, p.row_scale, tp.V,
+                                                                reinterpret_cast<float4*>(p.y), p.sim, p.argmax, p.denom, p.peers);
   else
-    corr_merge_kernel<false><<<(rows + 255) / 256, 256, 0, s>>>(tp.part, nparts, rows, p.NA, p.NB, p.Bphi, tp.sc, tp.V,
-                                                                 reinterpret_cast<float4*>(p.y), p.sim, p.argmax, p.peers);
+    corr_merge_kernel<false><<<(rows + 255) / 256, 256, 0, s>>>(tp.part, nparts, rows, p.NA, p.NB, p.Bphi, tp.sc, nullptr, tp.V,
+                                                                 reinterpret_cast<float4*>(p.y), p.sim, p.argmax, nullptr, p.peers);
   launch_counter_add(1);
   return 0;
 }

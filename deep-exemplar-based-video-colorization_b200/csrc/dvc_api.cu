@@ -1433,7 +1433,8 @@ extern "C" int dvc_corr_softmax_warp(dvc_ctx* c, const float* theta_hat, const f
                                      int Bphi, int NA, int NB, int C, float temperature, float* y, float* sim,
                                      int32_t* argmax, void* stream) {
   if (!c || !theta_hat || !phi_hat || !V || !y || !sim) return c ? fail(c, DVC_ERR_ARG, "corr: bad argument") : DVC_ERR_ARG;
-  if (C != 256) return fail(c, DVC_ERR_SHAPE, "corr: C must be 256 (WarpNet.inter_channels)");
+  if (C < 64 || C % 64 || C > 4096) return fail(c, DVC_ERR_SHAPE, "corr: C must be a multiple of 64 (WarpNet.inter_channels is 256)");
+  if (C != 256 && c->corr_math == DVC_MATH_FP32) return fail(c, DVC_ERR_SHAPE, "corr: the CUDA-core twin is built for C = 256");
   if (B < 1 || NA < 1 || NB < 1 || (Bphi != B && Bphi != 1)) return fail(c, DVC_ERR_SHAPE, "corr: bad sizes");
   if (!(temperature > 0.f)) return fail(c, DVC_ERR_ARG, "corr: temperature must be > 0");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1777,6 +1778,50 @@ extern "C" int dvc_rgb8_to_lab(dvc_ctx* c, const unsigned char* dev_rgb, int B, 
   CUDA_TRY(c, cudaSetDevice(c->device));
   launch_rgb8_to_lab(dev_rgb, dev_lab, B, H, W, (cudaStream_t)stream);
   return check_launch(c, "rgb8_to_lab");
+}
+
+// ---- ContextualLoss_forward (models/ContextualLoss.py:82-126; train.py's default "forward" direction), forward value only --
+// CX_b = mean_i max_j A_ij, A_ij = w_ij / sum_j w_ij, w_ij = exp((1 - d_ij / (min_j d_ij + 1e-5)) / h), d = 1 - X^T Y on centred,
+// unit-norm feature columns.  With m_i = max_j f_ij (f = X^T Y): max_j A_ij = 1 / sum_j exp((f_ij - m_i) / T_i),
+// T_i = h (1 - m_i + 1e-5) -- the row maximum (first pass of K7) and then K7's online softmax with a per-row temperature.
+extern "C" int dvc_contextual_loss_forward(dvc_ctx* c, const float* dev_X, const float* dev_Y, int B, int C, int NX, int NY, float h,
+                                           int feature_centering, float* dev_loss, void* stream) {
+  if (!c || !dev_X || !dev_Y || !dev_loss || B < 1 || NX < 1 || NY < 1) return c ? fail(c, DVC_ERR_ARG, "contextual_loss: bad argument") : DVC_ERR_ARG;
+  if (C < 64 || C % 64 || C > 4096) return fail(c, DVC_ERR_SHAPE, "contextual_loss: the feature depth must be a multiple of 64");
+  if (!(h > 0.f)) return fail(c, DVC_ERR_ARG, "contextual_loss: the bandwidth h must be > 0");
+  if (c->corr_math == DVC_MATH_FP32) return fail(c, DVC_ERR_STATE, "contextual_loss: needs a tensor-core correlation mode");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(c, cudaSetDevice(c->device));
+  void *mean, *xr, *yr, *V4, *y4, *m, *rsc, *den;
+  DVC_TRY(get_raw(c, "ctx.mean", (size_t)B * C * 4, &mean, s));
+  DVC_TRY(get_raw(c, "ctx.xrows", (size_t)B * NX * C * 4, &xr, s));
+  DVC_TRY(get_raw(c, "ctx.yrows", (size_t)B * NY * C * 4, &yr, s));
+  DVC_TRY(get_raw(c, "ctx.V4", (size_t)B * NY * 16, &V4, s));
+  DVC_TRY(get_raw(c, "ctx.y4", (size_t)B * NX * 16, &y4, s));
+  DVC_TRY(get_raw(c, "ctx.m", (size_t)B * NX * 4, &m, s));
+  DVC_TRY(get_raw(c, "ctx.rsc", (size_t)B * NX * 4, &rsc, s));
+  DVC_TRY(get_raw(c, "ctx.den", (size_t)B * NX * 4, &den, s));
+  // both X and Y are centred by Y's channel means (ContextualLoss.py:99-104), then every position is scaled to unit norm
+  if (feature_centering) {
+    launch_chan_mean(dev_Y, (float*)mean, B, C, NY, s);
+    DVC_TRY(check_launch(c, "chan_mean"));
+  }
+  const float eps = 2.220446049250313e-16f;
+  launch_center_norm_rows(dev_X, feature_centering ? (const float*)mean : nullptr, (float*)xr, B, C, NX, eps, s);
+  launch_center_norm_rows(dev_Y, feature_centering ? (const float*)mean : nullptr, (float*)yr, B, C, NY, eps, s);
+  DVC_TRY(check_launch(c, "center_norm_rows"));
+  launch_pack_v4(nullptr, (float*)V4, (size_t)B * NY, s);  // only the 4th lane (= 1) of the "colour" rows matters here
+  CorrParams p{};
+  p.theta = (float*)xr, p.phi = (float*)yr, p.V = (float*)V4, p.B = B, p.Bphi = B, p.NA = NX, p.NB = NY, p.C = C;
+  p.y = (float*)y4, p.sim = (float*)m, p.argmax = nullptr;
+  p.temperature = 1e-10f;  // pass 1: m_i = max_j f_ij
+  DVC_TRY(run_corr(c, p, s));
+  launch_ctx_row_scale((const float*)m, (float*)rsc, (size_t)B * NX, h, s);
+  DVC_TRY(check_launch(c, "ctx_row_scale"));
+  p.temperature = 1.0f, p.row_scale = (const float*)rsc, p.denom = (float*)den;  // pass 2: sum_j exp((f_ij - m_i) / T_i)
+  DVC_TRY(run_corr(c, p, s));
+  launch_ctx_loss((const float*)den, dev_loss, B, NX, s);
+  return check_launch(c, "ctx_loss");
 }
 
 // ---- Fast Global Smoother ("WLS filter", test.py:105-112) ---------------------------------------------------------

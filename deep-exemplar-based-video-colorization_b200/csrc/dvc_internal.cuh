@@ -214,7 +214,17 @@ struct CorrParams {
   float* sim;   // [B][NA]
   int* argmax;  // [B][NA] or nullptr
   CorrPeers peers;  // optional fused all-gather of (y, sim) rows (B = 1 only)
+  // tensor-core kernels only: per-query-row exponent scale log2(e) / T_i (forces the softmax epilogue, `temperature` is
+  // ignored) and the softmax denominators sum_j exp((f_ij - max_j f_ij) / T_i) -- the contextual loss (ContextualLoss.py:115-126)
+  const float* row_scale = nullptr;  // [B][NA]
+  float* denom = nullptr;            // [B][NA]
 };
+// contextual-loss helpers (prepost.cu): channel means over positions, centred + L2-normalised position-major rows,
+// per-row exponent scales from the row maxima, the final -log(mean_i 1 / denom_i)
+void launch_chan_mean(const float* x, float* mean, int B, int C, int N, cudaStream_t s);
+void launch_center_norm_rows(const float* x, const float* mean, float* rows, int B, int C, int N, float eps, cudaStream_t s);
+void launch_ctx_row_scale(const float* rowmax, float* row_sc, size_t n, float h, cudaStream_t s);
+void launch_ctx_loss(const float* denom, float* loss, int B, int N, cudaStream_t s);
 void launch_corr_simt(const CorrParams& p, cudaStream_t s);
 // [B][C][N] -> [B][N][C] and back (the C ABI of the stand-alone correlation entry is channel-major)
 void launch_transpose_cn(const float* src, float* dst, int B, int C, int N, cudaStream_t s);

@@ -205,6 +205,82 @@ __global__ void __launch_bounds__(256) zoom_crop_kernel(const double* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------ contextual loss
+// mean over the N positions of every (image, channel): one block per (b, c), double accumulation
+__global__ void __launch_bounds__(256) chan_mean_kernel(const float* __restrict__ x, float* __restrict__ mean, int N) {
+  __shared__ double red[256];
+  const float* p = x + (size_t)blockIdx.x * N;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < N; i += 256) acc += (double)__ldg(p + i);
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) mean[blockIdx.x] = (float)(red[0] / N);
+}
+
+// NCHW [B][C][N] -> position-major rows [B][N][C] of (x - mean_c) / (||x - mean||_2 over C + eps)  (ContextualLoss.py:99-111,
+// feature_normalize util.py:155-158).  One block = 32 positions: first the norms (reads coalesced over positions), then a
+// 32 x 32 shared-memory transpose per channel group so that the row stores are contiguous.
+__global__ void __launch_bounds__(256) center_norm_rows_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                               float* __restrict__ rows, int C, int N, float eps) {
+  __shared__ float tile[32][33];
+  __shared__ float s_inv[32];
+  __shared__ float s_part[8][32];
+  const int b = blockIdx.y, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* xb = x + (size_t)b * C * N;
+  const float* mb = mean ? mean + (size_t)b * C : nullptr;
+  const int n = n0 + tx;
+  float ss = 0.f;
+  for (int c = ty; c < C; c += 8) {
+    const float v = (n < N ? __ldg(xb + (size_t)c * N + n) : 0.f) - (mb ? __ldg(mb + c) : 0.f);
+    ss = fmaf(v, v, ss);
+  }
+  s_part[ty][tx] = ss;
+  __syncthreads();
+  if (ty == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += s_part[k][tx];
+    s_inv[tx] = 1.f / (sqrtf(t) + eps);
+  }
+  __syncthreads();
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    for (int k = ty; k < 32; k += 8) {  // channel c0 + k, position n0 + tx
+      const int c = c0 + k;
+      tile[k][tx] = (c < C && n < N) ? (__ldg(xb + (size_t)c * N + n) - (mb ? __ldg(mb + c) : 0.f)) * s_inv[tx] : 0.f;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {  // position n0 + k, channel c0 + tx
+      if (n0 + k < N && c0 + tx < C) rows[((size_t)b * N + n0 + k) * C + c0 + tx] = tile[tx][k];
+    }
+    __syncthreads();
+  }
+}
+
+// log2(e) / T_i with T_i = h * (min_j d_ij + 1e-5) = h * (1 - max_j f_ij + 1e-5)   (ContextualLoss.py:118-122)
+__global__ void __launch_bounds__(256) ctx_row_scale_kernel(const float* __restrict__ rowmax, float* __restrict__ row_sc, size_t n, float h) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    row_sc[i] = 1.4426950408889634f / (h * ((1.f - __ldg(rowmax + i)) + 1e-5f));
+}
+
+// loss_b = -log(mean_i max_j A_ij) with max_j A_ij = 1 / sum_j exp((f_ij - m_i) / T_i)   (ContextualLoss.py:123-126)
+__global__ void __launch_bounds__(256) ctx_loss_kernel(const float* __restrict__ denom, float* __restrict__ loss, int N) {
+  __shared__ double red[256];
+  const float* p = denom + (size_t)blockIdx.x * N;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < N; i += 256) acc += 1.0 / (double)__ldg(p + i);
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[blockIdx.x] = (float)(-log(red[0] / N));
+}
+
 inline int grid_for(size_t total, int threads, int cap = 148 * 16) {
   const size_t g = (total + threads - 1) / threads;
   return (int)(g < (size_t)cap ? (g ? g : 1) : cap);
@@ -212,6 +288,22 @@ inline int grid_for(size_t total, int threads, int cap = 148 * 16) {
 
 }  // namespace
 
+void launch_chan_mean(const float* x, float* mean, int B, int C, int N, cudaStream_t s) {
+  chan_mean_kernel<<<B * C, 256, 0, s>>>(x, mean, N);
+  launch_counter_add(1);
+}
+void launch_center_norm_rows(const float* x, const float* mean, float* rows, int B, int C, int N, float eps, cudaStream_t s) {
+  center_norm_rows_kernel<<<dim3((N + 31) / 32, B), 256, 0, s>>>(x, mean, rows, C, N, eps);
+  launch_counter_add(1);
+}
+void launch_ctx_row_scale(const float* rowmax, float* row_sc, size_t n, float h, cudaStream_t s) {
+  ctx_row_scale_kernel<<<grid_for(n, 256), 256, 0, s>>>(rowmax, row_sc, n, h);
+  launch_counter_add(1);
+}
+void launch_ctx_loss(const float* denom, float* loss, int B, int N, cudaStream_t s) {
+  ctx_loss_kernel<<<B, 256, 0, s>>>(denom, loss, N);
+  launch_counter_add(1);
+}
 void launch_fgs_weights(const unsigned char* guide, const float* lut, float* Ch, float* Cv, int H, int W, cudaStream_t s) {
   fgs_weights_kernel<<<grid_for((size_t)H * W, 256), 256, 0, s>>>(guide, lut, Ch, Cv, H, W);
   launch_counter_add(1);

@@ -23,7 +23,7 @@ EXPORTED = [
     "dvc_exemplar_export", "dvc_exemplar_import", "dvc_launch_count", "dvc_profile_corr", "dvc_corr_mean_ms",
     "dvc_debug_set_flag", "dvc_debug_get_buffer", "dvc_debug_conv2d", "dvc_profile_conv", "dvc_conv_profile",
     "dvc_resize_half", "dvc_upsample2_scaled", "dvc_lab_to_rgb8", "dvc_rgb8_to_lab",
-    "dvc_fgs_filter", "dvc_l_to_guide8", "dvc_resize_antialias_crop_rgb8",
+    "dvc_fgs_filter", "dvc_l_to_guide8", "dvc_resize_antialias_crop_rgb8", "dvc_contextual_loss_forward",
     "dvc_peer_buffer_create", "dvc_peer_buffer_open", "dvc_peer_buffer_close", "dvc_peer_buffer_destroy",
     "dvc_corr_set_peer_outputs",
 ]
@@ -84,6 +84,7 @@ def load_library():
         lib.dvc_l_to_guide8.argtypes = [c_void, c_void, c_int, c_int, c_void, c_void]
         lib.dvc_resize_antialias_crop_rgb8.argtypes = [c_void, c_void, c_int, c_int, c_int, c_int, c_int, c_int, c_void, c_int, c_int,
                                                        c_void]
+        lib.dvc_contextual_loss_forward.argtypes = [c_void, c_void, c_void, c_int, c_int, c_int, c_int, c_float, c_int, c_void, c_void]
         lib.dvc_peer_buffer_create.argtypes = [c_void, c_i64, P(c_void), ctypes.c_char_p]
         lib.dvc_peer_buffer_open.argtypes = [c_void, ctypes.c_char_p, P(c_void)]
         lib.dvc_peer_buffer_close.argtypes = [c_void, c_void]
@@ -312,6 +313,19 @@ class Context:
         out = torch.empty(B, 3, H, W, device=rgb.device, dtype=torch.float32)
         self._check(self.lib.dvc_rgb8_to_lab(self.h, ctypes.c_void_p(rgb.data_ptr()), B, H, W, _ptr(out), _stream(rgb.device)),
                     "dvc_rgb8_to_lab")
+        return out
+
+    def contextual_loss_forward(self, X_features, Y_features, h=0.1, feature_centering=True):
+        """ContextualLoss_forward.forward (models/ContextualLoss.py:82-126), value only: CUDA float32 [B,C,h,w] (or [B,C,N])
+        feature maps -> loss [B]."""
+        X, Y = _dev_f32(X_features, "contextual_loss X"), _dev_f32(Y_features, "contextual_loss Y")
+        B, C = X.shape[0], X.shape[1]
+        if Y.shape[0] != B or Y.shape[1] != C:
+            raise DvcError("contextual_loss: X and Y must share batch size and feature depth")
+        NX, NY = X[0, 0].numel(), Y[0, 0].numel()
+        out = torch.empty(B, device=X.device, dtype=torch.float32)
+        self._check(self.lib.dvc_contextual_loss_forward(self.h, _ptr(X), _ptr(Y), B, C, NX, NY, float(h), 1 if feature_centering else 0,
+                                                         _ptr(out), _stream(X.device)), "dvc_contextual_loss_forward")
         return out
 
     def fgs_filter(self, guide, src, lam=500.0, sigma_color=4.0, lambda_attenuation=0.25, num_iter=3):

@@ -97,7 +97,8 @@ int dvc_colorvidnet_forward(dvc_ctx* ctx, const float* dev_x, int B, int H, int 
 /* f = theta_hat^T phi_hat; sim = rowmax f; P = softmax_j(f/T); y = P V   (NonlocalNet.py:477-498)
  * dev_theta_hat [B,C,NA], dev_phi_hat [Bphi,C,NB] (Bphi == B or 1: one exemplar shared by B frames),
  * dev_V [Bphi,NB,3]; outputs dev_y [B,NA,3], dev_sim [B,NA]; dev_argmax [B,NA] int32 may be NULL.
- * C must be 256 (WarpNet.inter_channels, NonlocalNet.py:360). */
+ * C must be a multiple of 64 (256 = WarpNet.inter_channels, NonlocalNet.py:360; other depths, e.g. the patch features of
+ * NonlocalWeightedAverage, NonlocalNet.py:95-108, take the exact 3-pass kernel). */
 int dvc_corr_softmax_warp(dvc_ctx* ctx, const float* dev_theta_hat, const float* dev_phi_hat,
                           const float* dev_V, int B, int Bphi, int NA, int NB, int C, float temperature,
                           float* dev_y, float* dev_sim, int32_t* dev_argmax, void* stream);
@@ -143,6 +144,14 @@ int dvc_lab_to_rgb8(dvc_ctx* ctx, const float* dev_l, const float* dev_ab, int B
  * skimage.color.rgb2lab in float64 (uint8 / 255, inverse sRGB gamma, xyz_from_rgb, D65 / 2-degree white point,
  * 0.008856 cube-root threshold), cast to float32, then L - 50.  dev_rgb [B,H,W,3] uint8 -> dev_lab [B,3,H,W]. */
 int dvc_rgb8_to_lab(dvc_ctx* ctx, const unsigned char* dev_rgb, int B, int H, int W, float* dev_lab, void* stream);
+
+/* ContextualLoss_forward.forward(X_features, Y_features, h, feature_centering) (models/ContextualLoss.py:82-126; the default
+ * "forward" matching direction of train.py:79), VALUE ONLY -- no backward pass, so it serves evaluation, not training.
+ * dev_X [B,C,NX], dev_Y [B,C,NY] (the reference's [B,C,h,w] feature maps, positions flattened), C a multiple of 64;
+ * dev_loss [B] = -log(mean_i max_j A_ij).  Runs K7 twice: row maxima, then the online softmax with the per-row temperature
+ * h * (1 - max_j f_ij + 1e-5).  Needs a tensor-core correlation mode. */
+int dvc_contextual_loss_forward(dvc_ctx* ctx, const float* dev_X, const float* dev_Y, int B, int C, int NX, int NY, float h,
+                                int feature_centering, float* dev_loss, void* stream);
 
 /* The "WLS filter" of test.py:105-112: cv2.ximgproc.createFastGlobalSmootherFilter(guide, lambda, sigma_color,
  * lambda_attenuation = 0.25, num_iter = 3).filter(plane) for `planes` fp32 planes [planes,H,W] sharing one single-channel uint8

@@ -380,3 +380,21 @@ def legal_shape(H, W):
 def corr_flops(NA, NB, C=256, ch=3):
     """Algorithmic FLOPs of the correlation + warp: 2*NA*NB*(C+ch)."""
     return 2.0 * NA * NB * (C + ch)
+
+
+def contextual_loss_forward(X_features, Y_features, h=0.1, feature_centering=True):
+    """ContextualLoss_forward.forward, models/ContextualLoss.py:82-126, line by line (train.py's default matching direction).
+    X_features, Y_features [B,C,h,w]; returns the per-sample loss [B]."""
+    batch_size, feature_depth = X_features.shape[0], X_features.shape[1]
+    if feature_centering:
+        mean_y = Y_features.view(batch_size, feature_depth, -1).mean(dim=-1).unsqueeze(dim=-1).unsqueeze(dim=-1)
+        X_features = X_features - mean_y
+        Y_features = Y_features - mean_y
+    X = feature_normalize(X_features).view(batch_size, feature_depth, -1)
+    Y = feature_normalize(Y_features).view(batch_size, feature_depth, -1)
+    d = 1 - torch.matmul(X.permute(0, 2, 1), Y)
+    d_norm = d / (torch.min(d, dim=-1, keepdim=True)[0] + 1e-5)
+    w = torch.exp((1 - d_norm) / h)
+    A_ij = w / torch.sum(w, dim=-1, keepdim=True)
+    CX = torch.mean(torch.max(A_ij, dim=-1)[0], dim=1)
+    return -torch.log(CX)

@@ -51,10 +51,14 @@ def load():
             from models.ColorVidNet import ColorVidNet
             from models.FrameColor import frame_colorization
             from utils.util import tensor_lab2rgb, uncenter_l, feature_normalize, gray2rgb_batch
+            try:  # training-side consumer of the dense contraction; needs torchvision at import
+                from models.ContextualLoss import ContextualLoss_forward
+            except Exception:  # pragma: no cover
+                ContextualLoss_forward = None
         ns = types.SimpleNamespace(
             WarpNet=WarpNet, VGG19_pytorch=VGG19_pytorch, ColorVidNet=ColorVidNet,
             frame_colorization=frame_colorization, tensor_lab2rgb=tensor_lab2rgb, uncenter_l=uncenter_l,
-            feature_normalize=feature_normalize, gray2rgb_batch=gray2rgb_batch,
+            feature_normalize=feature_normalize, gray2rgb_batch=gray2rgb_batch, ContextualLoss_forward=ContextualLoss_forward,
         )
     finally:
         sys.path[:] = saved_path

@@ -225,6 +225,45 @@ def test_corr_static_exemplar_side(ctx, corr_math):
         assert not torch.equal(b1[1], a1[1])
 
 
+@pytest.mark.parametrize("B,C,h,w", [(2, 256, 24, 32), (1, 128, 40, 40), (1, 512, 20, 24), (1, 256, 64, 64)])
+def test_contextual_loss_forward_vs_oracle(ctx, B, C, h, w):
+    """SURVEY.md §8f row 4 (value only): ContextualLoss_forward on K7 -- row maxima, then the online softmax with a per-row
+    temperature -- against the fp64 evaluation of the reference's formula; the reference's own fp32 run is the yardstick."""
+    import dvc
+
+    ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
+    g = torch.Generator().manual_seed(C + h)
+    X = torch.relu(torch.randn(B, C, h, w, generator=g))
+    Y = torch.relu(torch.randn(B, C, h, w, generator=g) + 0.5 * X)   # VGG-like non-negative maps, correlated content
+    for centering in (True, False):
+        with torch.no_grad():
+            ref64 = O.contextual_loss_forward(X.double(), Y.double(), 0.1, centering)
+            ref32 = O.contextual_loss_forward(X, Y, 0.1, centering)
+        out = ctx.contextual_loss_forward(X.cuda(), Y.cuda(), 0.1, centering).cpu().double()
+        floor = (ref32.double() - ref64).abs().max().item()
+        err = (out - ref64).abs().max().item()
+        assert err <= max(2e-4 * ref64.abs().max().item(), 4 * floor), (err, floor, ref64)
+
+
+def test_corr_other_feature_depths(ctx):
+    """The stand-alone K7 entry at C != 256 (e.g. the 3x3-patch features of NonlocalWeightedAverage, NonlocalNet.py:95-108)."""
+    import dvc
+
+    ctx.set_math(conv=dvc.MATH_TF32X3, corr=dvc.MATH_FP16X3)
+    for C in (64, 128, 576):
+        gen = torch.Generator().manual_seed(C)
+        th = torch.nn.functional.normalize(torch.randn(1, C, 300, generator=gen), dim=1)
+        ph = torch.nn.functional.normalize(torch.randn(1, C, 450, generator=gen), dim=1)
+        V = torch.randn(1, 450, 3, generator=gen) * 30
+        for T in (1e-10, 0.1):
+            y, sim = ctx.corr_softmax_warp(th.cuda(), ph.cuda(), V.cuda(), T)
+            yo, so = O.corr_softmax_warp(th.double(), ph.double(), V.double(), T)
+            assert (sim.cpu().double() - so).abs().max() < 2e-6
+            gap = O.top2_gap(th.double(), ph.double())[0]
+            ok = gap > 1e-5 if T < 1e-9 else torch.ones_like(gap, dtype=torch.bool)
+            assert (y.cpu().double()[0][ok] - yo[0][ok]).abs().max() < 2e-3
+
+
 def test_corr_golden_operands(ctx):
     g = load_golden("small_32x48")
     y, sim, am = ctx.corr_softmax_warp(cu(g["theta_hat32"]), cu(g["phi_hat32"]), cu(g["V32"]), 1e-10, want_argmax=True)

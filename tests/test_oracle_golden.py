@@ -131,3 +131,22 @@ def test_rgb8_to_lab_oracle_anchors():
     lab = O.rgb8_to_lab(rgb)
     back = O.lab_to_rgb8(lab[:, 0:1], lab[:, 1:3])
     assert int((back.int() - rgb.int()).abs().max()) <= 1
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_contextual_loss_restatement_is_the_reference():
+    """oracle.contextual_loss_forward == models/ContextualLoss.py: ContextualLoss_forward of the unmodified reference, bit for
+    bit (same torch ops in the same order), on seeded feature maps of several depths."""
+    ns = ref_import.load()
+    if ns.ContextualLoss_forward is None:
+        pytest.skip("reference ContextualLoss could not be imported (torchvision)")
+    mod = ns.ContextualLoss_forward()
+    g = torch.Generator().manual_seed(31)
+    for (B, C, h, w) in ((2, 128, 12, 16), (1, 256, 16, 16), (1, 512, 8, 12)):
+        X = torch.relu(torch.randn(B, C, h, w, generator=g))
+        Y = torch.relu(torch.randn(B, C, h, w, generator=g) + 0.3 * X)
+        for centering in (True, False):
+            with torch.no_grad():
+                ref = mod(X.clone(), Y.clone(), 0.1, centering)
+                mine = O.contextual_loss_forward(X, Y, 0.1, centering)
+            assert torch.equal(ref, mine), (ref, mine)
