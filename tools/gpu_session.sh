@@ -25,6 +25,10 @@ for S in $STEPS; do
     bench3rs) timeout 600 python bench.py --steps 20 --warmup 5 --clip-astreams 2 --tc-rowshare 1 --cpu-sample 0 --clip-frames 0 > $O/${TAG}_bench3rs.json 2> $O/${TAG}_bench3rs.err ;;
     benchN)   NG=$(nvidia-smi -L | wc -l); timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29711 \
                 bench.py --gpus $NG --steps 20 --warmup 5 --cpu-sample 0 > $O/${TAG}_bench${NG}gpu.json 2> $O/${TAG}_bench${NG}gpu.err ;;
+    sanitize) for tool in memcheck racecheck synccheck initcheck; do
+                timeout 900 compute-sanitizer --tool $tool --error-exitcode 1 python tools/sanitize_small.py > $O/${TAG}_sanitize_$tool.log 2>&1
+                echo "  sanitizer $tool rc=$? $(grep -c 'ERROR SUMMARY' $O/${TAG}_sanitize_$tool.log)" >> $O/${TAG}_steps.log; tail -n 3 $O/${TAG}_sanitize_$tool.log >> $O/${TAG}_steps.log
+              done ;;
     multi)    timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -s -p no:cacheprovider > $O/${TAG}_multi.log 2>&1 ;;
     *) echo "unknown step $S" ;;
   esac
