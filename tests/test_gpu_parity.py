@@ -392,6 +392,12 @@ def test_fused_clip_recurrence(ctx, conv_math):
         ab = ctx.colorize_frames(L, last)
         assert torch.equal(ab.cpu(), out[t:t + 1])
         last = torch.cat((L, ab), 1)
+    # free-running against the reference's free-running clip: frame 0 has no history and must match; afterwards the
+    # recurrence is chaotic (two bit-different fp32 runs of the REFERENCE are 0.4 apart by frame 3, its 1- vs
+    # 8-thread runs 1.5e-3 apart on a single frame), so the later frames are reported, not gated
+    free = [float(np.abs(out[t].numpy() - ref[t]).max()) for t in range(frames.shape[0])]
+    print(f"free-running |ab - reference| per frame ({conv_math}): " + ", ".join(f"{v:.2e}" for v in free))
+    assert free[0] < 5e-3
     # teacher forcing against the reference's own outputs
     last = torch.zeros(1, 3, 32, 48, device="cuda")
     for t in range(frames.shape[0]):
