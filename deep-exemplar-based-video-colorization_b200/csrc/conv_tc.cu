@@ -233,17 +233,18 @@ __global__ void __launch_bounds__(NTHREADS, 1)
           tc::mbar_wait(&empty[stage], phase ^ 1);
           if (tc::elect_one()) {
             uint8_t* st = smem + stage * C::STAGE_BYTES;
+            const bool skip_lo = (p.dbg & 2) != 0;  // TIMING EXPERIMENT ONLY (wrong results): do not fetch the activation lo plane
             if (CL == 1) {
-              tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+              tc::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES - (skip_lo ? A_BYTES : 0));
               tc::tma_load_2d(st, &tmXh, &full[stage], kb * KE, m0 + off);
-              tc::tma_load_2d(st + A_BYTES, &tmXl, &full[stage], kb * KE, m0 + off);
+              if (!skip_lo) tc::tma_load_2d(st + A_BYTES, &tmXl, &full[stage], kb * KE, m0 + off);
               tc::tma_load_2d(st + 2 * A_BYTES, &tmWh, &full[stage], kb * KE, tap * p.CoutPad + n0);
               tc::tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tmWl, &full[stage], kb * KE, tap * p.CoutPad + n0);
             } else {  // my pixel rows and my half of the channel rows; all bytes are counted by the leader's barrier
-              if (crank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+              if (crank == 0) tc::mbar_arrive_expect_tx(&full[stage], 2 * (C::STAGE_BYTES - (skip_lo ? A_BYTES : 0)));
               const int hrow = crank * (BN / 2);
               tc::tma_load_2d_pair(st, &tmXh, &full[stage], kb * KE, m0 + off);
-              tc::tma_load_2d_pair(st + A_BYTES, &tmXl, &full[stage], kb * KE, m0 + off);
+              if (!skip_lo) tc::tma_load_2d_pair(st + A_BYTES, &tmXl, &full[stage], kb * KE, m0 + off);
               tc::tma_load_2d_pair(st + 2 * A_BYTES, &tmWh, &full[stage], kb * KE, tap * p.CoutPad + n0 + hrow);
               tc::tma_load_2d_pair(st + 2 * A_BYTES + C::B_BYTES, &tmWl, &full[stage], kb * KE, tap * p.CoutPad + n0 + hrow);
             }
@@ -273,7 +274,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             tc::mbar_wait(&full[R::A_STAGES + bs], bph);
             tc::tc_fence_after();
             // the tap's rows start (tap_off[tap] - tap_off[first tap of the row]) rows into the shared tile
-            const int shift = p.tap_off[ty * ntx + tx] - p.tap_off[ty * ntx];
+            // (p.dbg & 1: TIMING EXPERIMENT ONLY, wrong results -- every tap reads the tile at its aligned start)
+            const int shift = (p.dbg & 1) ? 0 : p.tap_off[ty * ntx + tx] - p.tap_off[ty * ntx];
             const uint32_t sa = tc::smem_u32(smem + as * R::A_STAGE) + (uint32_t)shift * 128u;
             const uint32_t sb = ringB + bs * R::B_STAGE;
             const uint64_t bo = p.rs_base_offset ? ((uint64_t)(shift & 7) << 49) : 0ull;

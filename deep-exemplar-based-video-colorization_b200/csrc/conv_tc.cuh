@@ -46,6 +46,7 @@ struct ConvTcParams {
   int rowshare;   // 1 / 2: the taps of one kernel row share one activation tile in shared memory (conv_tc.cu: CfgRS); 2 also
                   // sets the descriptors' base-offset field to the row shift; 0: one activation tile per tap
   int rs_ntx, rs_base_offset;  // filled by the launcher
+  int dbg;        // timing experiments (results are WRONG when set): 1 = row-shared taps without the row shift, 2 = no activation lo plane
 };
 
 int conv_tc_pick_bn(int cout);  // channel tile (64 / 128 / 256) used for `cout` output channels

@@ -139,6 +139,7 @@ struct dvc_ctx {
   CorrWorkspace corr_ws2;  // the same for the second phase-A stream of the clip driver (clip_astreams = 2)
   int clip_astreams = 1;   // clip driver: 1 = frame t+1's phase A overlaps frame t's ColorVidNet; 2 = frames t+1 AND t+2
   long long ex_version = 0;  // bumped whenever ex_phi's contents change (the correlation caches the exemplar's planes)
+  int tc_dbg = 0;         // timing experiments of the conv engine (wrong results): see ConvTcParams::dbg
   int tc_rowshare = 0;    // tensor-core convolutions: taps of a kernel row share one activation tile (conv_tc.cu: CfgRS)
   int tc_force_bn = 0;    // tests: channel tile (64 / 128 / 256) forced on every tensor-core convolution it divides
   int tc_tail = 0;        // tensor-core convolutions: 1 = 128-channel tiles for the partial last round of 256-channel
@@ -595,6 +596,7 @@ static int run_conv(dvc_ctx* c, const ConvW* w, const Act& x, Act& y, const Conv
     t.act = o.act, t.slope = o.slope, t.stats = o.stats, t.kc = c->tc_kc, t.cluster = c->tc_cluster, t.kbytes = c->tc_kbytes;
     t.tail = c->tc_tail;
     t.rowshare = c->tc_rowshare;
+    t.dbg = c->tc_dbg;
     t.force_bn = (c->tc_force_bn && !o.fin_w && w->cout_pad_tc % c->tc_force_bn == 0) ? c->tc_force_bn : 0;
     t.splits = c->tc_splits, t.ws = nullptr, t.flags = nullptr, t.epoch = 0;
     if (c->tc_splits != 1 && (c->tc_splits > 1 || t.Mtot <= 128 * 8 * c->num_sms)) {  // split-K hand-over workspace + flags of this phase's arena (L2-resident, reused by every layer)
@@ -1151,6 +1153,7 @@ extern "C" int dvc_debug_set_flag(dvc_ctx* c, const char* name, int value) {
   if (!strcmp(name, "tc_splits")) { c->tc_splits = value < 0 ? 0 : (value > 8 ? 8 : value); return DVC_OK; }
   if (!strcmp(name, "tc_kbytes")) { c->tc_kbytes = value == 64 ? 64 : 128; return DVC_OK; }
   if (!strcmp(name, "tc_cluster")) { c->tc_cluster = value == 2 ? 2 : 1; return DVC_OK; }
+  if (!strcmp(name, "tc_dbg")) { c->tc_dbg = value; return DVC_OK; }
   if (!strcmp(name, "tc_rowshare")) { c->tc_rowshare = value < 0 ? 0 : (value > 2 ? 2 : value); return DVC_OK; }
   if (!strcmp(name, "tc_force_bn")) {
     if (value != 0 && value != 64 && value != 128 && value != 256) return fail(c, DVC_ERR_ARG, "tc_force_bn must be 0, 64, 128 or 256");

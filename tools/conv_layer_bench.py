@@ -39,6 +39,10 @@ LAYERS = [
 VARIANTS = [("default", dict()), ("rowshare", dict(tc_rowshare=1)), ("bn128", dict(tc_force_bn=128)),
             ("bn128+rowshare", dict(tc_force_bn=128, tc_rowshare=1)), ("bn64+rowshare", dict(tc_force_bn=64, tc_rowshare=1)),
             ("bn256+rowshare", dict(tc_force_bn=256, tc_rowshare=1)), ("kc2", dict(tc_kc=2)), ("kc2+rowshare", dict(tc_kc=2, tc_rowshare=1))]
+if os.environ.get("DVC_LAYER_EXPERIMENTS"):  # timing-only experiments (results are wrong): which resource binds the tile?
+    VARIANTS = [("default", dict()), ("no-lo-plane", dict(tc_dbg=2)), ("rowshare", dict(tc_rowshare=1)),
+                ("rowshare-noshift", dict(tc_rowshare=1, tc_dbg=1)), ("single-cta", dict(tc_cluster=1)), ("kc2", dict(tc_kc=2)),
+                ("kc2+no-lo", dict(tc_kc=2, tc_dbg=2)), ("kc4", dict(tc_kc=4))]
 lines = []
 for label, net, name, cin, cout, H, W, kw in LAYERS:
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -47,9 +51,10 @@ for label, net, name, cin, cout, H, W, kw in LAYERS:
     flop = 2.0 * H * W * (4 if kw.get("upconv") else 1) * taps * cin * cout
     row = {"layer": label, "gflop": flop / 1e9}
     for vname, flags in VARIANTS:
-        for k in ("tc_rowshare", "tc_force_bn"):
+        for k in ("tc_rowshare", "tc_force_bn", "tc_dbg"):
             ctx.debug_flag(k, flags.get(k, 0))
         ctx.debug_flag("tc_kc", flags.get("tc_kc", 1))
+        ctx.debug_flag("tc_cluster", flags.get("tc_cluster", 2))
         ctx.debug_conv2d(net, name, x, cout, **kw)
         ctx.profile_conv(True)
         ctx.conv_profile(0, reset=True)
@@ -60,9 +65,10 @@ for label, net, name, cin, cout, H, W, kw in LAYERS:
         ctx.profile_conv(False)
         us = 1e3 * ms / args.reps
         row[vname] = {"us": us, "tflops": flop / us / 1e6}
-    for k in ("tc_rowshare", "tc_force_bn"):
+    for k in ("tc_rowshare", "tc_force_bn", "tc_dbg"):
         ctx.debug_flag(k, 0)
     ctx.debug_flag("tc_kc", 1)
+    ctx.debug_flag("tc_cluster", 2)
     lines.append(row)
     print(label, f"{row['gflop']:.1f} GF:", "  ".join(f"{v} {row[v]['us']:.1f}us ({row[v]['tflops']:.0f})" for v, _ in VARIANTS), flush=True)
 if args.out:

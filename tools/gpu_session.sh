@@ -29,6 +29,7 @@ for S in $STEPS; do
                 timeout 900 compute-sanitizer --tool $tool --error-exitcode 1 python tools/sanitize_small.py > $O/${TAG}_sanitize_$tool.log 2>&1
                 echo "  sanitizer $tool rc=$? $(grep -c 'ERROR SUMMARY' $O/${TAG}_sanitize_$tool.log)" >> $O/${TAG}_steps.log; tail -n 3 $O/${TAG}_sanitize_$tool.log >> $O/${TAG}_steps.log
               done ;;
+    layersx)  DVC_LAYER_EXPERIMENTS=1 timeout 300 python tools/conv_layer_bench.py > $O/${TAG}_layersx.log 2>&1 ;;
     multi)    timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -s -p no:cacheprovider > $O/${TAG}_multi.log 2>&1 ;;
     *) echo "unknown step $S" ;;
   esac
