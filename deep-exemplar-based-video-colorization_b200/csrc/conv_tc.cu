@@ -51,7 +51,8 @@ struct Cfg {
   static constexpr int B_BYTES = (BN / CL) * KBY;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int NBUF = 512 / BN;  // TMEM accumulators (2 / 4 / 8): deeper ring hides the flush round trip
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + 8 * BN * 4;  // + barriers + statistics [4][2][BN]
+  // + barriers + statistics [4][2][BN] (one area per warp set on the narrow, ping-pong tiles)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + 8 * BN * 4 * (BN <= 128 ? 2 : 1);
 };
 
 // Row-shared taps (RS): the three horizontal taps of a 3x3 row (two of a 2x2 phase-convolution row) read pixel rows
@@ -73,7 +74,7 @@ struct CfgRS {
   static constexpr int B_STAGES = (BN == 256) ? (CL == 2 ? 4 : 2) : (BN == 128 ? (CL == 2 ? 6 : 3) : (CL == 2 ? 9 : 6));
   static constexpr int RING_BYTES = A_STAGES * A_STAGE + B_STAGES * B_STAGE;
   static constexpr int NBUF = 512 / BN;
-  static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 512 + 8 * BN * 4;
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 512 + 8 * BN * 4 * (BN <= 128 ? 2 : 1);
 };
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -103,7 +104,18 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   constexpr int NFULL = RS ? (R::A_STAGES + R::B_STAGES) : C::STAGES;  // "full" barriers (then as many "empty" ones)
   constexpr int KE = F16 ? KBY / 2 : KBY / 4;  // K elements per stage
   constexpr uint32_t IDESC = tc::umma_idesc(F16 ? 0u : 2u, BM * CL, BN);
-  constexpr int CPT = BN / 2;  // output channels per epilogue thread (two warps share a TMEM lane quarter)
+  // Epilogue organisation.  256-channel tile: the two warps of a TMEM lane quarter split the tile's channels (CPT = 128 each).
+  // Narrow tiles (PP, "ping-pong"): the two warp SETS (one warp per lane quarter each) take ALTERNATE tiles, every thread
+  // owning all BN channels of its pixel -- while one set runs the tile epilogue (bias, activation, statistics, stores), the
+  // other already drains the chunks of the next tile.  With shared tiles the MMAs of a short-K tile (9 k-blocks on 64 -> 64)
+  // waited for a free accumulator while the previous tile was being stored (profiles/conv_layers_r2_experiments.md).
+#ifdef DVC_NO_PINGPONG  // A/B builds only
+  constexpr bool PP = false;
+#else
+  constexpr bool PP = (BN <= 128);
+#endif
+  constexpr int CPT = PP ? BN : BN / 2;  // output channels per epilogue thread
+  constexpr int EPI_T = PP ? 128 : 256;  // threads that work on one tile's epilogue together
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -143,7 +155,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc::tma_prefetch_desc(&tmWh);
     tc::tma_prefetch_desc(&tmWl);
     for (int i = 0; i < NFULL; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
-    for (int i = 0; i < C::NBUF; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], 8 * CL);  // pair: both epilogues
+    for (int i = 0; i < C::NBUF; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], (PP ? 4 : 8) * CL);  // pair: both epilogues
     tc::fence_barrier_init();
   }
   if (CL == 2) tc::cluster_sync_all();  // both CTAs are resident before the pair allocation
@@ -380,10 +392,19 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     // ================= epilogue: 8 warps; thread = one output pixel x BN/2 channels =================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;       // which half of the tile's channels
-    const int etid = threadIdx.x - 128;     // 0..255
+    const int wset = (warp - 4) >> 2;       // warp set 0 / 1
+    const int half = PP ? 0 : wset;         // shared tiles: which half of the tile's channels
+    const int etid = PP ? ((threadIdx.x - 128) & 127) : (threadIdx.x - 128);  // index among the EPI_T threads of this tile
+    float* s_stat_set = s_stat + (PP ? wset * 8 * BN : 0);                  // ping-pong: one statistics area per set
+    int tile_seq = 0;                       // tiles this CTA has walked so far (ping-pong: set = tile_seq & 1 owns it)
     const int img = p.Hp * p.Wp;
     uint32_t chunk_id = 0;
+    auto epi_sync = [&]() {  // barrier among the threads that share this tile (named barrier 1, or 1 + set in ping-pong mode)
+      if constexpr (PP)
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + wset) : "memory");
+      else
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
     // device-side scales (conv -> ReLU -> conv chains on fp16 planes, dvc_internal.cuh: DynOut)
     float oscale = p.out_scale, yscale = 1.f, amax = 0.f;
     if constexpr (F16) {
@@ -391,11 +412,15 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       if (p.dyn.h16) {
         const int e_out = dyn_out_exponent(p.dyn);
         yscale = exp2_int(e_out);
-        if (etid == 0 && blockIdx.x == 0) p.dyn.cell_out->e = e_out;
+        if (threadIdx.x == 128 && blockIdx.x == 0) p.dyn.cell_out->e = e_out;
       }
     }
-    for (int work = item0; work < total_work; work += item_stride) {
+    for (int work = item0; work < total_work; work += item_stride, ++tile_seq) {
       const int sp = work / total_items, item = work - sp * total_items;
+      if (PP && (tile_seq & 1) != wset) {  // the other set's tile: only keep the chunk counter in step
+        chunk_id += (uint32_t)(nchunks * (sp + 1) / S - nchunks * sp / S);
+        continue;
+      }
       const int mg = item / n_tiles, nt = item - mg * n_tiles;
       const int m0 = (p.mt0 + mg * CL + crank) * BM, n0 = nt * BN;
       const int tile_id = (mg * CL + crank) * n_tiles + nt;
@@ -428,7 +453,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p.flags + tile_id) : "memory");
           } while (got != want);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        epi_sync();
 #pragma unroll
         for (int j = 0; j < CPT; ++j) tot[j] = __ldcg(wsp + (size_t)j * BM);
       }
@@ -487,7 +512,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 #pragma unroll
         for (int j = 0; j < CPT; ++j) __stcg(wsp + (size_t)j * BM, tot[j]);
         __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        epi_sync();
         if (etid == 0) {
           const int v = p.epoch * 16 + sp + 1;
           asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.flags + tile_id), "r"(v) : "memory");
@@ -595,8 +620,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                   qv[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
                 }
               }
-              s_stat[(q * 2 + 0) * BN + half * CPT + c * 32 + lane] = sv[0];
-              s_stat[(q * 2 + 1) * BN + half * CPT + c * 32 + lane] = qv[0];
+              s_stat_set[(q * 2 + 0) * BN + half * CPT + c * 32 + lane] = sv[0];
+              s_stat_set[(q * 2 + 1) * BN + half * CPT + c * 32 + lane] = qv[0];
             } else if (valid) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -608,33 +633,35 @@ __global__ void __launch_bounds__(NTHREADS, 1)
         }
       }
       if (BN == 128 && p.fin_out) {  // the two channel halves of a pixel meet in shared memory
-        float2* s_fin = reinterpret_cast<float2*>(s_stat);
-        if (half == 1) s_fin[q * 32 + lane] = make_float2(fs0, fs1);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float2* s_fin = reinterpret_cast<float2*>(s_stat_set);
+        if (!PP) {  // shared tile: the two channel halves of a pixel meet in shared memory
+          if (half == 1) s_fin[q * 32 + lane] = make_float2(fs0, fs1);
+          epi_sync();
+        }
         if (half == 0 && valid) {
-          const float2 o2 = s_fin[q * 32 + lane];
+          const float2 o2 = PP ? make_float2(0.f, 0.f) : s_fin[q * 32 + lane];
           const size_t hw = (size_t)p.H * p.W, po = (size_t)yo * p.W + xo;
           p.fin_out[((size_t)b * 2 + 0) * hw + po] = tanhf(fs0 + o2.x + __ldg(p.fin_b + 0)) * 128.f;
           p.fin_out[((size_t)b * 2 + 1) * hw + po] = tanhf(fs1 + o2.y + __ldg(p.fin_b + 1)) * 128.f;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        epi_sync();
       }
       if (p.stats) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        epi_sync();
         if (uniform_img) {
-          for (int i = etid; i < BN; i += 256) {
+          for (int i = etid; i < BN; i += EPI_T) {
             const int chn = n0 + i;
             if (chn < p.Cout) {
-              const double s4 = (double)s_stat[0 * BN + i] + (double)s_stat[2 * BN + i] + (double)s_stat[4 * BN + i] +
-                                (double)s_stat[6 * BN + i];
-              const double q4 = (double)s_stat[1 * BN + i] + (double)s_stat[3 * BN + i] + (double)s_stat[5 * BN + i] +
-                                (double)s_stat[7 * BN + i];
+              const double s4 = (double)s_stat_set[0 * BN + i] + (double)s_stat_set[2 * BN + i] + (double)s_stat_set[4 * BN + i] +
+                                (double)s_stat_set[6 * BN + i];
+              const double q4 = (double)s_stat_set[1 * BN + i] + (double)s_stat_set[3 * BN + i] + (double)s_stat_set[5 * BN + i] +
+                                (double)s_stat_set[7 * BN + i];
               atomicAdd(&p.stats[((size_t)b_first * p.Cout + chn) * 2 + 0], s4);
               atomicAdd(&p.stats[((size_t)b_first * p.Cout + chn) * 2 + 1], q4);
             }
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        epi_sync();
       }
     }
     if (F16 && p.dyn.cell_out) warp_amax_commit(amax, p.dyn.cell_out);

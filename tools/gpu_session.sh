@@ -30,6 +30,10 @@ for S in $STEPS; do
                 echo "  sanitizer $tool rc=$? $(grep -c 'ERROR SUMMARY' $O/${TAG}_sanitize_$tool.log)" >> $O/${TAG}_steps.log; tail -n 3 $O/${TAG}_sanitize_$tool.log >> $O/${TAG}_steps.log
               done ;;
     layersx)  DVC_LAYER_EXPERIMENTS=1 timeout 300 python tools/conv_layer_bench.py > $O/${TAG}_layersx.log 2>&1 ;;
+    ab_alt)   L=deep-exemplar-based-video-colorization_b200/lib; cp $L/libdvc.so /tmp/libdvc_main.so; cp $L/libdvc_alt.so $L/libdvc.so;
+              timeout 300 python tools/conv_layer_bench.py > $O/${TAG}_layers_alt.log 2>&1;
+              timeout 300 python bench.py --steps 20 --warmup 5 --cpu-sample 0 --clip-frames 0 --sustain-s 0 > $O/${TAG}_bench_alt.json 2> $O/${TAG}_bench_alt.err;
+              cp /tmp/libdvc_main.so $L/libdvc.so ;;
     multi)    timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -s -p no:cacheprovider > $O/${TAG}_multi.log 2>&1 ;;
     *) echo "unknown step $S" ;;
   esac
