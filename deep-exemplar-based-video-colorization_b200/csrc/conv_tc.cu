@@ -122,9 +122,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING);
   uint64_t* full = bars;          // RS: [A_STAGES] activation tiles, then [B_STAGES] weight tiles
   uint64_t* empty = bars + NFULL;
-  uint64_t* tfull = bars + 2 * NFULL;                  // [NBUF]
-  uint64_t* tempty = bars + 2 * NFULL + C::NBUF;       // [NBUF]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NFULL + 2 * C::NBUF);
+  // "accumulator full" barriers: ping-pong tiles have one bank per warp set -- a set only ever waits on the phases of its OWN
+  // tiles (an mbarrier wait carries one parity bit: a waiter that skipped phases could not tell them apart)
+  constexpr int NTF = (PP ? 2 : 1) * C::NBUF;
+  uint64_t* tfull = bars + 2 * NFULL;                  // [NTF]
+  uint64_t* tempty = bars + 2 * NFULL + NTF;           // [NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NFULL + NTF + C::NBUF);
   float* s_stat = reinterpret_cast<float*>(smem + RING + 512);  // [4 lane quarters][2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,7 +158,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     tc::tma_prefetch_desc(&tmWh);
     tc::tma_prefetch_desc(&tmWl);
     for (int i = 0; i < NFULL; ++i) tc::mbar_init(&full[i], 1), tc::mbar_init(&empty[i], 1);
-    for (int i = 0; i < C::NBUF; ++i) tc::mbar_init(&tfull[i], 1), tc::mbar_init(&tempty[i], (PP ? 4 : 8) * CL);  // pair: both epilogues
+    for (int i = 0; i < NTF; ++i) tc::mbar_init(&tfull[i], 1);
+    for (int i = 0; i < C::NBUF; ++i) tc::mbar_init(&tempty[i], (PP ? 4 : 8) * CL);  // pair: both epilogues
     tc::fence_barrier_init();
   }
   if (CL == 2) tc::cluster_sync_all();  // both CTAs are resident before the pair allocation
@@ -273,7 +277,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       const uint32_t ringB = tc::smem_u32(smem + R::A_STAGES * R::A_STAGE);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0, chunk_id = 0;
-      for (int work = item0; work < total_work; work += item_stride) {
+      int tseq = 0;
+      for (int work = item0; work < total_work; work += item_stride, ++tseq) {
+        uint64_t* tfull_set = tfull + (PP ? (tseq & 1) * C::NBUF : 0);  // the bank of the warp set that owns this tile
         for (int ch = 0; ch < nchunks; ++ch, ++chunk_id) {
           const int buf = chunk_id % C::NBUF;
           tc::mbar_wait(&tempty[buf], ((chunk_id / C::NBUF) & 1) ^ 1);
@@ -316,11 +322,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
               if (CL == 1) {
                 tc::umma_commit(&empty[R::A_STAGES + bs]);
                 if (tx == ntx - 1) tc::umma_commit(&empty[as]);
-                if (k == k_end - 1) tc::umma_commit(&tfull[buf]);
+                if (k == k_end - 1) tc::umma_commit(&tfull_set[buf]);
               } else {
                 tc::umma_commit_pair_mc(&empty[R::A_STAGES + bs], 3);
                 if (tx == ntx - 1) tc::umma_commit_pair_mc(&empty[as], 3);
-                if (k == k_end - 1) tc::umma_commit_pair_mc(&tfull[buf], 3);
+                if (k == k_end - 1) tc::umma_commit_pair_mc(&tfull_set[buf], 3);
               }
             }
             __syncwarp();
@@ -333,7 +339,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk_id = 0;  // global chunk counter: TMEM buffer = chunk_id % NBUF
-      for (int work = item0; work < total_work; work += item_stride) {
+      int tseq = 0;
+      for (int work = item0; work < total_work; work += item_stride, ++tseq) {
+        uint64_t* tfull_set = tfull + (PP ? (tseq & 1) * C::NBUF : 0);  // the bank of the warp set that owns this tile
         const int sp = work / total_items;
         for (int ch = nchunks * sp / S; ch < nchunks * (sp + 1) / S; ++ch, ++chunk_id) {
           const int buf = chunk_id % C::NBUF;
@@ -375,10 +383,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
               }
               if (CL == 1) {
                 tc::umma_commit(&empty[stage]);
-                if (k == k_end - 1) tc::umma_commit(&tfull[buf]);
+                if (k == k_end - 1) tc::umma_commit(&tfull_set[buf]);
               } else {  // release the stage to both producers, hand the accumulator to both epilogues
                 tc::umma_commit_pair_mc(&empty[stage], 3);
-                if (k == k_end - 1) tc::umma_commit_pair_mc(&tfull[buf], 3);
+                if (k == k_end - 1) tc::umma_commit_pair_mc(&tfull_set[buf], 3);
               }
             }
             __syncwarp();
@@ -397,6 +405,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     const int etid = PP ? ((threadIdx.x - 128) & 127) : (threadIdx.x - 128);  // index among the EPI_T threads of this tile
     float* s_stat_set = s_stat + (PP ? wset * 8 * BN : 0);                  // ping-pong: one statistics area per set
     int tile_seq = 0;                       // tiles this CTA has walked so far (ping-pong: set = tile_seq & 1 owns it)
+    uint32_t par_mask = 0;                  // ping-pong: bit b = parity of this set's next "full" phase of accumulator b
     const int img = p.Hp * p.Wp;
     uint32_t chunk_id = 0;
     auto epi_sync = [&]() {  // barrier among the threads that share this tile (named barrier 1, or 1 + set in ping-pong mode)
@@ -465,7 +474,12 @@ __global__ void __launch_bounds__(NTHREADS, 1)
       for (int ch = ch_lo; ch < ch_hi; ++ch, ++chunk_id) {
         const int buf = chunk_id % C::NBUF;
         const uint32_t acc_phase = (chunk_id / C::NBUF) & 1;
-        tc::mbar_wait(&tfull[buf], acc_phase);
+        if constexpr (PP) {  // my own bank: the parity of my next phase on this buffer
+          tc::mbar_wait(&tfull[wset * C::NBUF + buf], (par_mask >> buf) & 1u);
+          par_mask ^= 1u << buf;
+        } else {
+          tc::mbar_wait(&tfull[buf], acc_phase);
+        }
         tc::tc_fence_after();
         const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * CPT;
         if constexpr (CPT >= 64) {

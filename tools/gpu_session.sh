@@ -34,6 +34,8 @@ for S in $STEPS; do
               timeout 300 python tools/conv_layer_bench.py > $O/${TAG}_layers_alt.log 2>&1;
               timeout 300 python bench.py --steps 20 --warmup 5 --cpu-sample 0 --clip-frames 0 --sustain-s 0 > $O/${TAG}_bench_alt.json 2> $O/${TAG}_bench_alt.err;
               cp /tmp/libdvc_main.so $L/libdvc.so ;;
+    convtest) timeout 240 python -m pytest tests/test_gpu_conv_layers.py -m gpu -q -x -p no:cacheprovider > $O/${TAG}_convtest.log 2>&1 ;;
+    testq)    timeout 420 python -m pytest tests -m gpu -q --maxfail=10 -p no:cacheprovider > $O/${TAG}_test.log 2>&1 ;;
     multi)    timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -s -p no:cacheprovider > $O/${TAG}_multi.log 2>&1 ;;
     *) echo "unknown step $S" ;;
   esac
