@@ -39,7 +39,9 @@ for S in $STEPS; do
     multi)    timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -s -p no:cacheprovider > $O/${TAG}_multi.log 2>&1 ;;
     *) echo "unknown step $S" ;;
   esac
-  echo "step $S rc=$? $(( $(date +%s) - T0 ))s" >> $O/${TAG}_steps.log
+  RC=$?
+  echo "step $S rc=$RC $(( $(date +%s) - T0 ))s" >> $O/${TAG}_steps.log
+  if [ "$S" = "convtest" ] && [ $RC -ne 0 ]; then echo "convtest failed: stopping the session" >> $O/${TAG}_steps.log; break; fi
 done
 tail -n 12 $O/${TAG}_steps.log
 for f in $O/${TAG}_test.log $O/${TAG}_testfast.log; do [ -f $f ] && tail -n 6 $f; done
