@@ -17,7 +17,8 @@
 //   warp 1       TMEM owner + MMA issuer (leader CTA of a pair): 4 k-steps x 3 tcgen05.mma per k-block (the two cross
 //                terms of the whole k-block first, hi.hi last) into a ring of 512/BN TMEM accumulators;
 //                tcgen05.commit (multicast in a pair) frees the stage / publishes the chunk.
-//   warps 4..11  epilogue: every chunk (kc k-blocks) the TMEM partial sum is added to fp32 register totals with
+//   warps 4..11  epilogue (256- / 64-channel tiles: the two warps of a lane quarter split the channels; 128-channel tile: the two
+//                warp sets take alternate tiles): every chunk (kc k-blocks) the TMEM partial sum is added to fp32 register totals with
 //                round-to-nearest adds (the TMEM accumulator truncates); then + bias, + skip addend, activation,
 //                InstanceNorm statistics (transpose-reduce in registers -> one double atomic per channel and tile),
 //                measured max |y|, masked store of the interior pixel as fp32 / tf32 planes / fp16 planes -- or the
@@ -52,7 +53,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int NBUF = 512 / BN;  // TMEM accumulators (2 / 4 / 8): deeper ring hides the flush round trip
   // + barriers + statistics [4][2][BN] (one area per warp set on the narrow, ping-pong tiles)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + 8 * BN * 4 * (BN <= 128 ? 2 : 1);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + 8 * BN * 4 * (BN == 128 ? 2 : 1);
 };
 
 // Row-shared taps (RS): the three horizontal taps of a 3x3 row (two of a 2x2 phase-convolution row) read pixel rows
@@ -74,7 +75,7 @@ struct CfgRS {
   static constexpr int B_STAGES = (BN == 256) ? (CL == 2 ? 4 : 2) : (BN == 128 ? (CL == 2 ? 6 : 3) : (CL == 2 ? 9 : 6));
   static constexpr int RING_BYTES = A_STAGES * A_STAGE + B_STAGES * B_STAGE;
   static constexpr int NBUF = 512 / BN;
-  static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 512 + 8 * BN * 4 * (BN <= 128 ? 2 : 1);
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 512 + 8 * BN * 4 * (BN == 128 ? 2 : 1);
 };
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -105,14 +106,14 @@ __global__ void __launch_bounds__(NTHREADS, 1)
   constexpr int KE = F16 ? KBY / 2 : KBY / 4;  // K elements per stage
   constexpr uint32_t IDESC = tc::umma_idesc(F16 ? 0u : 2u, BM * CL, BN);
   // Epilogue organisation.  256-channel tile: the two warps of a TMEM lane quarter split the tile's channels (CPT = 128 each).
-  // Narrow tiles (PP, "ping-pong"): the two warp SETS (one warp per lane quarter each) take ALTERNATE tiles, every thread
-  // owning all BN channels of its pixel -- while one set runs the tile epilogue (bias, activation, statistics, stores), the
-  // other already drains the chunks of the next tile.  With shared tiles the MMAs of a short-K tile (9 k-blocks on 64 -> 64)
-  // waited for a free accumulator while the previous tile was being stored (profiles/conv_layers_r2_experiments.md).
+  // 128-channel tile (PP, "ping-pong"): the two warp SETS (one warp per lane quarter each) take ALTERNATE tiles, every thread
+  // owning all 128 channels of its pixel -- while one set runs the tile epilogue (bias, activation, statistics, stores), the
+  // other already drains the chunks of the next tile.  With shared tiles the MMAs waited for a free accumulator while the
+  // previous tile was being stored (profiles/conv_layers_r2_experiments.md): +9 ... +20 % on the 128-channel layers.
 #ifdef DVC_NO_PINGPONG  // A/B builds only
   constexpr bool PP = false;
 #else
-  constexpr bool PP = (BN <= 128);
+  constexpr bool PP = (BN == 128);  // (the 64-channel tile is 11 % slower this way: four warps drain a chunk slower than its MMAs)
 #endif
   constexpr int CPT = PP ? BN : BN / 2;  // output channels per epilogue thread
   constexpr int EPI_T = PP ? 128 : 256;  // threads that work on one tile's epilogue together
