@@ -36,6 +36,28 @@ for S in $STEPS; do
               cp /tmp/libdvc_main.so $L/libdvc.so ;;
     convtest) timeout 240 python -m pytest tests/test_gpu_conv_layers.py -m gpu -q -x -p no:cacheprovider > $O/${TAG}_convtest.log 2>&1 ;;
     testq)    timeout 420 python -m pytest tests -m gpu -q --maxfail=10 -p no:cacheprovider > $O/${TAG}_test.log 2>&1 ;;
+    folder)   timeout 300 python - > $O/${TAG}_folder.log 2>&1 <<'PYEOF'
+import os, subprocess, sys
+import numpy as np
+from PIL import Image
+rng = np.random.default_rng(0)
+os.makedirs("/tmp/clip", exist_ok=True)
+base = np.kron(rng.integers(0, 255, (54, 96, 3)), np.ones((10, 10, 1))).astype(np.uint8)      # 540 x 960 blocky content
+for t in range(4):
+    img = np.clip(np.roll(base, 7 * t, axis=1).astype(np.int32) + rng.integers(-12, 13, base.shape), 0, 255).astype(np.uint8)
+    Image.fromarray(img).convert("L").convert("RGB").save(f"/tmp/clip/frame{t:03d}.png")       # grayscale frames
+Image.fromarray(base).save("/tmp/ref.png")
+rc = subprocess.call([sys.executable, "tools/colorize_folder.py", "--clip", "/tmp/clip", "--ref", "/tmp/ref.png", "--out", "/tmp/out",
+                      "--seeded-weights"])
+outs = sorted(os.listdir("/tmp/out")) if os.path.isdir("/tmp/out") else []
+print("rc", rc, "outputs", outs)
+for o in outs:
+    a = np.asarray(Image.open(os.path.join("/tmp/out", o)))
+    print(o, a.shape, a.dtype, float(a.mean()), float(a.std()))
+assert rc == 0 and len(outs) == 4
+PYEOF
+              ;;
+    smoke)    timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1 ;;
     multi)    timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -s -p no:cacheprovider > $O/${TAG}_multi.log 2>&1 ;;
     *) echo "unknown step $S" ;;
   esac
