@@ -14,8 +14,12 @@ Timed legs (own arm):
   value : frames already resident in HBM, dvc_colorize_clip on device buffers, CUDA events.
   e2e   : the public clip API (dvc_colorize_clip) on PINNED HOST buffers: every step copies one L frame
           host->device and the predicted ab device->host inside the timed region.
-  roofline : the correlation kernel (K7) timed with CUDA events on its own stream inside the steps;
-          achieved = 2*N*N*(256+3) FLOP / mean launch time against the measured dense-bf16 peak.
+  roofline : every tensor-core convolution launch (the dominant kernel, ~78 % of the device time) and, as roofline_corr, the
+          correlation (K7), timed with CUDA events on the launching stream in a single-stream pass inside this run;
+          achieved = algorithmic FLOPs / launch time against the measured dense-bf16 peak (burst: the pass lasts ~35 ms).
+  sustained : the `value` leg back to back for >= 2.5 s with its own clock samples.
+  clip64 : BASELINE configs[2], 64 frames in N segments, exemplar prologue + NCCL broadcast inside the wall clock.
+  rank_checksum : every rank colourises one common frame; the bit patterns must agree across ranks or the run aborts.
   cpu_baseline : the CPU oracle (port of the reference's PyTorch forward) on the host cores, bounded sample.
 Reference arm (--impl reference): the same CPU oracle timed step by step on rank 0 (the reference is pure
 Python/PyTorch and cannot travel to the GPU box; oracle/dvc_oracle.py is bit-exact with it, tests/golden/PIN_REPORT.txt).
