@@ -58,6 +58,7 @@ assert rc == 0 and len(outs) == 4
 PYEOF
               ;;
     smoke)    timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1 ;;
+    rsq)      DVC_TEST_ROWSHARE=1 timeout 150 python -m pytest tests/test_gpu_rowshare.py -m gpu -q -x -p no:cacheprovider > $O/${TAG}_rsq.log 2>&1 ;;
     multi)    timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -s -p no:cacheprovider > $O/${TAG}_multi.log 2>&1 ;;
     *) echo "unknown step $S" ;;
   esac
